@@ -1,0 +1,35 @@
+"""ORACLE -- CPU restatement of the reference's fairness-guidance path.
+
+THIS PACKAGE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import it.  Nothing under ``finetune-fair-diffusion_b200/`` imports it,
+and the product path raises if its CUDA library is missing.
+
+What it restates (paths relative to the reference root; E1 = exp-1-debias-gender/1-main-debias.py,
+E3 = exp-3-debias-gender-race/1-main-debias.py, E4 = exp-4-debias-gender-race-age/1-main-debias.py):
+
+    boxes.py    get_largest_face_app E1:1292-1304, expand_bbox E1:238-265
+    crop.py     crop_face E1:267-290, Resize(224) E1:1905
+    head.py     get_face_gender E1:1355-1401, get_face_gender_race E3:1387-1457,
+                get_face_gender_race_age E4:1378-1475
+    assign.py   generate_dynamic_targets E1:1403-1447, ..._gender_race E3:1459-1569,
+                ..._gender_race_age E4:1477-1615, thresholding E3:2022-2025
+    hooks.py    apply_grad_hook_face E1:1584-1617 / E3:1751-1784 / E4:1823-1867,
+                gen_dynamic_weights E1:1619-1633 / E3:1787-1803 / E4:1870-1895
+    loss.py     loss assembly E1:1912-1933 / E3:2114-2147 / E4:2238-2283
+    emd.py      exact transport solve standing in for POT ``ot.emd`` (not installed)
+
+Parity pinning: the reference has no tests or golden vectors.  The
+oracle is pinned instead against outputs of the reference's OWN function bodies, executed
+in this container by ``tests/golden/make_golden.py`` (which reads the reference sources at
+generation time, compiles the named function definitions unmodified, and stores their
+outputs under ``tests/golden/``).  Two third-party pieces could not be executed and are
+substituted there and here, which is the residual unpinned part:
+  * ``ot.emd`` (POT 0.9.3, absent): an exact LP solve (scipy HiGHS / linear_sum_assignment);
+    identical to any exact solver on tie-free costs.
+  * ``torchvision.transforms.Resize``: torchvision 0.16.2 resized tensors WITHOUT antialias
+    by default; the installed 0.26 defaults to antialias=True, so ``antialias=False`` is
+    passed explicitly.
+"""
+
+from . import boxes, crop, head, assign, hooks, loss, emd  # noqa: F401

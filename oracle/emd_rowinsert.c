@@ -1,0 +1,173 @@
+/*
+ * ORACLE (test infrastructure, not product code).
+ *
+ * Exact solver for the transport problem the reference hands to POT:
+ *     T = ot.emd(a = ones(N), b, M)          exp-3-debias-gender-race/1-main-debias.py:1528-1532
+ *                                            exp-4-debias-gender-race-age/1-main-debias.py:1562-1566
+ * with unit supplies and integer demands b (sum b = N).  POT 0.9.3 (environment.yml:172) is
+ * not installed in this image, so its network simplex cannot be run; with unit supplies and
+ * integer demands every vertex of the transport polytope is a 0/1 matrix, so on tie-free
+ * costs ANY exact method returns the same plan.  This file is one such method, chosen to
+ * be algorithmically unrelated to the CUDA solver (which rebalances a greedy start):
+ *
+ *   row insertion -- items enter one at a time; each entry runs Bellman-Ford over the
+ *   (K+1)-node graph {new item} U {classes}, where the edge class k -> class l costs
+ *   min over items currently in k of (M[i,l] - M[i,k]); the shortest path to any class
+ *   with spare capacity is applied.  Per-pair binary heaps with lazy deletion keep the
+ *   edge minima.
+ *
+ * Checked in tests/test_oracle_emd.py against scipy.optimize.linear_sum_assignment and
+ * scipy.optimize.linprog(highs) (identical plans and objective).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#define KMAX 32
+
+typedef struct { double key; int32_t item; int32_t stamp; } hent_t;
+typedef struct { hent_t* e; int n, cap; } heap_t;
+
+static int ent_less(const hent_t* a, const hent_t* b) {
+    if (a->key != b->key) return a->key < b->key;
+    return a->item < b->item;
+}
+static void heap_push(heap_t* h, hent_t x) {
+    if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 64; h->e = (hent_t*)realloc(h->e, sizeof(hent_t) * h->cap); }
+    int i = h->n++;
+    while (i > 0) {
+        int p = (i - 1) >> 1;
+        if (!ent_less(&x, &h->e[p])) break;
+        h->e[i] = h->e[p]; i = p;
+    }
+    h->e[i] = x;
+}
+static void heap_pop(heap_t* h) {
+    hent_t x = h->e[--h->n];
+    int i = 0;
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= h->n) break;
+        if (c + 1 < h->n && ent_less(&h->e[c + 1], &h->e[c])) c++;
+        if (!ent_less(&h->e[c], &x)) break;
+        h->e[i] = h->e[c]; i = c;
+    }
+    if (h->n > 0) h->e[i] = x;
+}
+
+/* Returns 0 on success; assign[i] in [0,K).  M is row-major [N,K]. */
+int fg_oracle_emd_unit(const double* M, const int64_t* b, int N, int K, int32_t* assign, double* objective) {
+    if (K > KMAX || K <= 0 || N < 0) return -1;
+    int64_t tot = 0;
+    for (int j = 0; j < K; j++) { if (b[j] < 0) return -2; tot += b[j]; }
+    if (tot != N) return -3;
+
+    heap_t* heaps = (heap_t*)calloc((size_t)K * K, sizeof(heap_t));
+    int32_t* stamp = (int32_t*)calloc((size_t)(N > 0 ? N : 1), sizeof(int32_t));
+    int64_t count[KMAX];
+    memset(count, 0, sizeof(count));
+    for (int i = 0; i < N; i++) assign[i] = -1;
+
+    for (int i = 0; i < N; i++) {
+        const double* Mi = M + (size_t)i * K;
+        /* edge minima between classes, from valid heap tops */
+        double w[KMAX][KMAX]; int32_t wi[KMAX][KMAX];
+        for (int k = 0; k < K; k++)
+            for (int l = 0; l < K; l++) {
+                w[k][l] = INFINITY; wi[k][l] = -1;
+                if (k == l) continue;
+                heap_t* h = &heaps[k * K + l];
+                while (h->n > 0) {
+                    hent_t* t = &h->e[0];
+                    if (assign[t->item] == k && stamp[t->item] == t->stamp) { w[k][l] = t->key; wi[k][l] = t->item; break; }
+                    heap_pop(h);
+                }
+            }
+        /* Bellman-Ford from the new item */
+        double dist[KMAX]; int pred[KMAX];
+        for (int j = 0; j < K; j++) { dist[j] = Mi[j]; pred[j] = -1; }
+        for (int round = 0; round < K; round++) {
+            int changed = 0;
+            for (int k = 0; k < K; k++) {
+                if (!(dist[k] < INFINITY)) continue;
+                for (int l = 0; l < K; l++) {
+                    if (wi[k][l] < 0) continue;
+                    double d = dist[k] + w[k][l];
+                    if (d < dist[l]) { dist[l] = d; pred[l] = k; changed = 1; }
+                }
+            }
+            if (!changed) break;
+        }
+        int best = -1;
+        for (int j = 0; j < K; j++)
+            if (count[j] < b[j] && (best < 0 || dist[j] < dist[best])) best = j;
+        if (best < 0) { free(stamp); for (int q = 0; q < K * K; q++) free(heaps[q].e); free(heaps); return -4; }
+        /* unwind the path: ... -> pred[best] -> best */
+        int path[KMAX + 1]; int plen = 0;
+        for (int j = best; j >= 0; j = pred[j]) { path[plen++] = j; if (plen > K) break; }
+        /* path[plen-1] is the class the new item enters; moves cascade towards path[0] */
+        int32_t movers[KMAX + 1];
+        for (int q = plen - 1; q >= 1; q--) movers[q] = wi[path[q]][path[q - 1]];
+        for (int q = 1; q <= plen - 1; q++) {
+            int32_t it = movers[q]; int to = path[q - 1];
+            assign[it] = to; stamp[it]++;
+            const double* Mt = M + (size_t)it * K;
+            for (int m = 0; m < K; m++) if (m != to) {
+                hent_t x = { Mt[m] - Mt[to], it, stamp[it] };
+                heap_push(&heaps[to * K + m], x);
+            }
+        }
+        {
+            int to = path[plen - 1];
+            assign[i] = to; stamp[i]++;
+            for (int m = 0; m < K; m++) if (m != to) {
+                hent_t x = { Mi[m] - Mi[to], i, stamp[i] };
+                heap_push(&heaps[to * K + m], x);
+            }
+        }
+        count[best]++;
+    }
+    if (objective) {
+        double s = 0.0;
+        for (int i = 0; i < N; i++) s += M[(size_t)i * K + assign[i]];
+        *objective = s;
+    }
+    free(stamp);
+    for (int q = 0; q < K * K; q++) free(heaps[q].e);
+    free(heaps);
+    return 0;
+}
+
+/*
+ * Cost matrix in a fixed IEEE op order (no FMA contraction: compile with -ffp-contract=off),
+ * restating exp-3 .../1-main-debias.py:1509-1526 (K=8) and exp-4 .../1-main-debias.py:1533-1560
+ * (K=16, age term with the doubled young-probability residual for the "old" target).
+ * np.linalg.norm(x)**2 is sqrt(sum sq) squared; the product keeps that sqrt-then-square.
+ * The age residual (E4:1547-1557) is formed from numpy SCALARS of the probs dtype and Python
+ * ints, so it is rounded in the probs dtype (float32, or float16 in an fp16 run) before
+ * math.sqrt widens it; the caller computes that part in the right dtype and passes
+ * ``ca`` [N,2] = cost_age for the (young, old) target as doubles.
+ * Class index: K=8  -> g*4+r ; K=16 -> g*8+r*2+a.
+ */
+static double sq(double x) { return x * x; }
+void fg_oracle_cost_matrix(const double* pg, const double* pr, const double* ca, int N, int K, double* M) {
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < K; j++) {
+            int g, r, a = 0;
+            if (K == 8) { g = j >> 2; r = j & 3; } else { g = j >> 3; r = (j >> 1) & 3; a = j & 1; }
+            double ng = sqrt(sq(pg[2 * i] - (g == 0 ? 1.0 : 0.0)) + sq(pg[2 * i + 1] - (g == 1 ? 1.0 : 0.0)));
+            double s4 = 0.0;
+            for (int q = 0; q < 4; q++) s4 = s4 + sq(pr[4 * i + q] - (r == q ? 1.0 : 0.0));
+            double nr = sqrt(s4);
+            double c = ng * ng + nr * nr;
+            if (K == 16) {
+                double cav = ca[2 * i + a];
+                c = c + cav * cav;
+            }
+            M[(size_t)i * K + j] = sqrt(c);
+        }
+    }
+}
