@@ -1,0 +1,313 @@
+"""Python call surface of the guidance path, mirroring exp-*/1-main-debias.py.
+
+Same names, argument order, return tuples and -1 sentinels as the reference closures
+(SURVEY.md section 8b).  The reference's closures capture ``gender_classifier`` /
+``accelerator`` from ``main``; here they are explicit keyword arguments, and ``bind()`` builds
+closures with the reference's exact signatures.  Every function below runs hand-written sm_100a
+kernels through the C ABI (include/fairguide.h); there is no CPU or eager-PyTorch fallback.
+
+E1 = exp-1-debias-gender/1-main-debias.py, E3 = exp-3-debias-gender-race/1-main-debias.py,
+E4 = exp-4-debias-gender-race-age/1-main-debias.py.
+"""
+import types
+
+import torch
+
+from . import autograd as ag
+from . import dist as fdist
+from . import ops
+
+_HEADS = {
+    # kind: (col_start, width)
+    "gender": ([40], [2]),                    # E1:1370  logits.view(B,-1,2)[:,20,:]
+    "gender_race": ([0, 2], [2, 4]),          # E3:1404-1407
+    "gender_race_age": ([0, 2, 6], [2, 4, 2]),  # E4:1398-1403
+}
+
+
+# ----------------------------------------------------------------------------- boxes / crop
+def expand_bbox(bbox, expand_coef, target_ratio):
+    """E1:238-265.  ``bbox`` = 4 numbers (numpy float32 in the reference) -> list of 4 ints."""
+    b = torch.as_tensor([[float(v) for v in bbox]], dtype=torch.float32, device="cuda").view(1, 1, 4)
+    _, out = ops.select_expand_boxes(b, None, 1 << 30, expand_coef, target_ratio)
+    return [int(v) for v in out[0].tolist()]
+
+
+def select_and_expand(boxes, counts, dim_max, expand_coef=0.5, target_ratio=1, fill_value=-1):
+    """Batched get_largest_face_app (E1:1292-1304) + expand_bbox for [n,F,4] candidate boxes.
+    -> (face_indicators bool [n], face_bboxs int64 [n,4])."""
+    return ops.select_expand_boxes(boxes, counts, dim_max, expand_coef, target_ratio, fill_value)
+
+
+def crop_face(img_tensor, bbox_new, target_size, fill_value):
+    """E1:267-290.  ``img_tensor`` [3,H,W] (may require grad) -> [3,h,w]."""
+    box = torch.as_tensor([list(bbox_new)], dtype=torch.int64, device=img_tensor.device)
+    chips = ag.CropResize.apply(img_tensor.unsqueeze(0), box, None, None, None,
+                                (int(target_size[0]), int(target_size[1])), None, float(fill_value))
+    return chips[0]
+
+
+def crop_faces(images, face_bboxs, face_indicators, size_face=224, fill_value=-1):
+    """The crop part of get_face_app's per-image loop (E1:1324-1345) in one launch:
+    chips [n,3,size,size]; rows without a face are all ``fill_value`` (E1:1328-1332)."""
+    return ag.CropResize.apply(images, face_bboxs, face_indicators, None, None, (size_face, size_face), None, float(fill_value))
+
+
+def resize_small(images, img_size_small=224):
+    """transforms.Resize(img_size_small) on a square batch (E1:1860, E1:1905)."""
+    return ag.CropResize.apply(images, None, None, None, None, None, (img_size_small, img_size_small), -1.0)
+
+
+def crop_and_resize(images, face_bboxs, face_indicators, region=None, scale=None, size_face=224, img_size_small=224,
+                    fill_value=-1):
+    """Fused entry point the reference lacks: (face_chips, images_small) from one pass over the
+    images; in the backward the gradient arriving through ``images_small`` is scaled by ``scale``
+    inside ``region`` (= apply_grad_hook_face placed before the resize, E3:2106-2107) while the
+    gradient arriving through ``face_chips`` is not (crops are taken before the hook, E3:2103)."""
+    return ag.CropResize.apply(images, face_bboxs, face_indicators, region, scale, (size_face, size_face),
+                               (img_size_small, img_size_small), float(fill_value))
+
+
+# ----------------------------------------------------------------------------- classifier heads
+def _split_classifier(classifier):
+    """torchvision MobileNetV3: (backbone callable -> pooled [m,960], W1, b1, W2, b2); else None."""
+    feats = getattr(classifier, "features", None)
+    cls = getattr(classifier, "classifier", None)
+    if feats is None or cls is None or len(cls) != 4:
+        return None
+    l1, l2 = cls[0], cls[3]
+    if not isinstance(l1, torch.nn.Linear) or not isinstance(l2, torch.nn.Linear):
+        return None
+    if classifier.training:
+        raise RuntimeError("fairguide head implements the eval-mode classifier (Dropout = identity)")
+
+    def backbone(x):
+        return torch.flatten(classifier.avgpool(feats(x)), 1)
+
+    return backbone, l1.weight, l1.bias, l2.weight, l2.bias
+
+
+def classifier_logits(classifier, chips):
+    """logits [m,k_head] float32 with autograd back to ``chips``: backbone in torch/cuDNN, the dense
+    head (classifier[0..3]) in our kernel.  A classifier without the MobileNetV3 layout is treated
+    as an opaque logits producer."""
+    parts = _split_classifier(classifier)
+    if parts is None:
+        return classifier(chips).float()
+    backbone, w1, b1, w2, b2 = parts
+    return ag.Head.apply(backbone(chips), w1, b1, w2, b2)
+
+
+class _HeadAttributes(torch.autograd.Function):
+    """slice -> softmax -> argmax -> scatter(fill) for every attribute, one launch."""
+
+    @staticmethod
+    def forward(ctx, logits, src_row, selector, n, kind, fill, dtype):
+        cs, ws = _HEADS[kind]
+        preds, probs, louts = ops.head_attributes(logits, src_row, selector, n, cs, ws, fill, dtype)
+        ctx.kind, ctx.shape = kind, tuple(logits.shape)
+        ctx.save_for_backward(src_row, selector, *probs)
+        out = []
+        for a in range(len(ws)):
+            out += [preds[a], probs[a], louts[a]]
+        ctx.mark_non_differentiable(*[preds[a] for a in range(len(ws))])
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        cs, ws = _HEADS[ctx.kind]
+        src_row, selector, *probs = ctx.saved_tensors
+        g_full = torch.zeros(ctx.shape, dtype=torch.float32, device=grads[0].device if grads[0] is not None else probs[0].device)
+        rows = torch.arange(g_full.shape[0], device=g_full.device) if src_row is None else None
+        for a, (c, w) in enumerate(zip(cs, ws)):
+            g_probs, g_logits = grads[3 * a + 1], grads[3 * a + 2]
+            sel = slice(None) if selector is None else selector
+            acc = None
+            if g_logits is not None:
+                acc = g_logits[sel].float()
+            if g_probs is not None:
+                p, gp = probs[a][sel].float(), g_probs[sel].float()
+                term = p * (gp - (gp * p).sum(-1, keepdim=True))
+                acc = term if acc is None else acc + term
+            if acc is not None:
+                g_full[:, c:c + w] += acc
+        return g_full, None, None, None, None, None, None
+
+
+def _heads(kind, classifier, face_chips, selector, fill_value):
+    n_attr = len(_HEADS[kind][1])
+    chips = face_chips[selector] if selector is not None else face_chips
+    n = selector.shape[0] if selector is not None else face_chips.shape[0]
+    if chips.shape[0] == 0:
+        logits = torch.zeros((0, _HEADS[kind][0][-1] + _HEADS[kind][1][-1]), dtype=torch.float32, device=face_chips.device)
+    else:
+        logits = classifier_logits(classifier, chips)
+    if selector is not None:
+        src_row = (torch.cumsum(selector.to(torch.int32), 0, dtype=torch.int32) - 1)
+        out = _HeadAttributes.apply(logits, src_row, selector, n, kind, float(fill_value), face_chips.dtype)
+    else:
+        out = _HeadAttributes.apply(logits, None, None, n, kind, float(fill_value), face_chips.dtype)
+    if kind == "gender_race_age" and selector is None:
+        return out[:6]          # the reference returns only gender+race here (E4:1475); kept
+    return out[:3 * n_attr]
+
+
+def get_face_gender(face_chips, selector=None, fill_value=-1, *, gender_classifier):
+    """E1:1355-1401 -> (preds_gender, probs_gender, logits_gender)."""
+    return _heads("gender", gender_classifier, face_chips, selector, fill_value)
+
+
+def get_face_gender_race(face_chips, selector=None, fill_value=-1, *, gender_race_classifier):
+    """E3:1387-1457 -> (preds_g, probs_g, logits_g, preds_r, probs_r, logits_r)."""
+    return _heads("gender_race", gender_race_classifier, face_chips, selector, fill_value)
+
+
+def get_face_gender_race_age(face_chips, selector=None, fill_value=-1, *, gender_race_age_classifier):
+    """E4:1378-1475 -> 9-tuple (6-tuple when selector is None, like the reference)."""
+    return _heads("gender_race_age", gender_race_age_classifier, face_chips, selector, fill_value)
+
+
+# ----------------------------------------------------------------------------- assignment
+@torch.no_grad()
+def generate_dynamic_targets(probs, target_ratio=0.5, w_uncertainty=False, *, uncertainty_threshold=None):
+    """E1:1403-1447.  ``uncertainty_threshold`` (not in the reference signature) fuses E1:1835."""
+    thr = -1.0 if uncertainty_threshold is None else float(uncertainty_threshold)
+    t, u = ops.assign_rank_binom(probs, target_ratio, thr, w_uncertainty)
+    return (t, u) if w_uncertainty else t
+
+
+@torch.no_grad()
+def _mc_targets(probs, w_uncertainty, num_samples_per_device, rand_tensors, num_valid, uncertainty_threshold, group,
+                return_counts=False):
+    pg, pr = probs[0], probs[1]
+    pa = probs[2] if len(probs) == 3 else None
+    K = 16 if pa is not None else 8
+    n_all = pg.shape[0]
+    if num_valid is None:
+        # the reference has the same device->host read: ``if idxs_2_rank.sum() == 0`` (E3:1476)
+        num_valid = int(((pg != -1).all(dim=-1) * (pr != -1).all(dim=-1)).sum().item())
+    S = num_samples_per_device
+    ws = ops.OtWorkspace(n_all, K, S, pg.device)
+    if num_valid > 0 and rand_tensors is None:
+        # same call order, shape, dtype and device as E3:1491-1492 / E4:1503-1505
+        rand_tensors = tuple(torch.rand([S, num_valid], dtype=pg.dtype, device=pg.device) for _ in range(len(probs)))
+    counts = ops.ot_plan_counts(pg, pr, pa, rand_tensors or (), num_valid, ws)
+    if num_valid > 0:
+        fdist.all_reduce_counts(counts, group)            # E3:1535, on exact int32 counts
+    thr = -1.0 if uncertainty_threshold is None else float(uncertainty_threshold)
+    ts, us = ops.ot_targets(counts, pg, pr, num_valid, ws, thr, w_uncertainty)
+    out = []
+    for a in range(len(ts)):
+        out.append(ts[a])
+        if w_uncertainty:
+            out.append(us[a])
+    if return_counts:
+        return tuple(out), counts, ws
+    return tuple(out)
+
+
+def generate_dynamic_targets_gender_race(probs_gender, probs_race, w_uncertainty=False, num_samples_per_device=100, *,
+                                         rand_tensors=None, num_valid=None, uncertainty_threshold=None, group=None):
+    """E3:1459-1569 -> (t_g, u_g, t_r, u_r) or (t_g, t_r).  Keyword-only extras: ``rand_tensors`` =
+    the (gender, race) uniform draws [S,N] (default: torch.rand in the reference's order);
+    ``num_valid`` = N if the caller already knows it (skips one device->host read);
+    ``uncertainty_threshold`` fuses E3:2022-2023; ``group`` = process group of the all-reduce."""
+    return _mc_targets((probs_gender, probs_race), w_uncertainty, num_samples_per_device, rand_tensors, num_valid,
+                       uncertainty_threshold, group)
+
+
+def generate_dynamic_targets_gender_race_age(probs_gender, probs_race, probs_age, w_uncertainty=False,
+                                             num_samples_per_device=100, *, rand_tensors=None, num_valid=None,
+                                             uncertainty_threshold=None, group=None):
+    """E4:1477-1615 -> (t_g, u_g, t_r, u_r, t_a, u_a) or targets only."""
+    return _mc_targets((probs_gender, probs_race, probs_age), w_uncertainty, num_samples_per_device, rand_tensors,
+                       num_valid, uncertainty_threshold, group)
+
+
+def threshold_and_slice(targets_all, uncertainty_all, uncertainty_threshold, n_local, local_process_index):
+    """E3:2022-2025: ``targets_all[uncertainty_all > thr] = -1`` (in place) and this rank's rows."""
+    targets_all[uncertainty_all > uncertainty_threshold] = -1
+    return targets_all[n_local * local_process_index:n_local * (local_process_index + 1)]
+
+
+# ----------------------------------------------------------------------------- hooks / weights
+def _as_lists(args, n_attr):
+    """(t0, pred0, prob0, t1, pred1, prob1, ...) -> ([t...], [pred...])"""
+    return [args[3 * a] for a in range(n_attr)], [args[3 * a + 1] for a in range(n_attr)]
+
+
+def _hook(images, face_bboxs, face_bboxs_ori, targets, preds_ori, factors, e1_rule):
+    H, W = images.shape[-2:]
+    region, scale, _ = ops.guidance_factors(None, face_bboxs, face_bboxs_ori, targets, preds_ori, factors, None, e1_rule,
+                                            H, W, want_region=True, want_weights=False)
+    return ag.RegionScale.apply(images, region, scale)
+
+
+def _weights(face_indicators, targets, preds_ori, factors, e1_rule, dtype):
+    _, _, w = ops.guidance_factors(face_indicators, None, None, targets, preds_ori, None, factors, e1_rule, 0, 0,
+                                   want_region=False, want_weights=True)
+    return w.to(dtype)
+
+
+def apply_grad_hook_face(images, face_bboxs, face_bboxs_ori, *attr_args, **factors):
+    """E1:1584-1617 (``factor=``), E3:1751-1784 (``factor_gender=, factor_race=``), E4:1823-1867
+    (``+ factor_age=``).  ``attr_args`` = (targets, preds_ori, probs_ori) per attribute, in the
+    reference's positional order.  Forward is the identity; backward scales the face region."""
+    n_attr = len(attr_args) // 3
+    targets, preds = _as_lists(attr_args, n_attr)
+    if n_attr == 1:
+        return _hook(images, face_bboxs, face_bboxs_ori, targets, preds, [factors.get("factor", 0.1)], True)
+    if n_attr == 2:
+        f = [factors.get("factor_gender", 0.3), factors.get("factor_race", 0.3)]
+    else:
+        f = [factors.get("factor_gender", 0.2), factors.get("factor_race", 0.3), factors.get("factor_age", 0.3)]
+    return _hook(images, face_bboxs, face_bboxs_ori, targets, preds, f, False)
+
+
+def gen_dynamic_weights(face_indicators, *attr_args, **factors):
+    """E1:1619-1633 (``factor=``), E3:1787-1803, E4:1870-1895 -> weights [b] in probs_ori's dtype."""
+    n_attr = len(attr_args) // 3
+    targets, preds = _as_lists(attr_args, n_attr)
+    dtype = attr_args[2].dtype
+    if n_attr == 1:
+        return _weights(face_indicators, targets, preds, [factors.get("factor", 0.2)], True, dtype)
+    if n_attr == 2:
+        f = [factors.get("factor_gender", 0.3), factors.get("factor_race", 0.6)]
+    else:
+        f = [factors.get("factor_gender", 0.2), factors.get("factor_race", 0.6), factors.get("factor_age", 0.6)]
+    return _weights(face_indicators, targets, preds, f, False, dtype)
+
+
+# ----------------------------------------------------------------------------- loss
+def fairness_ce_loss(logits, targets, face_indicators, fill_value=-1):
+    """The three reference lines ``loss = ones*(-1); idx = (face * (targets != -1)).nonzero();
+    loss[idx] = CE_loss(logits[idx], targets[idx])`` (E3:2114-2117) without the host sync."""
+    return ag.FairCE.apply(logits, targets, face_indicators, float(fill_value))
+
+
+# ----------------------------------------------------------------------------- collectives
+def customized_all_gather(tensor, accelerator=None, return_tensor_other_processes=False):
+    """E1:222-235 with one all_gather_into_tensor instead of a list gather + cat."""
+    return fdist.customized_all_gather(tensor, accelerator, return_tensor_other_processes)
+
+
+def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_classifier=None, accelerator=None):
+    """Closures with the reference's exact signatures (the reference captures these objects from
+    ``main``): ``fg = bind(gender_race_classifier=clf, accelerator=acc); fg.get_face_gender_race(chips, sel)``."""
+    ns = types.SimpleNamespace(
+        expand_bbox=expand_bbox, crop_face=crop_face, crop_faces=crop_faces, resize_small=resize_small,
+        crop_and_resize=crop_and_resize, select_and_expand=select_and_expand,
+        generate_dynamic_targets=generate_dynamic_targets,
+        generate_dynamic_targets_gender_race=generate_dynamic_targets_gender_race,
+        generate_dynamic_targets_gender_race_age=generate_dynamic_targets_gender_race_age,
+        apply_grad_hook_face=apply_grad_hook_face, gen_dynamic_weights=gen_dynamic_weights,
+        fairness_ce_loss=fairness_ce_loss, threshold_and_slice=threshold_and_slice)
+    ns.get_face_gender = lambda face_chips, selector=None, fill_value=-1: get_face_gender(
+        face_chips, selector, fill_value, gender_classifier=gender_classifier)
+    ns.get_face_gender_race = lambda face_chips, selector=None, fill_value=-1: get_face_gender_race(
+        face_chips, selector, fill_value, gender_race_classifier=gender_race_classifier)
+    ns.get_face_gender_race_age = lambda face_chips, selector=None, fill_value=-1: get_face_gender_race_age(
+        face_chips, selector, fill_value, gender_race_age_classifier=gender_race_age_classifier)
+    ns.customized_all_gather = lambda tensor, acc=accelerator, return_tensor_other_processes=False: customized_all_gather(
+        tensor, acc, return_tensor_other_processes)
+    return ns

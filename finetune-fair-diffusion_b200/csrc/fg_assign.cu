@@ -1,0 +1,729 @@
+// Distributional-alignment target assignment on the device.
+//
+//   generate_dynamic_targets                  E1:1403-1447   rank split + binomial-CDF uncertainty
+//   generate_dynamic_targets_gender_race      E3:1459-1569   Monte-Carlo exact transport, K = 8
+//   generate_dynamic_targets_gender_race_age  E4:1477-1615   same, K = 16, 75/25 age target
+//   thresholding                              E1:1835, E3:2022-2023, E4:2129-2131
+//
+// The reference solves, per rank, S = 100 transport problems  ot.emd(ones(N), b_s, M)  that share
+// the cost matrix M [N,K] and differ only in the demand vector b_s (the class histogram of one
+// random draw).  With unit supplies the optimum is a 0/1 matrix, i.e. an assignment of rows to
+// classes with prescribed class sizes.  Exact method used here:
+//
+//   * an assignment that minimises  sum_i (M[i,s(i)] - v[s(i)])  for ANY price vector v is
+//     optimal among all assignments with the same class sizes;
+//   * from such a state, moving one unit from an over-full class to an under-full class along a
+//     SHORTEST path of the K-node class graph (edge k->l costs  min_{i in k} M[i,l]-M[i,k])
+//     keeps optimality for the new class sizes (successive shortest paths);
+//   * so one "base" assignment for the expected demand is computed once (coarse-to-fine over
+//     growing prefixes of the rows, each level warm-started by the previous level's prices), and
+//     every draw only repairs  |b_s - b_base|_1 / 2  units starting from the base.
+//
+// One CTA per problem; the class graph lives in shared memory; edge minima are found with
+// warp-level REDUX reductions on order-preserving 64-bit keys; the shortest-path search
+// (Bellman-Ford over <= 16 nodes) runs in one warp with shuffles.  All cost arithmetic is fp64
+// like POT's; ties resolve to the lowest row index / lowest class index, deterministically.
+#include "fg_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int KP = 16;                 // classes padded to 16
+constexpr int SOLVER_THREADS = 256;
+constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
+constexpr unsigned long long KEY_INF = 0xFFFFFFFFFFFFFFFFull;
+
+enum { ST_NVALID_MISMATCH = 1, ST_NO_PATH = 2, ST_PATH_OVERFLOW = 4, ST_ITER_CAP = 8, ST_BAD_DEMAND = 16 };
+
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+struct OtWs {
+    int* status;        // [4]: status bits, n_valid seen on device, augmentations (base), augmentations (draws)
+    int* idx;           // [n_all] compacted row -> original row
+    int* pos;           // [n_all] original row -> compacted row or -1
+    double* M;          // [n_valid, K]
+    int* hist;          // [S, KP]
+    double* prices;     // [KP]
+    uint8_t* sigma0;    // [n_valid]
+    size_t total;
+};
+
+static OtWs ot_carve(void* base, int n_all, int K, int S) {
+    OtWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += fg_align_up(bytes, 256); return (char*)base + o; };
+    w.status = (int*)take(4 * sizeof(int));
+    w.idx = (int*)take((size_t)n_all * sizeof(int));
+    w.pos = (int*)take((size_t)n_all * sizeof(int));
+    w.M = (double*)take((size_t)n_all * K * sizeof(double));
+    w.hist = (int*)take((size_t)(S > 0 ? S : 1) * KP * sizeof(int));
+    w.prices = (double*)take(KP * sizeof(double));
+    w.sigma0 = (uint8_t*)take((size_t)n_all);
+    w.total = off;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// valid-row compaction: idx / pos, one CTA, ordered
+template <typename T>
+__global__ void __launch_bounds__(1024)
+compact_kernel(const T* __restrict__ pg, const T* __restrict__ pr, int n_all, int n_valid_expected,
+               int* __restrict__ idx, int* __restrict__ pos, int* __restrict__ status) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < n_all; start += 1024) {
+        int i = start + threadIdx.x;
+        bool v = false;
+        if (i < n_all) {
+            v = to_f32(pg[2 * i]) != -1.f && to_f32(pg[2 * i + 1]) != -1.f;
+            for (int q = 0; q < 4; q++) v = v && to_f32(pr[4 * i + q]) != -1.f;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, v);
+        int in_warp = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[warp] = __popc(m);
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+            warp_sums[lane] = s;          // inclusive
+        }
+        __syncthreads();
+        int before = base + (warp ? warp_sums[warp - 1] : 0) + in_warp;
+        if (i < n_all) {
+            pos[i] = v ? before : -1;
+            if (v) idx[before] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        status[1] = base;
+        if (n_valid_expected >= 0 && base != n_valid_expected) atomicOr(&status[0], ST_NVALID_MISMATCH);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost matrix (fixed IEEE op order, identical to oracle/emd_rowinsert.c) + per-draw histograms
+__device__ __forceinline__ double dsq(double x) { return __dmul_rn(x, x); }
+
+template <typename T>
+__device__ __forceinline__ void cost_row(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
+                                         int i, int K, double* __restrict__ out) {
+    double g[2] = {(double)to_f32(pg[2 * i]), (double)to_f32(pg[2 * i + 1])};
+    double r[4];
+    for (int q = 0; q < 4; q++) r[q] = (double)to_f32(pr[4 * i + q]);
+    double ca[2] = {0.0, 0.0};
+    if (K == 16) {
+        double a0 = (double)to_f32(pa[2 * i]), a1 = (double)to_f32(pa[2 * i + 1]);
+        ca[0] = __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(a0, 1.0)), dsq(__dsub_rn(a1, 0.0))));
+        ca[1] = __dsqrt_rn(__dadd_rn(dsq(__dmul_rn(__dsub_rn(a0, 0.0), 2.0)), dsq(__dsub_rn(a1, 1.0))));
+    }
+    for (int j = 0; j < K; j++) {
+        int gi, ri, ai = 0;
+        if (K == 8) { gi = j >> 2; ri = j & 3; } else { gi = j >> 3; ri = (j >> 1) & 3; ai = j & 1; }
+        double ng = __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(g[0], gi == 0 ? 1.0 : 0.0)), dsq(__dsub_rn(g[1], gi == 1 ? 1.0 : 0.0))));
+        double s4 = dsq(__dsub_rn(r[0], ri == 0 ? 1.0 : 0.0));
+        for (int q = 1; q < 4; q++) s4 = __dadd_rn(s4, dsq(__dsub_rn(r[q], ri == q ? 1.0 : 0.0)));
+        double nr = __dsqrt_rn(s4);
+        double c = __dadd_rn(dsq(ng), dsq(nr));
+        if (K == 16) c = __dadd_rn(c, dsq(ca[ai]));
+        out[j] = __dsqrt_rn(c);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
+                 const int* __restrict__ idx, int N, int K, double* __restrict__ M, int cost_blocks,
+                 const T* __restrict__ rg, const T* __restrict__ rr, const T* __restrict__ ra, int S,
+                 int* __restrict__ hist) {
+    if ((int)blockIdx.x < cost_blocks) {
+        int r = blockIdx.x * 256 + threadIdx.x;
+        if (r < N) cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
+        return;
+    }
+    int s = blockIdx.x - cost_blocks;
+    if (s >= S) return;
+    __shared__ int h[KP];
+    if (threadIdx.x < KP) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += 256) {
+        size_t e = (size_t)s * N + j;
+        float ug = to_f32(rg[e]), ur = to_f32(rr[e]);
+        int g = ug > 0.5f ? 1 : 0;                                           // E3:1496
+        int r = 0;                                                            // E3:1498-1501
+        if (ur > 0.25f && ur <= 0.5f) r = 1;
+        if (ur > 0.5f && ur <= 0.75f) r = 2;
+        if (ur > 0.75f) r = 3;
+        int c;
+        if (K == 8) c = g * 4 + r;                                            // E3:1506
+        else { int a = to_f32(ra[e]) > 0.75f ? 1 : 0; c = g * 8 + r * 2 + a; }  // E4:1518, 1523
+        atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < KP) hist[s * KP + threadIdx.x] = h[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// the solver
+struct Demand { int b[KP]; };
+
+struct SolverSmem {
+    double w[KP][KP];
+    int wi[KP][KP];
+    double dist[KP];
+    double price[KP];
+    int pred[KP];
+    int cnt[KP];
+    int b[KP];
+    unsigned long long red_key[SOLVER_WARPS][KP];
+    int red_idx[SOLVER_WARPS][KP];
+    int path[KP + 1];
+    int moved[KP + 1];
+    unsigned need[KP + 1];
+    int path_len;
+    int status;
+};
+
+// Recompute w[k][l], wi[k][l] for the classes l in `mask` by scanning the rows currently in class k.
+__device__ void rescan_class(SolverSmem& sm, const uint8_t* sigma, const double* __restrict__ M, int N, int K,
+                             int k, unsigned mask) {
+    unsigned long long best[KP];
+    int besti[KP];
+#pragma unroll
+    for (int l = 0; l < KP; l++) { best[l] = KEY_INF; besti[l] = 0x7fffffff; }
+    for (int i = threadIdx.x; i < N; i += SOLVER_THREADS) {
+        if (sigma[i] != k) continue;
+        const double* row = M + (size_t)i * K;
+        double mk = row[k];
+#pragma unroll
+        for (int l = 0; l < KP; l++) {
+            if (l < K && ((mask >> l) & 1u)) {
+                unsigned long long key = dkey(__dsub_rn(row[l], mk));
+                if (key < best[l]) { best[l] = key; besti[l] = i; }     // rows visited in increasing order
+            }
+        }
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int l = 0; l < KP; l++) {
+        if (!((mask >> l) & 1u)) continue;                               // block-uniform
+        unsigned hi = (unsigned)(best[l] >> 32);
+        unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        unsigned lo = hi == mhi ? (unsigned)best[l] : 0xffffffffu;
+        unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+        unsigned cand = (hi == mhi && lo == mlo) ? (unsigned)besti[l] : 0x7fffffffu;
+        unsigned mi = __reduce_min_sync(0xffffffffu, cand);
+        if (lane == 0) { sm.red_key[warp][l] = ((unsigned long long)mhi << 32) | mlo; sm.red_idx[warp][l] = (int)mi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < KP && ((mask >> threadIdx.x) & 1u)) {
+        int l = threadIdx.x;
+        unsigned long long bk = KEY_INF; int bi = 0x7fffffff;
+        for (int wq = 0; wq < SOLVER_WARPS; wq++) {
+            unsigned long long kk = sm.red_key[wq][l]; int ii = sm.red_idx[wq][l];
+            if (kk < bk || (kk == bk && ii < bi)) { bk = kk; bi = ii; }
+        }
+        if (bi == 0x7fffffff) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
+        else { sm.w[k][l] = dunkey(bk); sm.wi[k][l] = bi; }
+    }
+    __syncthreads();
+}
+
+// warp 0: shortest path from the over-full classes to the cheapest under-full class
+__device__ void find_path(SolverSmem& sm, int K) {
+    int lane = threadIdx.x & 31;
+    int l = lane & 15, half = lane >> 4;
+    bool surplus = l < K && sm.cnt[l] > sm.b[l];
+    bool deficit = l < K && sm.cnt[l] < sm.b[l];
+    unsigned def_mask = __ballot_sync(0xffffffffu, deficit && half == 0);
+    if (def_mask == 0) { if (lane == 0) sm.path_len = 0; return; }
+    if (half == 0) { sm.dist[l] = surplus ? 0.0 : INFINITY; sm.pred[l] = -1; }
+    __syncwarp();
+    for (int round = 0; round < KP; round++) {
+        double cur = sm.dist[l];
+        double best = cur; int bestk = -1;
+#pragma unroll
+        for (int j = 0; j < KP / 2; j++) {
+            int k = half + 2 * j;
+            double cand = sm.dist[k] + sm.w[k][l];
+            if (k != l && cand < best) { best = cand; bestk = k; }
+        }
+        double ob = __shfl_xor_sync(0xffffffffu, best, 16);
+        int ok = __shfl_xor_sync(0xffffffffu, bestk, 16);
+        if (ob < best || (ob == best && ok >= 0 && (bestk < 0 || ok < bestk))) { best = ob; bestk = ok; }
+        bool improved = bestk >= 0 && best < cur;
+        unsigned any = __ballot_sync(0xffffffffu, improved && half == 0);
+        __syncwarp();
+        if (improved && half == 0) { sm.dist[l] = best; sm.pred[l] = bestk; }
+        __syncwarp();
+        if (!any) break;
+    }
+    // cheapest under-full class (lowest index on ties)
+    unsigned long long key = (deficit && half == 0) ? dkey(sm.dist[l]) : KEY_INF;
+    unsigned hi = (unsigned)(key >> 32);
+    unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
+    unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+    unsigned cand = (hi == mhi && lo == mlo && half == 0 && deficit) ? (unsigned)l : 0xffu;
+    unsigned t = __reduce_min_sync(0xffffffffu, cand);
+    if (lane == 0) {
+        if (t >= (unsigned)K || !(sm.dist[t] < INFINITY)) { sm.status |= ST_NO_PATH; sm.path_len = 0; return; }
+        int rev[KP + 1]; int len = 0; int node = (int)t;
+        while (node >= 0 && len <= KP) { rev[len++] = node; node = sm.pred[node]; }
+        if (len > KP || len < 2) { sm.status |= ST_PATH_OVERFLOW; sm.path_len = 0; return; }
+        for (int q = 0; q < len; q++) sm.path[q] = rev[len - 1 - q];
+        sm.path_len = len;
+    }
+}
+
+// mode 0: start from argmin_l (M[i,l] - price[l]) over rows [0,N)   (price = 0: greedy)
+// mode 1: start from sigma_in (the base assignment)
+// demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x]
+__global__ void __launch_bounds__(SOLVER_THREADS)
+ot_solve_kernel(const double* __restrict__ M, int N, int K, int mode,
+                const uint8_t* __restrict__ sigma_in, double* __restrict__ prices,
+                Demand demand_by_value, const int* __restrict__ hist,
+                uint8_t* __restrict__ sigma_out, int32_t* __restrict__ assign_out,
+                int32_t* __restrict__ counts, int* __restrict__ status, int status_slot) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
+    uint8_t* sigma = dyn_smem + sizeof(SolverSmem);
+    const int tid = threadIdx.x;
+
+    if (tid < KP) {
+        sm.cnt[tid] = 0;
+        sm.b[tid] = hist ? hist[blockIdx.x * KP + tid] : demand_by_value.b[tid];
+        sm.price[tid] = (mode == 0 && prices) ? prices[tid] : 0.0;
+        if (tid >= K) sm.b[tid] = 0;
+    }
+    if (tid == 0) { sm.status = 0; sm.path_len = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        long long tot = 0;
+        for (int k = 0; k < K; k++) { if (sm.b[k] < 0) sm.status |= ST_BAD_DEMAND; tot += sm.b[k]; }
+        if (tot != N) sm.status |= ST_BAD_DEMAND;
+    }
+    // initial assignment
+    for (int i = tid; i < N; i += SOLVER_THREADS) {
+        int s;
+        if (mode == 1) s = sigma_in[i];
+        else {
+            const double* row = M + (size_t)i * K;
+            double bv = INFINITY; s = 0;
+            for (int l = 0; l < K; l++) { double v = __dsub_rn(row[l], sm.price[l]); if (v < bv) { bv = v; s = l; } }
+        }
+        sigma[i] = (uint8_t)s;
+        atomicAdd(&sm.cnt[s], 1);
+    }
+    for (int e = tid; e < KP * KP; e += SOLVER_THREADS) { sm.w[e / KP][e % KP] = INFINITY; sm.wi[e / KP][e % KP] = -1; }
+    __syncthreads();
+    const unsigned all_mask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+    if (!(sm.status & ST_BAD_DEMAND)) {
+        for (int k = 0; k < K; k++) rescan_class(sm, sigma, M, N, K, k, all_mask & ~(1u << k));
+
+        int iters = 0;
+        const int max_iters = N + KP;
+        for (;; iters++) {
+            if (tid < 32) find_path(sm, K);
+            __syncthreads();
+            int len = sm.path_len;
+            if (len == 0) break;
+            if (iters >= max_iters) { if (tid == 0) sm.status |= ST_ITER_CAP; break; }
+            if (tid == 0) {
+                for (int e = 0; e + 1 < len; e++) {
+                    int u = sm.path[e], v = sm.path[e + 1];
+                    int item = sm.wi[u][v];
+                    sm.moved[e] = item;
+                    unsigned need = 0;
+                    for (int l = 0; l < K; l++) if (l != u && sm.wi[u][l] == item) need |= 1u << l;
+                    sm.need[e] = need;
+                }
+                for (int e = 0; e + 1 < len; e++) sigma[sm.moved[e]] = (uint8_t)sm.path[e + 1];
+                sm.cnt[sm.path[0]]--;
+                sm.cnt[sm.path[len - 1]]++;
+            }
+            __syncthreads();
+            for (int e = 0; e + 1 < len; e++) rescan_class(sm, sigma, M, N, K, sm.path[e], sm.need[e]);
+            // rows that arrived in path[e+1]: fold their outgoing differences into the minima
+            if (tid < KP && tid < K) {
+                int l = tid;
+                for (int e = 0; e + 1 < len; e++) {
+                    int v = sm.path[e + 1], item = sm.moved[e];
+                    if (l == v) continue;
+                    const double* row = M + (size_t)item * K;
+                    double d = __dsub_rn(row[l], row[v]);
+                    double cur = sm.w[v][l];
+                    if (d < cur || (d == cur && item < sm.wi[v][l])) { sm.w[v][l] = d; sm.wi[v][l] = item; }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && status) atomicAdd(&status[status_slot], iters);
+    }
+    __syncthreads();
+
+    // outputs
+    if (sigma_out) for (int i = tid; i < N; i += SOLVER_THREADS) sigma_out[i] = sigma[i];
+    if (assign_out) for (int i = tid; i < N; i += SOLVER_THREADS) assign_out[i] = sigma[i];
+    if (counts) for (int i = tid; i < N; i += SOLVER_THREADS) atomicAdd(&counts[(size_t)i * K + sigma[i]], 1);
+    if (mode == 0 && prices) {
+        // feasible prices for the final state: v_l = min(0, min_k v_k + w[k][l]) (difference constraints)
+        if (tid < 32) {
+            int lane = tid;
+            if (lane < KP) sm.dist[lane] = 0.0;
+            __syncwarp();
+            for (int round = 0; round < KP; round++) {
+                double best = lane < KP ? sm.dist[lane] : 0.0;
+                if (lane < K) for (int k = 0; k < K; k++) { double c = sm.dist[k] + sm.w[k][lane]; if (k != lane && c < best) best = c; }
+                bool ch = lane < K && best < sm.dist[lane];
+                unsigned any = __ballot_sync(0xffffffffu, ch);
+                __syncwarp();
+                if (ch) sm.dist[lane] = best;
+                __syncwarp();
+                if (!any) break;
+            }
+            if (lane < KP) prices[lane] = sm.dist[lane];
+        }
+    }
+    if (tid == 0 && sm.status && status) atomicOr(&status[0], sm.status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue E3:1534-1565 (+ thresholding E3:2022-2023): one thread per image row
+template <typename T>
+__device__ __forceinline__ float seq_sum_T(const float* tp, const int* cols, int ncols) {
+    float s = tp[cols[0]];
+    for (int q = 1; q < ncols; q++) s = __fadd_rn(s, tp[cols[q]]);
+    return round_to<T>(s);
+}
+
+template <typename T>
+__global__ void ot_targets_kernel(const int32_t* __restrict__ counts, const int* __restrict__ pos, int n_all, int n_valid, int K,
+                                  float threshold, long long* __restrict__ tg, T* __restrict__ ug, long long* __restrict__ tr,
+                                  T* __restrict__ ur, long long* __restrict__ ta, T* __restrict__ ua) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    int p = n_valid > 0 ? pos[i] : -1;
+    const int n_attr = K == 16 ? 3 : 2;
+    long long* tout[3] = {tg, tr, ta};
+    T* uout[3] = {ug, ur, ua};
+    if (p < 0) {
+        for (int a = 0; a < n_attr; a++) { if (tout[a]) tout[a][i] = -1; if (uout[a]) uout[a][i] = from_f32<T>(-1.f); }
+        return;
+    }
+    // total = target_probs[0,:].sum() in the probs dtype
+    float total = 0.f;
+    for (int j = 0; j < K; j++) total = __fadd_rn(total, round_to<T>((float)counts[j]));
+    total = round_to<T>(total);
+    float tp[KP];
+    for (int j = 0; j < K; j++) tp[j] = round_to<T>(__fdiv_rn(round_to<T>((float)counts[(size_t)p * K + j]), total));
+    float thr = round_to<T>(threshold);
+    for (int a = 0; a < n_attr; a++) {
+        int width = (a == 1) ? 4 : 2;
+        float best = 0.f; int besti = 0;
+        for (int c = 0; c < width; c++) {
+            int cols[8]; int nc = 0;
+            if (K == 8) {
+                if (a == 0) { for (int q = 0; q < 4; q++) cols[nc++] = c * 4 + q; }              // E3:1538-1541
+                else { cols[nc++] = c; cols[nc++] = c + 4; }                                    // E3:1542-1549
+            } else {
+                if (a == 0) { for (int q = 0; q < 8; q++) cols[nc++] = c * 8 + q; }              // E4:1572-1575
+                else if (a == 1) { cols[nc++] = 2 * c; cols[nc++] = 2 * c + 1; cols[nc++] = 2 * c + 8; cols[nc++] = 2 * c + 9; }  // E4:1576-1583
+                else { for (int q = 0; q < 8; q++) cols[nc++] = 2 * q + c; }                     // E4:1584-1589
+            }
+            float m = seq_sum_T<T>(tp, cols, nc);
+            if (c == 0 || m > best) { best = m; besti = c; }
+        }
+        float unc = round_to<T>(__fsub_rn(1.f, best));
+        long long t = besti;
+        if (threshold >= 0.f && unc > thr) t = -1;
+        if (tout[a]) tout[a][i] = t;
+        if (uout[a]) uout[a][i] = from_f32<T>(unc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E1: binomial CDF tables + rank split
+struct RankWs { int* nvalid; double* cdf0; double* cdf1; size_t total; };
+static RankWs rank_carve(void* base, int n_all) {
+    RankWs w; size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += fg_align_up(bytes, 256); return (char*)base + o; };
+    w.nvalid = (int*)take(sizeof(int));
+    w.cdf0 = (double*)take((size_t)(n_all + 1) * sizeof(double));
+    w.cdf1 = (double*)take((size_t)(n_all + 1) * sizeof(double));
+    w.total = off;
+    return w;
+}
+
+__device__ __forceinline__ double binom_pmf(int k, int n, double p) {
+    if (p <= 0.0) return k == 0 ? 1.0 : 0.0;
+    if (p >= 1.0) return k == n ? 1.0 : 0.0;
+    double lg = lgamma((double)n + 1.0) - lgamma((double)k + 1.0) - lgamma((double)(n - k) + 1.0)
+              + (double)k * log(p) + (double)(n - k) * log1p(-p);
+    return exp(lg);
+}
+
+// cdf0[k] = P[Bin(N, ratio) <= k], cdf1[k] = P[Bin(N, 1-ratio) <= k]; one CTA, chunked scan
+template <typename T>
+__global__ void __launch_bounds__(1024)
+binom_tables_kernel(const T* __restrict__ probs, int n_all, double ratio, int* __restrict__ nvalid_out,
+                    double* __restrict__ cdf0, double* __restrict__ cdf1) {
+    __shared__ int s_cnt;
+    __shared__ double warp_tot[2][32];
+    __shared__ double carry[2];
+    if (threadIdx.x == 0) { s_cnt = 0; carry[0] = 0.0; carry[1] = 0.0; }
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < n_all; i += 1024)
+        local += (to_f32(probs[2 * i]) != -1.f && to_f32(probs[2 * i + 1]) != -1.f) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    const int N = s_cnt;
+    if (threadIdx.x == 0) *nvalid_out = N;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start <= N; start += 1024) {
+        int k = start + threadIdx.x;
+        double v[2] = {0.0, 0.0};
+        if (k <= N) { v[0] = binom_pmf(k, N, ratio); v[1] = binom_pmf(k, N, 1.0 - ratio); }
+        for (int q = 0; q < 2; q++) {
+            double s = v[q];
+            for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+            if (lane == 31) warp_tot[q][warp] = s;
+            v[q] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int q = 0; q < 2; q++) {
+                double s = warp_tot[q][lane];
+                for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+                warp_tot[q][lane] = s;
+            }
+        }
+        __syncthreads();
+        if (k <= N) {
+            double c0 = carry[0] + (warp ? warp_tot[0][warp - 1] : 0.0) + v[0];
+            double c1 = carry[1] + (warp ? warp_tot[1][warp - 1] : 0.0) + v[1];
+            cdf0[k] = c0 > 1.0 ? 1.0 : c0;
+            cdf1[k] = c1 > 1.0 ? 1.0 : c1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += warp_tot[0][31]; carry[1] += warp_tot[1][31]; }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+rank_split_kernel(const T* __restrict__ probs, int n_all, double ratio, float threshold,
+                  const int* __restrict__ nvalid, const double* __restrict__ cdf0, const double* __restrict__ cdf1,
+                  long long* __restrict__ targets, T* __restrict__ unc) {
+    __shared__ float tile[256];
+    __shared__ uint8_t tile_ok[256];
+    int i = blockIdx.x * 256 + threadIdx.x;
+    float p0 = 0.f, p1 = 0.f; bool ok = false;
+    if (i < n_all) { p0 = to_f32(probs[2 * i]); p1 = to_f32(probs[2 * i + 1]); ok = p0 != -1.f && p1 != -1.f; }
+    int rank = 0;
+    for (int start = 0; start < n_all; start += 256) {
+        int j = start + threadIdx.x;
+        float q0 = 0.f, q1 = 0.f;
+        if (j < n_all) { q0 = to_f32(probs[2 * j]); q1 = to_f32(probs[2 * j + 1]); }
+        __syncthreads();
+        tile[threadIdx.x] = q1;
+        tile_ok[threadIdx.x] = (j < n_all && q0 != -1.f && q1 != -1.f) ? 1 : 0;
+        __syncthreads();
+        int lim = min(256, n_all - start);
+        for (int t = 0; t < lim; t++) {
+            float q = tile[t];
+            int jj = start + t;
+            rank += (tile_ok[t] && (q < p1 || (q == p1 && jj < i))) ? 1 : 0;
+        }
+    }
+    if (i >= n_all) return;
+    if (!ok) { targets[i] = -1; if (unc) unc[i] = from_f32<T>(-1.f); return; }
+    const int N = *nvalid;
+    // (rank >= N*ratio) is evaluated by torch in float32: int64 tensor vs python float (E1:1420)
+    float cut = (float)((double)N * ratio);
+    long long t = ((float)rank >= cut) ? 1 : 0;
+    double u = t == 1 ? 1.0 - cdf1[rank] : cdf0[rank];                        // E1:1425-1440
+    float uf = round_to<T>((float)u);
+    if (threshold >= 0.f && uf > round_to<T>(threshold)) t = -1;              // E1:1835
+    targets[i] = t;
+    if (unc) unc[i] = from_f32<T>(uf);
+}
+
+static int solver_smem_bytes(int N) { return (int)(sizeof(SolverSmem) + fg_align_up((size_t)N, 16)); }
+
+static int solver_prepare(int N) {
+    int bytes = solver_smem_bytes(N);
+    if (bytes > 227 * 1024) return FG_ERR_LIMIT;
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return FG_OK;
+}
+
+// expected demand for n rows: largest-remainder rounding of n*q
+static void expected_demand(int n, int K, Demand* d) {
+    double q[KP]; double frac[KP]; long long tot = 0;
+    for (int j = 0; j < KP; j++) { q[j] = 0.0; d->b[j] = 0; }
+    if (K == 8) for (int j = 0; j < 8; j++) q[j] = 1.0 / 8.0;
+    else for (int j = 0; j < 16; j++) q[j] = 0.5 * 0.25 * ((j & 1) ? 0.25 : 0.75);
+    for (int j = 0; j < K; j++) { double x = q[j] * n; d->b[j] = (int)floor(x); frac[j] = x - floor(x); tot += d->b[j]; }
+    for (long long r = tot; r < n; r++) {          // fewer than K units remain
+        int best = 0;
+        for (int j = 1; j < K; j++) if (frac[j] > frac[best]) best = j;
+        d->b[best]++; frac[best] = -1.0 - (double)(r - tot);
+    }
+}
+
+// base assignment: coarse-to-fine over growing prefixes, each level warm-started by the previous prices
+static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) {
+    int rc = solver_prepare(N);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(w.prices, 0, KP * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+    int levels[16]; int nl = 0;
+    for (long long L = 256; L < N && nl < 14; L *= 4) levels[nl++] = (int)L;
+    levels[nl++] = N;
+    for (int q = 0; q < nl; q++) {
+        int n = levels[q];
+        Demand d; expected_demand(n, K, &d);
+        bool last = q == nl - 1;
+        ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n), st>>>(M, n, K, 0, nullptr, w.prices, d, nullptr,
+                                                                         last ? w.sigma0 : nullptr, nullptr, nullptr, w.status, 2);
+        FG_LAUNCH_CHECK();
+    }
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" size_t fg_ot_workspace_bytes(int n_all, int K, int S) {
+    if (n_all < 0 || (K != 8 && K != 16) || S < 0) return 0;
+    return ot_carve(nullptr, n_all > 0 ? n_all : 1, K, S).total;
+}
+
+extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_race, const void* probs_age, int n_all,
+                                 const void* rand_gender, const void* rand_race, const void* rand_age, int S, int n_valid,
+                                 int32_t* counts, void* workspace, size_t workspace_bytes, int dtype, void* stream) {
+    const int K = probs_age ? 16 : 8;
+    if (n_all < 0 || S < 0 || n_valid < 0 || n_valid > n_all) return FG_ERR_INVALID_ARG;
+    if (n_all > 0 && (!probs_gender || !probs_race)) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_ot_workspace_bytes(n_all, K, S)) return FG_ERR_WORKSPACE;
+    OtWs w = ot_carve(workspace, n_all > 0 ? n_all : 1, K, S);
+    cudaStream_t st = fg_stream(stream);
+    cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    if (n_all == 0) return FG_OK;
+    FG_DISPATCH_DTYPE(dtype, T,
+        compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status));
+    FG_LAUNCH_CHECK();
+    if (n_valid == 0) return FG_OK;
+    if (!counts || (S > 0 && (!rand_gender || !rand_race || (K == 16 && !rand_age)))) return FG_ERR_INVALID_ARG;
+    e = cudaMemsetAsync(counts, 0, (size_t)n_valid * K * sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    int cost_blocks = (n_valid + 255) / 256;
+    FG_DISPATCH_DTYPE(dtype, T,
+        cost_hist_kernel<T><<<cost_blocks + S, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age,
+            w.idx, n_valid, K, w.M, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist));
+    FG_LAUNCH_CHECK();
+    if (S == 0) return FG_OK;
+    int rc = launch_base(w.M, n_valid, K, w, st);
+    if (rc) return rc;
+    Demand none = {};
+    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid), st>>>(w.M, n_valid, K, 1, w.sigma0, nullptr, none, w.hist,
+                                                                          nullptr, nullptr, counts, w.status, 3);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_ot_targets(const int32_t* counts, const void* probs_gender, const void* probs_race, int n_all, int n_valid,
+                             int K, float threshold,
+                             int64_t* targets_gender, void* unc_gender, int64_t* targets_race, void* unc_race,
+                             int64_t* targets_age, void* unc_age, void* workspace, size_t workspace_bytes,
+                             int dtype, void* stream) {
+    (void)probs_gender; (void)probs_race;
+    if (n_all < 0 || n_valid < 0 || n_valid > n_all || (K != 8 && K != 16)) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_ot_workspace_bytes(n_all, K, 0)) return FG_ERR_WORKSPACE;
+    if (n_valid > 0 && !counts) return FG_ERR_INVALID_ARG;
+    if (n_all == 0) return FG_OK;
+    OtWs w = ot_carve(workspace, n_all, K, 0);
+    FG_DISPATCH_DTYPE(dtype, T,
+        ot_targets_kernel<T><<<(n_all + 127) / 128, 128, 0, fg_stream(stream)>>>(counts, w.pos, n_all, n_valid, K, threshold,
+            (long long*)targets_gender, (T*)unc_gender, (long long*)targets_race, (T*)unc_race, (long long*)targets_age, (T*)unc_age));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* b_host, int32_t* assign,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 0 || (K != 8 && K != 16) || !b_host || (n > 0 && (!M || !assign))) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_ot_workspace_bytes(n, K, 0)) return FG_ERR_WORKSPACE;
+    if (n == 0) return FG_OK;
+    Demand d = {};
+    for (int j = 0; j < K; j++) { if (b_host[j] < 0 || b_host[j] > n) return FG_ERR_INVALID_ARG; d.b[j] = (int)b_host[j]; }
+    OtWs w = ot_carve(workspace, n, K, 0);
+    cudaStream_t st = fg_stream(stream);
+    cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    int rc = launch_base(M, n, K, w, st);      // exercises the coarse-to-fine path as well
+    if (rc) return rc;
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n), st>>>(M, n, K, 1, w.sigma0, nullptr, d, nullptr, nullptr, assign,
+                                                                      nullptr, w.status, 3);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_ot_cost_matrix(const void* probs_gender, const void* probs_race, const void* probs_age, int n_all,
+                                 int n_valid, double* M, void* workspace, size_t workspace_bytes, int dtype, void* stream) {
+    const int K = probs_age ? 16 : 8;
+    if (n_all <= 0 || n_valid < 0 || !probs_gender || !probs_race || !M) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_ot_workspace_bytes(n_all, K, 0)) return FG_ERR_WORKSPACE;
+    OtWs w = ot_carve(workspace, n_all, K, 0);
+    cudaStream_t st = fg_stream(stream);
+    cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    FG_DISPATCH_DTYPE(dtype, T,
+        compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status);
+        if (n_valid > 0) cost_hist_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
+            (const T*)probs_age, w.idx, n_valid, K, M, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" size_t fg_rank_binom_workspace_bytes(int n_all) {
+    return rank_carve(nullptr, n_all > 0 ? n_all : 1).total;
+}
+
+extern "C" int fg_assign_rank_binom(const void* probs, int n_all, double target_ratio, float threshold,
+                                    int64_t* targets, void* uncertainty, void* workspace, size_t workspace_bytes,
+                                    int dtype, void* stream) {
+    if (n_all < 0 || !(target_ratio >= 0.0 && target_ratio <= 1.0)) return FG_ERR_INVALID_ARG;
+    if (n_all == 0) return FG_OK;
+    if (!probs || !targets) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_rank_binom_workspace_bytes(n_all)) return FG_ERR_WORKSPACE;
+    RankWs w = rank_carve(workspace, n_all);
+    cudaStream_t st = fg_stream(stream);
+    FG_DISPATCH_DTYPE(dtype, T,
+        binom_tables_kernel<T><<<1, 1024, 0, st>>>((const T*)probs, n_all, target_ratio, w.nvalid, w.cdf0, w.cdf1);
+        rank_split_kernel<T><<<(n_all + 255) / 256, 256, 0, st>>>((const T*)probs, n_all, target_ratio, threshold, w.nvalid,
+                                                                  w.cdf0, w.cdf1, (long long*)targets, (T*)uncertainty));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}

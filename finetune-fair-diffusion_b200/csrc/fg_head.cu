@@ -1,0 +1,232 @@
+// Attribute-classifier head: torchvision MobileNetV3 `classifier`
+//   Linear(960,1280) -> Hardswish -> Dropout(eval: identity) -> Linear(1280,K_head)
+// (mobilenetv3.py:190-216, instantiated at E1:929-935 / E3:940-941 / E4:931-932), followed by the
+// per-attribute slice / softmax / argmax / scatter of get_face_gender* (E1:1355-1401,
+// E3:1387-1457, E4:1378-1475).
+//
+// Round-1 implementation: the two projections run as shared-memory tiled fp32-accumulate GEMMs on
+// the CUDA cores (exact fp32 for the fp32 configs).  The 960->1280 projection is the only
+// GEMM-shaped work on the path (2.46 MFLOP per face); the tcgen05 version is in fg_head_tc.cu and
+// is selected for bf16/fp16 inputs when FG_HEAD_TC is enabled.
+#include "fg_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float hardswish(float x) {
+    float r = fminf(fmaxf(x + 3.f, 0.f), 6.f);
+    return x * r * (1.f / 6.f);
+}
+__device__ __forceinline__ float hardswish_grad(float x) {
+    if (x < -3.f) return 0.f;
+    if (x <= 3.f) return x * (1.f / 3.f) + 0.5f;
+    return 1.f;
+}
+
+// C[M,N] = A[M,K] * op(B) (+ bias[N]);  A row-major (K contiguous).
+// B_IS_NK: B is [N,K] row-major (a torch Linear weight, y = x W^T); else B is [K,N] row-major.
+// EPI 0: C = acc + bias, stored as TC.   EPI 1: C = (acc) stored as TC (no bias).
+template <typename TA, typename TB, typename TC, bool B_IS_NK, bool HAS_BIAS>
+__global__ void __launch_bounds__(256)
+gemm_tile_kernel(const TA* __restrict__ A, const TB* __restrict__ B, const TB* __restrict__ bias,
+                 TC* __restrict__ C, int M, int N, int K) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 1];
+    __shared__ float Bs[BK][BN + 1];
+    int tid = threadIdx.x;
+    int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads, 4x4 outputs each
+    int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // A tile: 64 rows x 16 k
+        for (int e = tid; e < BM * BK; e += 256) {
+            int r = e / BK, kk = e % BK;
+            int gm = m0 + r, gk = k0 + kk;
+            As[kk][r] = (gm < M && gk < K) ? to_f32(A[(size_t)gm * K + gk]) : 0.f;
+        }
+        if (B_IS_NK) {
+            for (int e = tid; e < BN * BK; e += 256) {
+                int c = e / BK, kk = e % BK;
+                int gn = n0 + c, gk = k0 + kk;
+                Bs[kk][c] = (gn < N && gk < K) ? to_f32(B[(size_t)gn * K + gk]) : 0.f;
+            }
+        } else {
+            for (int e = tid; e < BN * BK; e += 256) {
+                int kk = e / BN, c = e % BN;
+                int gn = n0 + c, gk = k0 + kk;
+                Bs[kk][c] = (gn < N && gk < K) ? to_f32(B[(size_t)gk * N + gn]) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (HAS_BIAS) v += to_f32(bias[gn]);
+            C[(size_t)gm * N + gn] = from_f32<TC>(v);
+        }
+    }
+}
+
+// logits[m, k] = sum_j hardswish(pre[m,j]) * W2[k,j] + b2[k]; one warp per (row, group of 8 outputs)
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_logits_kernel(const T* __restrict__ pre, const T* __restrict__ w2, const T* __restrict__ b2,
+                   float* __restrict__ logits, int m, int d_hid, int k_head) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int groups = (k_head + 7) / 8;
+    int row = warp / groups, grp = warp - row * groups;
+    if (row >= m) return;
+    float acc[8] = {};
+    const T* p = pre + (size_t)row * d_hid;
+    for (int j = lane; j < d_hid; j += 32) {
+        float h = round_to<T>(hardswish(to_f32(p[j])));
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int k = grp * 8 + q;
+            if (k < k_head) acc[q] = fmaf(h, to_f32(w2[(size_t)k * d_hid + j]), acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        float v = acc[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        int k = grp * 8 + q;
+        if (lane == 0 && k < k_head) logits[(size_t)row * k_head + k] = v + to_f32(b2[k]);
+    }
+}
+
+// g_pre[m,j] = hardswish'(pre[m,j]) * sum_k g_logits[m,k] * W2[k,j]
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_hidden_kernel(const float* __restrict__ g_logits, const T* __restrict__ pre, const T* __restrict__ w2,
+                       float* __restrict__ g_pre, int m, int d_hid, int k_head) {
+    extern __shared__ float gl[];            // [k_head] for this row
+    int row = blockIdx.x;
+    for (int k = threadIdx.x; k < k_head; k += blockDim.x) gl[k] = g_logits[(size_t)row * k_head + k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < d_hid; j += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < k_head; k++) s = fmaf(gl[k], to_f32(w2[(size_t)k * d_hid + j]), s);
+        g_pre[(size_t)row * d_hid + j] = s * hardswish_grad(to_f32(pre[(size_t)row * d_hid + j]));
+    }
+}
+
+// per image: slice -> softmax -> argmax -> scatter (or fill)
+template <typename T>
+__global__ void head_attr_kernel(const float* __restrict__ logits, int m, int k_head,
+                                 const int32_t* __restrict__ src_row, const uint8_t* __restrict__ selector,
+                                 int n, int n_attr, int c0, int c1, int c2, int w0, int w1, int w2, float fill,
+                                 long long* __restrict__ preds, T* __restrict__ probs, T* __restrict__ logits_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool sel = !selector || selector[i];
+    int row = src_row ? src_row[i] : i;
+    if (row < 0 || row >= m) sel = false;
+    const int cs[3] = {c0, c1, c2}, ws[3] = {w0, w1, w2};
+    size_t off = 0;
+    for (int a = 0; a < n_attr; a++) {
+        int w = ws[a];
+        T* po = probs ? probs + off + (size_t)i * w : nullptr;
+        T* lo = logits_out ? logits_out + off + (size_t)i * w : nullptr;
+        if (!sel) {
+            if (preds) preds[(size_t)a * n + i] = (long long)fill;
+            for (int q = 0; q < w; q++) { if (po) po[q] = from_f32<T>(fill); if (lo) lo[q] = from_f32<T>(fill); }
+        } else {
+            const float* lg = logits + (size_t)row * k_head + cs[a];
+            float mx = -INFINITY;
+            for (int q = 0; q < w; q++) mx = fmaxf(mx, round_to<T>(lg[q]));
+            float den = 0.f;
+            for (int q = 0; q < w; q++) den += expf(round_to<T>(lg[q]) - mx);
+            int best = 0; float bestp = -1.f;
+            for (int q = 0; q < w; q++) {
+                float p = round_to<T>(expf(round_to<T>(lg[q]) - mx) / den);
+                if (p > bestp) { bestp = p; best = q; }          // first maximum, like torch.max
+                if (po) po[q] = from_f32<T>(p);
+                if (lo) lo[q] = from_f32<T>(lg[q]);
+            }
+            if (preds) preds[(size_t)a * n + i] = best;
+        }
+        off += (size_t)n * w;
+    }
+}
+
+}  // namespace
+
+extern "C" size_t fg_head_workspace_bytes(int m, int d_in, int d_hid, int k_head, int dtype) {
+    (void)d_in; (void)k_head; (void)dtype;
+    return fg_align_up((size_t)(m > 0 ? m : 1) * d_hid * sizeof(float), 256);
+}
+
+extern "C" int fg_head_fwd(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2,
+                           int m, int d_in, int d_hid, int k_head, void* hidden_pre, float* logits,
+                           void* workspace, size_t workspace_bytes, int dtype, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (m < 0 || d_in <= 0 || d_hid <= 0 || k_head <= 0) return FG_ERR_INVALID_ARG;
+    if (!pooled || !w1 || !b1 || !w2 || !b2 || !hidden_pre || !logits) return FG_ERR_INVALID_ARG;
+    if (m == 0) return FG_OK;
+    dim3 grid((d_hid + 63) / 64, (m + 63) / 64);
+    int groups = (k_head + 7) / 8;
+    long long warps = (long long)m * groups;
+    FG_DISPATCH_DTYPE(dtype, T,
+        gemm_tile_kernel<T, T, T, true, true><<<grid, 256, 0, fg_stream(stream)>>>(
+            (const T*)pooled, (const T*)w1, (const T*)b1, (T*)hidden_pre, m, d_hid, d_in);
+        head_logits_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, fg_stream(stream)>>>(
+            (const T*)hidden_pre, (const T*)w2, (const T*)b2, logits, m, d_hid, k_head));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_head_bwd(const float* g_logits, const void* hidden_pre, const void* w1, const void* w2,
+                           int m, int d_in, int d_hid, int k_head, void* g_pooled,
+                           void* workspace, size_t workspace_bytes, int dtype, void* stream) {
+    if (m < 0 || d_in <= 0 || d_hid <= 0 || k_head <= 0) return FG_ERR_INVALID_ARG;
+    if (!g_logits || !hidden_pre || !w1 || !w2 || !g_pooled) return FG_ERR_INVALID_ARG;
+    if (m == 0) return FG_OK;
+    if (!workspace || workspace_bytes < fg_head_workspace_bytes(m, d_in, d_hid, k_head, dtype)) return FG_ERR_WORKSPACE;
+    float* g_pre = (float*)workspace;
+    dim3 grid((d_in + 63) / 64, (m + 63) / 64);
+    FG_DISPATCH_DTYPE(dtype, T,
+        head_bwd_hidden_kernel<T><<<m, 256, k_head * sizeof(float), fg_stream(stream)>>>(
+            g_logits, (const T*)hidden_pre, (const T*)w2, g_pre, m, d_hid, k_head);
+        gemm_tile_kernel<float, T, T, false, false><<<grid, 256, 0, fg_stream(stream)>>>(
+            g_pre, (const T*)w1, nullptr, (T*)g_pooled, m, d_in, d_hid));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_head_attributes(const float* logits, int m, int k_head, const int32_t* src_row, const uint8_t* selector,
+                                  int n, int n_attr, const int32_t* col_start, const int32_t* width, float fill,
+                                  int64_t* preds, void* probs, void* logits_out, int dtype, void* stream) {
+    if (n < 0 || m < 0 || n_attr < 1 || n_attr > 3 || !col_start || !width || (!logits && m > 0)) return FG_ERR_INVALID_ARG;
+    int c[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+    for (int a = 0; a < n_attr; a++) {
+        c[a] = col_start[a]; w[a] = width[a];
+        if (w[a] <= 0 || w[a] > 64 || c[a] < 0 || c[a] + w[a] > k_head) return FG_ERR_INVALID_ARG;
+    }
+    if (n == 0) return FG_OK;
+    FG_DISPATCH_DTYPE(dtype, T,
+        head_attr_kernel<T><<<(n + 127) / 128, 128, 0, fg_stream(stream)>>>(
+            logits, m, k_head, src_row, selector, n, n_attr, c[0], c[1], c[2], w[0], w[1], w[2], fill,
+            (long long*)preds, (T*)probs, (T*)logits_out));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}

@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and the
+current CUDA stream, raise on a non-zero return code.  No arithmetic happens here."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"fairguide: unsupported dtype {t.dtype}") from None
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fairguide ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+def _u8(t):
+    if t is None:
+        return None
+    return (t.to(torch.uint8) if t.dtype != torch.bool else t.view(torch.uint8)).contiguous()
+
+
+def _farr(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def _iarr(vals):
+    return (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+# ------------------------------------------------------------------ boxes
+def select_expand_boxes(boxes, counts, dim_max, expand_coef=0.5, target_ratio=1.0, fill=-1):
+    """boxes [n,F,4] float32, counts [n] int32|None -> (indicators bool [n], boxes int64 [n,4])."""
+    _cuda(boxes, counts)
+    boxes = boxes.to(torch.float32).contiguous()
+    n, F = boxes.shape[0], boxes.shape[1]
+    counts = None if counts is None else counts.to(torch.int32).contiguous()
+    out = torch.empty((n, 4), dtype=torch.int64, device=boxes.device)
+    ind = torch.empty((n,), dtype=torch.uint8, device=boxes.device)
+    check(_lib.lib().fg_select_expand_boxes(_p(boxes), _p(counts), n, F, int(dim_max), float(expand_coef),
+                                            float(target_ratio), int(fill), _p(out), _p(ind), _stream()),
+          "fg_select_expand_boxes")
+    return ind.view(torch.bool), out
+
+
+# ------------------------------------------------------------------ crop / resize
+def crop_resize_fwd(images, boxes, indicators, chip_hw, small_hw, fill_value=-1.0):
+    """images [n,C,H,W]; returns (chips|None, small|None)."""
+    _cuda(images, boxes, indicators)
+    images = images.contiguous()
+    n, C, H, W = images.shape
+    chips = small = None
+    ch = cw = sh = sw = 0
+    if chip_hw is not None:
+        ch, cw = chip_hw
+        chips = torch.empty((n, C, ch, cw), dtype=images.dtype, device=images.device)
+        boxes = boxes.to(torch.int64).contiguous()
+    if small_hw is not None:
+        sh, sw = small_hw
+        small = torch.empty((n, C, sh, sw), dtype=images.dtype, device=images.device)
+    ind = _u8(indicators)
+    check(_lib.lib().fg_crop_resize_fwd(_p(images), n, C, H, W, _p(boxes) if chips is not None else None, _p(ind),
+                                        _p(chips), ch, cw, _p(small), sh, sw, float(fill_value), _dt(images), _stream()),
+          "fg_crop_resize_fwd")
+    return chips, small
+
+
+def image_grad(g_chips, g_small, boxes, indicators, region, scale, image_shape, dtype, device):
+    n, C, H, W = image_shape
+    _cuda(g_chips, g_small, boxes, indicators, region, scale)
+    g_chips, g_small = _c(g_chips), _c(g_small)
+    ch = cw = sh = sw = 0
+    if g_chips is not None:
+        ch, cw = g_chips.shape[-2:]
+        boxes = boxes.to(torch.int64).contiguous()
+    if g_small is not None:
+        sh, sw = g_small.shape[-2:]
+    out = torch.empty((n, C, H, W), dtype=dtype, device=device)
+    ind = _u8(indicators)
+    check(_lib.lib().fg_image_grad(_p(g_chips), _p(g_small), _p(boxes) if g_chips is not None else None, _p(ind),
+                                   _p(region), _p(scale), _p(out), n, C, H, W, ch, cw, sh, sw, _DT[dtype], _stream()),
+          "fg_image_grad")
+    return out
+
+
+def region_scale(g, region, scale):
+    _cuda(g, region, scale)
+    g = g.contiguous()
+    n, C, H, W = g.shape
+    out = torch.empty_like(g)
+    check(_lib.lib().fg_region_scale(_p(g), _p(region), _p(scale), _p(out), n, C, H, W, _dt(g), _stream()), "fg_region_scale")
+    return out
+
+
+def guidance_factors(face_indicators, bbox, bbox_ori, targets, preds_ori, hook_factors, weight_factors, e1_rule, H, W,
+                     want_region=True, want_weights=True):
+    """targets / preds_ori: lists (1..3) of int64 [n].  Returns (region int32 [n,4], scale f32 [n], weights f32 [n])."""
+    n_attr = len(targets)
+    dev = targets[0].device
+    n = targets[0].shape[0]
+    _cuda(face_indicators, bbox, bbox_ori, *targets, *preds_ori)
+    t = [x.to(torch.int64).contiguous() for x in targets] + [None] * (3 - n_attr)
+    p = [x.to(torch.int64).contiguous() for x in preds_ori] + [None] * (3 - n_attr)
+    region = scale = weights = None
+    if want_region:
+        region = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        scale = torch.empty((n,), dtype=torch.float32, device=dev)
+        bbox = bbox.to(torch.int64).contiguous()
+        bbox_ori = bbox_ori.to(torch.int64).contiguous()
+    if want_weights:
+        weights = torch.empty((n,), dtype=torch.float32, device=dev)
+    face = _u8(face_indicators)
+    hf = _farr(hook_factors) if hook_factors is not None else None
+    wf = _farr(weight_factors) if weight_factors is not None else None
+    check(_lib.lib().fg_guidance_factors(_p(face), _p(bbox) if want_region else None, _p(bbox_ori) if want_region else None,
+                                         _p(t[0]), _p(t[1]), _p(t[2]), _p(p[0]), _p(p[1]), _p(p[2]),
+                                         hf, wf, n_attr, 1 if e1_rule else 0, n, H, W, _p(region), _p(scale), _p(weights), _stream()),
+          "fg_guidance_factors")
+    return region, scale, weights
+
+
+# ------------------------------------------------------------------ head
+def head_fwd(pooled, w1, b1, w2, b2):
+    _cuda(pooled, w1, b1, w2, b2)
+    pooled = pooled.contiguous()
+    m, d_in = pooled.shape
+    d_hid, k_head = w1.shape[0], w2.shape[0]
+    dt = pooled.dtype
+    w1, b1, w2, b2 = (x.to(dt).contiguous() for x in (w1, b1, w2, b2))
+    hidden = torch.empty((m, d_hid), dtype=dt, device=pooled.device)
+    logits = torch.empty((m, k_head), dtype=torch.float32, device=pooled.device)
+    check(_lib.lib().fg_head_fwd(_p(pooled), _p(w1), _p(b1), _p(w2), _p(b2), m, d_in, d_hid, k_head, _p(hidden), _p(logits),
+                                 None, 0, _dt(pooled), _stream()), "fg_head_fwd")
+    return logits, hidden
+
+
+def head_bwd(g_logits, hidden, w1, w2):
+    _cuda(g_logits, hidden, w1, w2)
+    g_logits = g_logits.to(torch.float32).contiguous()
+    m, d_hid = hidden.shape
+    d_in, k_head = w1.shape[1], w2.shape[0]
+    dt = hidden.dtype
+    w1, w2 = w1.to(dt).contiguous(), w2.to(dt).contiguous()
+    nbytes = _lib.lib().fg_head_workspace_bytes(m, d_in, d_hid, k_head, _dt(hidden))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=hidden.device)
+    g_pooled = torch.empty((m, d_in), dtype=dt, device=hidden.device)
+    check(_lib.lib().fg_head_bwd(_p(g_logits), _p(hidden), _p(w1), _p(w2), m, d_in, d_hid, k_head, _p(g_pooled), _p(ws), nbytes,
+                                 _dt(hidden), _stream()), "fg_head_bwd")
+    return g_pooled
+
+
+def head_attributes(logits, src_row, selector, n, col_start, width, fill, dtype):
+    """-> (preds [A,n] int64, probs list of [n,w_a], logits list of [n,w_a]); attribute-major flat storage."""
+    _cuda(logits, src_row, selector)
+    dev = logits.device
+    logits = logits.to(torch.float32).contiguous()
+    A = len(width)
+    tot = sum(width)
+    preds = torch.empty((A, n), dtype=torch.int64, device=dev)
+    probs = torch.empty((n * tot,), dtype=dtype, device=dev)
+    lout = torch.empty((n * tot,), dtype=dtype, device=dev)
+    sel = _u8(selector)
+    src = None if src_row is None else src_row.to(torch.int32).contiguous()
+    check(_lib.lib().fg_head_attributes(_p(logits), logits.shape[0], logits.shape[1], _p(src), _p(sel), n, A,
+                                        _iarr(col_start), _iarr(width), float(fill), _p(preds), _p(probs), _p(lout),
+                                        _DT[dtype], _stream()), "fg_head_attributes")
+    ps, ls, off = [], [], 0
+    for w in width:
+        ps.append(probs[off:off + n * w].view(n, w))
+        ls.append(lout[off:off + n * w].view(n, w))
+        off += n * w
+    return preds, ps, ls
+
+
+# ------------------------------------------------------------------ loss
+def fair_ce_fwd(logits, targets, face, fill=-1.0):
+    _cuda(logits, targets, face)
+    logits = logits.contiguous()
+    n, k = logits.shape
+    loss = torch.empty((n,), dtype=logits.dtype, device=logits.device)
+    check(_lib.lib().fg_fair_ce_fwd(_p(logits), _p(targets.to(torch.int64).contiguous()), _p(_u8(face)), n, k, float(fill),
+                                    _p(loss), _dt(logits), _stream()), "fg_fair_ce_fwd")
+    return loss
+
+
+def fair_ce_bwd(logits, targets, face, g_loss):
+    logits = logits.contiguous()
+    n, k = logits.shape
+    g = torch.empty_like(logits)
+    check(_lib.lib().fg_fair_ce_bwd(_p(logits), _p(targets.to(torch.int64).contiguous()), _p(_u8(face)),
+                                    _p(g_loss.to(logits.dtype).contiguous()), n, k, _p(g), _dt(logits), _stream()), "fg_fair_ce_bwd")
+    return g
+
+
+# ------------------------------------------------------------------ assignment
+def assign_rank_binom(probs, target_ratio=0.5, threshold=-1.0, w_uncertainty=True):
+    _cuda(probs)
+    probs = probs.contiguous()
+    n_all = probs.shape[0]
+    targets = torch.empty((n_all,), dtype=torch.int64, device=probs.device)
+    unc = torch.empty((n_all,), dtype=probs.dtype, device=probs.device) if w_uncertainty else None
+    nbytes = _lib.lib().fg_rank_binom_workspace_bytes(n_all)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=probs.device)
+    check(_lib.lib().fg_assign_rank_binom(_p(probs), n_all, float(target_ratio), float(threshold), _p(targets), _p(unc),
+                                          _p(ws), nbytes, _dt(probs), _stream()), "fg_assign_rank_binom")
+    return targets, unc
+
+
+class OtWorkspace:
+    """Device scratch shared by ot_plan_counts and ot_targets of one assignment."""
+
+    def __init__(self, n_all, K, S, device):
+        self.n_all, self.K, self.S = n_all, K, S
+        self.nbytes = _lib.lib().fg_ot_workspace_bytes(n_all, K, S)
+        self.buf = torch.empty((max(self.nbytes, 16),), dtype=torch.uint8, device=device)
+
+    def status(self):
+        """[status bits, n_valid seen on the device, base augmentations, draw augmentations] (synchronises)."""
+        return self.buf[:16].view(torch.int32).tolist()
+
+
+def ot_plan_counts(probs_gender, probs_race, probs_age, rands, n_valid, ws):
+    """This rank's per-(row,class) plan counts, int32 [n_valid,K]."""
+    _cuda(probs_gender, probs_race, probs_age, *rands)
+    K = ws.K
+    dev = probs_gender.device
+    pg, pr = probs_gender.contiguous(), probs_race.contiguous()
+    pa = None if probs_age is None else probs_age.contiguous()
+    S = rands[0].shape[0] if (n_valid > 0 and len(rands) > 0) else 0
+    r = [x.to(pg.dtype).contiguous() for x in rands] + [None] * (3 - len(rands))
+    counts = torch.empty((n_valid, K), dtype=torch.int32, device=dev)
+    check(_lib.lib().fg_ot_plan_counts(_p(pg), _p(pr), _p(pa), pg.shape[0], _p(r[0]), _p(r[1]), _p(r[2]), S, n_valid,
+                                       _p(counts), _p(ws.buf), ws.nbytes, _dt(pg), _stream()), "fg_ot_plan_counts")
+    return counts
+
+
+def ot_targets(counts, probs_gender, probs_race, n_valid, ws, threshold=-1.0, w_uncertainty=True):
+    K = ws.K
+    dev = probs_gender.device
+    n_all = probs_gender.shape[0]
+    dt = probs_gender.dtype
+    A = 3 if K == 16 else 2
+    ts = [torch.empty((n_all,), dtype=torch.int64, device=dev) for _ in range(A)] + [None] * (3 - A)
+    us = ([torch.empty((n_all,), dtype=dt, device=dev) for _ in range(A)] if w_uncertainty else [None] * A) + [None] * (3 - A)
+    check(_lib.lib().fg_ot_targets(_p(counts), _p(probs_gender), _p(probs_race), n_all, n_valid, K, float(threshold),
+                                   _p(ts[0]), _p(us[0]), _p(ts[1]), _p(us[1]), _p(ts[2]), _p(us[2]),
+                                   _p(ws.buf), ws.nbytes, _DT[dt], _stream()), "fg_ot_targets")
+    return ts[:A], us[:A]
+
+
+def ot_solve_single(M, b):
+    """Test hook: exact assignment int32 [n] of the rows of M [n,K] float64 to classes with sizes b."""
+    _cuda(M)
+    M = M.to(torch.float64).contiguous()
+    n, K = M.shape
+    ws = OtWorkspace(n, K, 0, M.device)
+    out = torch.empty((n,), dtype=torch.int32, device=M.device)
+    barr = (ctypes.c_int64 * K)(*[int(v) for v in b])
+    check(_lib.lib().fg_ot_solve_single(_p(M), n, K, barr, _p(out), _p(ws.buf), ws.nbytes, _stream()), "fg_ot_solve_single")
+    return out, ws
+
+
+def ot_cost_matrix(probs_gender, probs_race, probs_age, n_valid):
+    _cuda(probs_gender, probs_race, probs_age)
+    K = 8 if probs_age is None else 16
+    n_all = probs_gender.shape[0]
+    ws = OtWorkspace(n_all, K, 0, probs_gender.device)
+    M = torch.empty((n_valid, K), dtype=torch.float64, device=probs_gender.device)
+    pa = None if probs_age is None else probs_age.contiguous()
+    check(_lib.lib().fg_ot_cost_matrix(_p(probs_gender.contiguous()), _p(probs_race.contiguous()), _p(pa), n_all, n_valid, _p(M),
+                                       _p(ws.buf), ws.nbytes, _dt(probs_gender), _stream()), "fg_ot_cost_matrix")
+    return M

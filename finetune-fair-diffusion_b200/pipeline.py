@@ -1,0 +1,265 @@
+"""The guidance path as ONE forward+backward pass over a batch of images (what bench.py times).
+
+Stage order (reference lines in parentheses; a1..a15 = SURVEY.md section 8a rows):
+
+  1  select largest face + expand box            a1,a2   (E1:1292-1304, E1:238-265)
+  2  fused crop 224^2 + resize 224^2             a3,a4,a12 (E1:267-290, E1:1905)
+  3  [classifier backbone: torchvision/cuDNN, not part of the path -- either the real
+      MobileNetV3 `features` (mode "backbone") or stand-in tensors (mode "standin")]
+  4  dense head + per-attribute softmax/argmax   a5      (E3:1387-1457)
+  5  all-gather of {indicator, probs}            a6      (E3:1978-1986)
+  6  balanced assignment + threshold + slice     a7-a10  (E1:1403-1447 / E3:1459-1569 / E4:1477-1615, E3:2022-2025)
+  7  fairness CE, its gradient, head backward    a14     (E3:2114-2122)
+  8  hook region/scale + dynamic weights         a11,a13 (E3:1751-1803)
+  9  loss assembly                               a14     (E3:2146-2147)
+  10 fused image gradient                        a11,a12,a3 backward
+
+The reference runs stages 1-6 without gradient on one generation of the images and stages 2-4,7-10
+with gradient on a second, numerically identical generation (E3:1956-2147); the owned arithmetic is
+the same, so one pass with shared forward results is what is measured.
+"""
+import dataclasses
+from typing import Optional
+
+import torch
+
+from . import api, dist as fdist, ops
+
+KINDS = {
+    # kind: (attribute widths, col_start, k_head, K classes of the assignment, e1_rule)
+    "gender": ([2], [40], 80, 2, True),
+    "gender_race": ([2, 4], [0, 2], 6, 8, False),
+    "gender_race_age": ([2, 4, 2], [0, 2, 6], 8, 16, False),
+}
+
+
+@dataclasses.dataclass
+class GuidanceConfig:
+    kind: str = "gender_race"
+    num_samples_per_device: int = 100            # E3:1460 keyword default
+    uncertainty_threshold: float = 0.2           # every shipped YAML (e.g. exp-3 configs/debias-text-encoder.yaml:10)
+    target_ratio: float = 0.5                    # E1:1404
+    factors1: tuple = (0.2, 0.6, 0.6)            # dynamic weights: factor1_gender/race/age (E4:484-487 defaults)
+    factors2: tuple = (0.2, 0.3, 0.3)            # hook: factor2_*
+    weight_loss_img: float = 8.0
+    weight_loss_face: float = 1.0
+    size_face: int = 224
+    img_size_small: int = 224
+    fill_value: float = -1.0
+    expand_coef: float = 0.5
+    d_in: int = 960
+    d_hid: int = 1280
+
+    @property
+    def n_attr(self):
+        return len(KINDS[self.kind][0])
+
+
+def make_head_weights(cfg: GuidanceConfig, dtype, device, seed=0, logit_scale=6.0):
+    """Random-init head of the MobileNetV3 layout (no checkpoint is available offline); the last
+    layer is scaled up so that a good share of faces pass the uncertainty threshold."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    k_head = KINDS[cfg.kind][2]
+    w1 = torch.randn(cfg.d_hid, cfg.d_in, generator=g) / cfg.d_in ** 0.5
+    b1 = torch.randn(cfg.d_hid, generator=g) * 0.1
+    w2 = torch.randn(k_head, cfg.d_hid, generator=g) * (logit_scale / cfg.d_hid ** 0.5)
+    b2 = torch.randn(k_head, generator=g) * 0.1
+    return tuple(t.to(device=device, dtype=dtype) for t in (w1, b1, w2, b2))
+
+
+def synth_batch(n, cfg: GuidanceConfig, dtype, device, seed=5991, H=512, W=512, max_faces=1, no_face_frac=0.05,
+                host=False):
+    """Synthetic images / candidate boxes / stand-ins of SURVEY.md section 8d, generated on the CPU
+    generator (so the oracle sees the same values) and moved to ``device``."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    yy = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
+    xx = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    ph = torch.rand(n, 3, 1, 1, generator=g) * 6.28
+    fr = 0.01 + 0.03 * torch.rand(n, 3, 1, 1, generator=g)
+    images = 0.6 * torch.sin(fr * xx + ph) * torch.cos(fr * 0.7 * yy - ph) + (torch.rand(n, 3, H, W, generator=g) - 0.5) * 0.2
+    images = images.clamp_(-1, 1)
+    ctr = 160 + 192 * torch.rand(n, max_faces, 2, generator=g)
+    side = 96 + 192 * torch.rand(n, max_faces, 2, generator=g) * torch.tensor([1.0, 1.0])
+    side[..., 1] = side[..., 0] * (0.8 + 0.4 * torch.rand(n, max_faces, generator=g))
+    cand = torch.cat([ctr - side / 2, ctr + side / 2], dim=-1).to(torch.float32)
+    if max_faces > 1:
+        counts = torch.randint(1, max_faces + 1, (n,), generator=g, dtype=torch.int32)
+        counts = torch.where(torch.rand(n, generator=g) < no_face_frac, torch.zeros_like(counts), counts)
+    else:
+        counts = (torch.rand(n, generator=g) >= no_face_frac).to(torch.int32)
+    jitter = torch.randint(-12, 13, (n, 4), generator=g)
+    k_head = KINDS[cfg.kind][2]
+    batch = dict(
+        images=images.to(dtype), cand_boxes=cand, counts=counts, bbox_jitter=jitter,
+        pooled=torch.randn(n, cfg.d_in, generator=g).to(dtype),                                   # backbone stand-in (fwd)
+        g_chips=(torch.randn(n, 3, cfg.size_face, cfg.size_face, generator=g) * 1e-3).to(dtype),  # backbone stand-in (bwd)
+        g_small=(torch.randn(n, 3, cfg.img_size_small, cfg.img_size_small, generator=g) * 1e-3).to(dtype),  # CLIP/DINO grad stand-in
+        loss_clip=torch.rand(n, generator=g).to(dtype), loss_dino=torch.rand(n, generator=g).to(dtype),
+        loss_face=torch.rand(n, generator=g).to(dtype),
+        preds_ori=[torch.randint(0, w, (n,), generator=g) for w in KINDS[cfg.kind][0]],
+        k_head=k_head,
+    )
+    if not host:
+        batch = {k: _to(v, device) for k, v in batch.items()}
+    return batch
+
+
+def synth_batch_device(n, cfg: GuidanceConfig, dtype, device, seed=5991, H=512, W=512, max_faces=1, no_face_frac=0.05):
+    """Same distributions as synth_batch, generated on the device in chunks (BASELINE-size batches
+    do not fit a CPU-side fp32 staging copy comfortably).  Used by bench.py only."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    images = torch.empty((n, 3, H, W), dtype=dtype, device=device)
+    yy = torch.arange(H, dtype=torch.float32, device=device).view(1, 1, H, 1)
+    xx = torch.arange(W, dtype=torch.float32, device=device).view(1, 1, 1, W)
+    for s in range(0, n, 32):
+        m = min(32, n - s)
+        ph = torch.rand(m, 3, 1, 1, generator=g, device=device) * 6.28
+        fr = 0.01 + 0.03 * torch.rand(m, 3, 1, 1, generator=g, device=device)
+        im = 0.6 * torch.sin(fr * xx + ph) * torch.cos(fr * 0.7 * yy - ph) + (torch.rand(m, 3, H, W, generator=g, device=device) - 0.5) * 0.2
+        images[s:s + m] = im.clamp_(-1, 1).to(dtype)
+    r = lambda *shape: torch.rand(*shape, generator=g, device=device)
+    ctr = 160 + 192 * r(n, max_faces, 2)
+    side = 96 + 192 * r(n, max_faces, 2)
+    side[..., 1] = side[..., 0] * (0.8 + 0.4 * r(n, max_faces))
+    cand = torch.cat([ctr - side / 2, ctr + side / 2], dim=-1).to(torch.float32)
+    if max_faces > 1:
+        counts = torch.randint(1, max_faces + 1, (n,), generator=g, device=device, dtype=torch.int32)
+    else:
+        counts = torch.ones(n, dtype=torch.int32, device=device)
+    counts = torch.where(r(n) < no_face_frac, torch.zeros_like(counts), counts)
+    rn = lambda *shape: torch.randn(*shape, generator=g, device=device)
+    return dict(
+        images=images, cand_boxes=cand, counts=counts,
+        bbox_jitter=torch.randint(-12, 13, (n, 4), generator=g, device=device),
+        pooled=rn(n, cfg.d_in).to(dtype),
+        g_chips=(rn(n, 3, cfg.size_face, cfg.size_face) * 1e-3).to(dtype),
+        g_small=(rn(n, 3, cfg.img_size_small, cfg.img_size_small) * 1e-3).to(dtype),
+        loss_clip=r(n).to(dtype), loss_dino=r(n).to(dtype), loss_face=r(n).to(dtype),
+        preds_ori=[torch.randint(0, w, (n,), generator=g, device=device) for w in KINDS[cfg.kind][0]],
+        k_head=KINDS[cfg.kind][2],
+    )
+
+
+def _to(v, device):
+    if torch.is_tensor(v):
+        return v.to(device)
+    if isinstance(v, list):
+        return [_to(x, device) for x in v]
+    return v
+
+
+class _NullProbe:
+    @staticmethod
+    def begin(name):
+        pass
+
+    @staticmethod
+    def end(name):
+        pass
+
+
+class GuidancePath:
+    """Holds the frozen head and the configuration; ``step`` runs stages 1-10 on this rank's images."""
+
+    def __init__(self, cfg: GuidanceConfig, head_weights, backbone=None, group=None):
+        self.cfg, self.head, self.backbone, self.group = cfg, head_weights, backbone, group
+
+    @torch.no_grad()
+    def step(self, batch, rand_tensors=None, num_valid: Optional[int] = None, probe=None):
+        """``probe``: optional object with begin(name)/end(name) (bench.py records CUDA events on the
+        current stream around the named stages)."""
+        cfg = self.cfg
+        P = probe if probe is not None else _NullProbe
+        widths, col_start, k_head, K, e1_rule = KINDS[cfg.kind]
+        images = batch["images"]
+        n, _, H, W = images.shape
+        world, rank = fdist._world(self.group)
+
+        # 1-2
+        ind, boxes = ops.select_expand_boxes(batch["cand_boxes"], batch["counts"], H, cfg.expand_coef, 1.0, -1)
+        P.begin("sample_fwd")
+        chips, small = ops.crop_resize_fwd(images, boxes, ind, (cfg.size_face,) * 2, (cfg.img_size_small,) * 2, cfg.fill_value)
+        P.end("sample_fwd")
+        # 3-4
+        pooled = batch["pooled"] if self.backbone is None else self.backbone(chips)
+        logits, hidden = ops.head_fwd(pooled, *self.head)
+        preds, probs, logits_attr = ops.head_attributes(logits, None, ind, n, col_start, widths, cfg.fill_value, images.dtype)
+        # 5
+        P.begin("assign")
+        ind_all, probs_all = fdist.gather_probs(ind, probs, self.group)
+        # 6
+        if cfg.kind == "gender":
+            t_all, _ = ops.assign_rank_binom(probs_all[0], cfg.target_ratio, cfg.uncertainty_threshold, True)
+            targets_all = [t_all]
+            counts = None
+        else:
+            n_all = ind_all.shape[0]
+            nv = num_valid if num_valid is not None else int(ind_all.sum().item())
+            ws = ops.OtWorkspace(n_all, K, cfg.num_samples_per_device, images.device)
+            if rand_tensors is None and nv > 0:
+                rand_tensors = tuple(torch.rand([cfg.num_samples_per_device, nv], dtype=images.dtype, device=images.device)
+                                     for _ in widths)
+            pa = probs_all[2] if len(widths) == 3 else None
+            counts = ops.ot_plan_counts(probs_all[0], probs_all[1], pa, rand_tensors or (), nv, ws)
+            if nv > 0:
+                fdist.all_reduce_counts(counts, self.group)
+            targets_all, _ = ops.ot_targets(counts, probs_all[0], probs_all[1], nv, ws, cfg.uncertainty_threshold, True)
+        targets = [t[n * rank:n * (rank + 1)] for t in targets_all]
+        P.end("assign")
+        # 7
+        g_logits = torch.zeros((n, k_head), dtype=torch.float32, device=images.device)
+        inv_n = torch.full((n,), 1.0 / n, dtype=images.dtype, device=images.device)
+        loss_fair = []
+        for a, (c, w) in enumerate(zip(col_start, widths)):
+            loss_fair.append(ops.fair_ce_fwd(logits_attr[a], targets[a], ind, -1.0))
+            g_logits[:, c:c + w] = ops.fair_ce_bwd(logits_attr[a], targets[a], ind, inv_n)
+        g_pooled = ops.head_bwd(g_logits, hidden, self.head[0], self.head[2])
+        # 8
+        bbox_ori = torch.where(ind.unsqueeze(1), boxes + batch["bbox_jitter"], boxes)
+        region, scale, dyn_w = ops.guidance_factors(ind, boxes, bbox_ori, targets, batch["preds_ori"],
+                                                    cfg.factors2[:len(widths)], cfg.factors1[:len(widths)], e1_rule, H, W)
+        # 9
+        loss = loss_fair[0].float()
+        for t in loss_fair[1:]:
+            loss = loss + t.float()
+        loss = loss + cfg.weight_loss_img * dyn_w * (batch["loss_clip"].float() + batch["loss_dino"].float()) \
+            + cfg.weight_loss_face * batch["loss_face"].float()
+        # 10
+        P.begin("image_grad")
+        g_images = ops.image_grad(batch["g_chips"], batch["g_small"], boxes, ind, region, scale, tuple(images.shape),
+                                  images.dtype, images.device)
+        P.end("image_grad")
+        return dict(indicators=ind, boxes=boxes, chips=chips, small=small, logits=logits, preds=preds, probs=probs,
+                    targets=targets, targets_all=targets_all, counts=counts, loss_fair=loss_fair, g_pooled=g_pooled,
+                    region=region, scale=scale, dyn_weights=dyn_w, loss=loss, loss_mean=loss.mean(), g_images=g_images,
+                    bbox_ori=bbox_ori)
+
+
+def smoke_check(device="cuda:0"):
+    """One small invocation of the whole path on the GPU, checked stage by stage against the oracle."""
+    import numpy as np
+    from oracle import pipeline as opipe          # the oracle is the checker here, never the product
+    torch.cuda.set_device(device)
+    for kind in ("gender", "gender_race", "gender_race_age"):
+        cfg = GuidanceConfig(kind=kind, num_samples_per_device=20)
+        host = synth_batch(12, cfg, torch.float32, "cpu", seed=7, H=256, W=256, max_faces=2, host=True)
+        head = make_head_weights(cfg, torch.float32, "cpu")
+        dev_batch = {k: _to(v, device) for k, v in host.items()}
+        nv = int((host["counts"] > 0).sum())
+        rands = None
+        if kind != "gender":
+            g = torch.Generator().manual_seed(3)
+            rands = tuple(torch.rand(cfg.num_samples_per_device, nv, generator=g) for _ in range(cfg.n_attr))
+        out = GuidancePath(cfg, tuple(t.to(device) for t in head)).step(
+            dev_batch, rand_tensors=None if rands is None else tuple(r.to(device) for r in rands), num_valid=nv)
+        ref = opipe.step(host, cfg, head, rand_tensors=rands)
+        torch.cuda.synchronize()
+        assert torch.equal(out["boxes"].cpu(), ref["boxes"]), kind
+        for a in range(cfg.n_attr):
+            assert torch.equal(out["targets"][a].cpu(), ref["targets"][a]), (kind, a)
+        np.testing.assert_allclose(out["chips"].cpu().numpy(), ref["chips"].numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(out["small"].cpu().numpy(), ref["small"].numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(out["loss"].cpu().numpy(), ref["loss"].numpy(), rtol=1e-3, atol=1e-4)
+        gref = ref["g_images"].numpy()
+        np.testing.assert_allclose(out["g_images"].cpu().numpy(), gref, rtol=1e-3, atol=1e-3 * float(np.abs(gref).max()))
+    return True

@@ -1,0 +1,179 @@
+/*
+ * fairguide -- C ABI of the B200 (sm_100a) fairness-guidance kernels.
+ *
+ * This is the drop-in boundary.  The reference (sail-sg/finetune-fair-diffusion) is pure Python
+ * with no FFI of its own: the interface it exposes for this path is the set of Python closures in
+ * exp-*-/1-main-debias.py.  Each entry point below names the reference
+ * function it replaces; the Python mirror of those closures lives in
+ * finetune-fair-diffusion_b200/api.py and reaches these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor is contiguous, row-major, device memory unless
+ *     the parameter says "host";
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises, allocates or keeps
+ *     global mutable state; calls on different streams with disjoint buffers are safe;
+ *   - return value: 0 = launched; < 0 = argument error (FG_ERR_*); > 0 = cudaError_t of a launch;
+ *   - `dtype` selects the element type of the `void*` image / probability tensors (fg_dtype_t);
+ *   - absence is signalled the way the reference does it: -1 sentinels (boxes, preds, probs,
+ *     targets, losses), never by an error.
+ *
+ * Reference citations: E1 = exp-1-debias-gender/1-main-debias.py, E3 = exp-3-debias-gender-race/
+ * 1-main-debias.py, E4 = exp-4-debias-gender-race-age/1-main-debias.py.
+ */
+#ifndef FAIRGUIDE_H
+#define FAIRGUIDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 1
+
+#define FG_OK 0
+#define FG_ERR_INVALID_ARG (-1)
+#define FG_ERR_DTYPE (-2)
+#define FG_ERR_LIMIT (-3)
+#define FG_ERR_WORKSPACE (-4)
+
+typedef enum { FG_F32 = 0, FG_BF16 = 1, FG_F16 = 2 } fg_dtype_t;
+
+int fg_abi_version(void);
+/* Static string for any value the functions below return (FG_ERR_* or a cudaError_t). */
+const char* fg_error_string(int code);
+
+/* ------------------------------------------------------------------ boxes ------------------
+ * get_largest_face_app (E1:1292-1304) + expand_bbox (E1:238-265), batched.
+ * boxes [n, max_faces, 4] float32 (x0,y0,x1,y1); counts [n] int32 (0 = no detection), NULL means
+ * every image has exactly max_faces candidates.  Largest area clipped to [0, dim_max]^2, strict
+ * '>' so the first maximum wins.  Output boxes_out [n,4] int64, rounded half-to-even in float32
+ * exactly like the reference; rows without a face get `fill` (E1:1328-1332) and indicator 0. */
+int fg_select_expand_boxes(const float* boxes, const int32_t* counts, int n, int max_faces, int dim_max,
+                           double expand_coef, double target_ratio, int64_t fill,
+                           int64_t* boxes_out, uint8_t* indicators_out, void* stream);
+
+/* ------------------------------------------------------------------ crop / resize ---------
+ * crop_face (E1:267-290) for every image of a batch, fused with transforms.Resize (E1:1905).
+ * images [n,C,H,W]; boxes [n,4] int64; indicators [n] uint8 or NULL (= all faces present).
+ * chips [n,C,chip_h,chip_w]: bilinear (align_corners=False, no antialias) resample of the box, the
+ * part of the box outside the image reading `fill_value`; images without a face, or with an empty /
+ * fully outside box, become all-`fill_value` chips.  small [n,C,small_h,small_w]: the same sampler
+ * over the whole image.  Either output may be NULL.  One launch reads each image once from HBM. */
+int fg_crop_resize_fwd(const void* images, int n, int C, int H, int W,
+                       const int64_t* boxes, const uint8_t* indicators,
+                       void* chips, int chip_h, int chip_w,
+                       void* small, int small_h, int small_w,
+                       float fill_value, int dtype, void* stream);
+
+/* apply_grad_hook_face (E1:1584-1617, E3:1751-1784, E4:1823-1867) and gen_dynamic_weights
+ * (E1:1619-1633, E3:1787-1803, E4:1870-1895) reduced to their per-image parameters.
+ * bbox / bbox_ori [n,4] int64; targets_a / preds_ori_a [n] int64 for attribute a < n_attr (unused
+ * slots NULL); hook_factors / weight_factors: HOST arrays of n_attr floats.  e1_rule != 0 selects
+ * E1's branch in which a -1 target always takes the factor.
+ * Outputs (each may be NULL): region [n,4] int32 = x0,y0,x1,y1 (half open, empty if x1<=x0) of
+ * bbox ^ bbox_ori ^ image with the reference's python-slice semantics for a -1 original box;
+ * scale [n] float32 = factor applied to the gradient inside the region (1 if bbox is all -1);
+ * weights [n] float32 = dynamic loss weight. */
+int fg_guidance_factors(const uint8_t* face_indicators, const int64_t* bbox, const int64_t* bbox_ori,
+                        const int64_t* targets0, const int64_t* targets1, const int64_t* targets2,
+                        const int64_t* preds_ori0, const int64_t* preds_ori1, const int64_t* preds_ori2,
+                        const float* hook_factors, const float* weight_factors, int n_attr, int e1_rule,
+                        int n, int H, int W, int32_t* region, float* scale, float* weights, void* stream);
+
+/* Backward of the fused forward, into the image: for every pixel
+ *   g_images = scale_in_region * resize_bwd(g_small) + crop_bwd(g_chips)
+ * (the fairness branch is taken before the hook, E3:2103 vs E3:2106, so it is not scaled).
+ * Gather formulation: deterministic, no atomics, g_images is written exactly once.
+ * g_chips / g_small / region+scale may be NULL (term dropped / scale 1). */
+int fg_image_grad(const void* g_chips, const void* g_small,
+                  const int64_t* boxes, const uint8_t* indicators,
+                  const int32_t* region, const float* scale,
+                  void* g_images, int n, int C, int H, int W,
+                  int chip_h, int chip_w, int small_h, int small_w, int dtype, void* stream);
+
+/* Backward of apply_grad_hook_face on its own: g_out = g_in * (scale inside region, 1 outside). */
+int fg_region_scale(const void* g_in, const int32_t* region, const float* scale, void* g_out,
+                    int n, int C, int H, int W, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ attribute head --------
+ * torchvision MobileNetV3 `classifier` (mobilenetv3.py:190-216 as used at E1:929-935):
+ *   logits = W2 * hardswish(W1 * pooled + b1) + b2      (Dropout is identity in eval mode)
+ * pooled [m,d_in], w1 [d_hid,d_in], b1 [d_hid], w2 [k_head,d_hid], b2 [k_head] in `dtype`;
+ * hidden_pre [m,d_hid] (dtype) receives the pre-activation for the backward; logits [m,k_head] f32. */
+size_t fg_head_workspace_bytes(int m, int d_in, int d_hid, int k_head, int dtype);
+int fg_head_fwd(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2,
+                int m, int d_in, int d_hid, int k_head, void* hidden_pre, float* logits,
+                void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* g_pooled [m,d_in] (dtype) from g_logits [m,k_head] f32; weights are frozen (no weight grads). */
+int fg_head_bwd(const float* g_logits, const void* hidden_pre, const void* w1, const void* w2,
+                int m, int d_in, int d_hid, int k_head, void* g_pooled,
+                void* workspace, size_t workspace_bytes, int dtype, void* stream);
+
+/* get_face_gender (E1:1355-1401), get_face_gender_race (E3:1387-1457), get_face_gender_race_age
+ * (E4:1378-1475) after the classifier: per-attribute logit slice, softmax, argmax, scatter into
+ * `fill`-initialised per-image rows.
+ * logits [m,k_head] f32; src_row [n] int32 = row of `logits` for image i, or NULL for i;
+ * selector [n] uint8 or NULL (= all selected); col_start / width: HOST arrays [n_attr] (E1: {40},{2};
+ * E3: {0,2},{2,4}; E4: {0,2,6},{2,4,2}).  Outputs are attribute-major and contiguous per attribute:
+ * preds [n_attr][n] int64; probs / logits_out: attribute a starts at element n*sum(width[<a]) and is
+ * [n,width[a]] in `dtype`. */
+int fg_head_attributes(const float* logits, int m, int k_head, const int32_t* src_row, const uint8_t* selector,
+                       int n, int n_attr, const int32_t* col_start, const int32_t* width, float fill,
+                       int64_t* preds, void* probs, void* logits_out, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ fairness loss ---------
+ * CE_loss(logits[idx], targets[idx]) on idx = face & target != -1, `fill` elsewhere
+ * (E1:1912-1915, E3:2114-2122, E4:2238-2251).  logits [n,k] dtype; loss [n] dtype. */
+int fg_fair_ce_fwd(const void* logits, const int64_t* targets, const uint8_t* face_indicators,
+                   int n, int k, float fill, void* loss, int dtype, void* stream);
+/* g_logits [n,k] = g_loss[i] * (softmax(logits[i]) - onehot(target_i)) on active rows, else 0. */
+int fg_fair_ce_bwd(const void* logits, const int64_t* targets, const uint8_t* face_indicators,
+                   const void* g_loss, int n, int k, void* g_logits, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ assignment ------------
+ * generate_dynamic_targets (E1:1403-1447): rank split at N*target_ratio and binomial-CDF
+ * uncertainty, N = rows of probs [n_all,2] without a -1.  Ties in probs[:,1] resolve by row index.
+ * targets [n_all] int64 (-1 for skipped rows); uncertainty [n_all] dtype or NULL.  If
+ * threshold >= 0, targets whose uncertainty exceeds it are set to -1 as at E1:1835. */
+size_t fg_rank_binom_workspace_bytes(int n_all);
+int fg_assign_rank_binom(const void* probs, int n_all, double target_ratio, float threshold,
+                         int64_t* targets, void* uncertainty, void* workspace, size_t workspace_bytes,
+                         int dtype, void* stream);
+
+/* generate_dynamic_targets_gender_race (E3:1459-1569; probs_age NULL, K = 8) and
+ * generate_dynamic_targets_gender_race_age (E4:1477-1615; K = 16), split at the all-reduce:
+ *
+ * fg_ot_plan_counts: this rank's S Monte-Carlo draws.  rand_* [S,n_valid] in `dtype` are the uniform
+ * draws (the caller draws them with torch.rand in the reference's order so seeded runs match);
+ * n_valid = rows with a face, which the caller knows (it fixed the shape of rand_*).  For every draw
+ * the class histogram b is formed and the exact transport problem ot.emd(ones, b, M) is solved on the
+ * device; counts [n_valid,K] int32 receives the number of draws that sent row i to class j
+ * (= target_probs before E3:1534).  Integer, so the cross-rank sum is order independent.
+ *
+ * fg_ot_targets: epilogue E3:1536-1565 on the rank-summed counts, in `dtype` arithmetic with the
+ * reference's operation order; optional thresholding (E3:2022-2023) when threshold >= 0.
+ * Outputs [n_all]: targets_* int64, unc_* dtype (NULL to skip); the age pair is used when K = 16. */
+size_t fg_ot_workspace_bytes(int n_all, int K, int S);
+int fg_ot_plan_counts(const void* probs_gender, const void* probs_race, const void* probs_age, int n_all,
+                      const void* rand_gender, const void* rand_race, const void* rand_age, int S, int n_valid,
+                      int32_t* counts, void* workspace, size_t workspace_bytes, int dtype, void* stream);
+int fg_ot_targets(const int32_t* counts, const void* probs_gender, const void* probs_race, int n_all, int n_valid,
+                  int K, float threshold,
+                  int64_t* targets_gender, void* unc_gender, int64_t* targets_race, void* unc_race,
+                  int64_t* targets_age, void* unc_age, void* workspace, size_t workspace_bytes,
+                  int dtype, void* stream);
+
+/* Test hook: exact assignment for ONE demand vector b (host array [K] int64) on a given cost matrix
+ * M [n,K] float64 (device); assign [n] int32.  Exercises the same solver kernel as fg_ot_plan_counts. */
+int fg_ot_solve_single(const double* M, int n, int K, const int64_t* b_host, int32_t* assign,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Test hook: the cost matrix the solver uses, M [n_valid,K] float64, rows in compacted order. */
+int fg_ot_cost_matrix(const void* probs_gender, const void* probs_race, const void* probs_age, int n_all,
+                      int n_valid, double* M, void* workspace, size_t workspace_bytes, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAIRGUIDE_H */

@@ -102,17 +102,21 @@ _A16 = np.array([[1, 0], [0, 1]] * 8)
 
 
 def cost_matrix_literal(pg, pr, pa=None):
-    """E3:1509-1526 / E4:1533-1560, element by element like the reference."""
+    """E3:1509-1526 / E4:1533-1560, element by element like the reference.
+
+    The rows are widened to float64 where the reference creates them: under its pinned NumPy
+    1.26 every expression below is promoted to float64 anyway (array - int64 array; float32
+    scalar - Python int), whereas NumPy 2 would keep the age residual in float32."""
     M = []
     for i in range(pg.shape[0]):
-        g = np.array(pg[i].cpu())
-        r = np.array(pr[i].cpu())
+        g = np.array(pg[i].cpu()).astype(np.float64)
+        r = np.array(pr[i].cpu()).astype(np.float64)
         row = []
         if pa is None:
             for j in range(8):
                 row.append((np.linalg.norm(g - _G8[j]) ** 2 + np.linalg.norm(r - _R8[j]) ** 2) ** 0.5)
         else:
-            a = np.array(pa[i].cpu())
+            a = np.array(pa[i].cpu()).astype(np.float64)
             for j in range(16):
                 if (_A16[j] == [1, 0]).all():
                     ca = math.sqrt((a[0] - 1) ** 2 + (a[1] - 0) ** 2)
@@ -126,12 +130,8 @@ def cost_matrix_literal(pg, pr, pa=None):
 def cost_matrix(pg, pr, pa=None, literal=False):
     if literal:
         return cost_matrix_literal(pg, pr, pa)
-    f = lambda t: t.detach().cpu().to(torch.float32).numpy().astype(np.float64)
-    age = None
-    if pa is not None:
-        # the age residual is rounded in the probs dtype (bf16 has no numpy type: widened to fp32)
-        age = pa.detach().cpu().numpy() if pa.dtype in (torch.float32, torch.float16) else pa.detach().cpu().float().numpy()
-    return _emd.cost_matrix_c(f(pg), f(pr), age)
+    f = lambda t: None if t is None else t.detach().cpu().to(torch.float32).numpy().astype(np.float64)
+    return _emd.cost_matrix_c(f(pg), f(pr), f(pa))
 
 
 def plan_counts(M, hists, emd=None):

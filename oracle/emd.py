@@ -92,25 +92,15 @@ def emd_lp(a, b, M):
     return np.rint(res.x.reshape(N, K))
 
 
-def age_cost_terms(pa):
-    """cost_age of E4:1547-1557 for the (young, old) target, rounded the way numpy scalar
-    arithmetic in the probs dtype rounds it; ``pa`` is a float32 or float16 array [N,2]."""
-    pa = np.asarray(pa)
-    assert pa.dtype in (np.float32, np.float16)
-    one, two = pa.dtype.type(1), pa.dtype.type(2)
-    young = (pa[:, 0] - one) ** 2 + (pa[:, 1]) ** 2
-    old = (pa[:, 0] * two) ** 2 + (pa[:, 1] - one) ** 2
-    return np.sqrt(np.stack([young, old], axis=1).astype(np.float64))
-
-
 def cost_matrix_c(pg, pr, pa=None):
     """Cost matrix in the fixed IEEE op order the CUDA kernel also uses (bit-comparable).
-    ``pa`` keeps its float32/float16 dtype (see age_cost_terms)."""
+    Inputs are the probabilities widened exactly to float64."""
     pg = np.ascontiguousarray(pg, dtype=np.float64)
     pr = np.ascontiguousarray(pr, dtype=np.float64)
     N = pg.shape[0]
     K = 8 if pa is None else 16
-    ca = np.ascontiguousarray(age_cost_terms(pa)) if pa is not None else None
+    if pa is not None:
+        pa = np.ascontiguousarray(pa, dtype=np.float64)
     M = np.empty((N, K), dtype=np.float64)
-    _lib().fg_oracle_cost_matrix(pg.ctypes.data, pr.ctypes.data, ca.ctypes.data if ca is not None else None, N, K, M.ctypes.data)
+    _lib().fg_oracle_cost_matrix(pg.ctypes.data, pr.ctypes.data, pa.ctypes.data if pa is not None else None, N, K, M.ctypes.data)
     return M

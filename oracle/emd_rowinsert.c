@@ -146,14 +146,13 @@ int fg_oracle_emd_unit(const double* M, const int64_t* b, int N, int K, int32_t*
  * restating exp-3 .../1-main-debias.py:1509-1526 (K=8) and exp-4 .../1-main-debias.py:1533-1560
  * (K=16, age term with the doubled young-probability residual for the "old" target).
  * np.linalg.norm(x)**2 is sqrt(sum sq) squared; the product keeps that sqrt-then-square.
- * The age residual (E4:1547-1557) is formed from numpy SCALARS of the probs dtype and Python
- * ints, so it is rounded in the probs dtype (float32, or float16 in an fp16 run) before
- * math.sqrt widens it; the caller computes that part in the right dtype and passes
- * ``ca`` [N,2] = cost_age for the (young, old) target as doubles.
+ * The age residual (E4:1547-1557) mixes numpy float32 scalars with Python ints; under the
+ * reference's pinned NumPy 1.26 that promotes to float64 (oracle/boxes.py explains), so it is
+ * double arithmetic on the exactly widened probabilities here too.
  * Class index: K=8  -> g*4+r ; K=16 -> g*8+r*2+a.
  */
 static double sq(double x) { return x * x; }
-void fg_oracle_cost_matrix(const double* pg, const double* pr, const double* ca, int N, int K, double* M) {
+void fg_oracle_cost_matrix(const double* pg, const double* pr, const double* pa, int N, int K, double* M) {
     for (int i = 0; i < N; i++) {
         for (int j = 0; j < K; j++) {
             int g, r, a = 0;
@@ -164,7 +163,9 @@ void fg_oracle_cost_matrix(const double* pg, const double* pr, const double* ca,
             double nr = sqrt(s4);
             double c = ng * ng + nr * nr;
             if (K == 16) {
-                double cav = ca[2 * i + a];
+                double cav;
+                if (a == 0) cav = sqrt(sq(pa[2 * i] - 1.0) + sq(pa[2 * i + 1] - 0.0));
+                else        cav = sqrt(sq((pa[2 * i] - 0.0) * 2.0) + sq(pa[2 * i + 1] - 1.0));
                 c = c + cav * cav;
             }
             M[(size_t)i * K + j] = sqrt(c);

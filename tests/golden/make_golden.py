@@ -132,6 +132,66 @@ def compile_into(ns, nodes):
         exec(compile(mod, "<reference>", "exec"), ns)
 
 
+class LegacyF32:
+    """A numpy float32 SCALAR as NumPy 1.26.4 (environment.yml:102, the reference's pin) treats it.
+
+    NumPy 2 (NEP 50, installed here) keeps ``np.float32(x) * 0.5`` in float32; the pinned 1.26
+    promotes scalar-with-Python-number arithmetic to float64 while float32-with-float32 stays
+    float32.  expand_bbox / get_largest_face_app receive numpy float32 scalars from insightface,
+    so the rounding of the box corners depends on this.  Feeding the reference functions these
+    wrappers makes them compute what they compute in their own environment."""
+    __array_ufunc__ = None
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = np.float32(v)
+
+    @staticmethod
+    def _bin(a, b, op):
+        if isinstance(a, LegacyF32) and isinstance(b, LegacyF32):
+            return LegacyF32(op(a.v, b.v))
+        fa = np.float64(a.v) if isinstance(a, LegacyF32) else np.float64(a)
+        fb = np.float64(b.v) if isinstance(b, LegacyF32) else np.float64(b)
+        return op(fa, fb)
+
+    def __sub__(self, o): return LegacyF32._bin(self, o, lambda x, y: x - y)
+    def __rsub__(self, o): return LegacyF32._bin(o, self, lambda x, y: x - y)
+    def __add__(self, o): return LegacyF32._bin(self, o, lambda x, y: x + y)
+    def __radd__(self, o): return LegacyF32._bin(o, self, lambda x, y: x + y)
+    def __mul__(self, o): return LegacyF32._bin(self, o, lambda x, y: x * y)
+    def __rmul__(self, o): return LegacyF32._bin(o, self, lambda x, y: x * y)
+    def __truediv__(self, o): return LegacyF32._bin(self, o, lambda x, y: x / y)
+    def __rtruediv__(self, o): return LegacyF32._bin(o, self, lambda x, y: x / y)
+    def _f(o): return float(o.v) if isinstance(o, LegacyF32) else float(o)
+    def __lt__(self, o): return float(self.v) < LegacyF32._f(o)
+    def __le__(self, o): return float(self.v) <= LegacyF32._f(o)
+    def __gt__(self, o): return float(self.v) > LegacyF32._f(o)
+    def __ge__(self, o): return float(self.v) >= LegacyF32._f(o)
+    def __round__(self, nd=None): return int(np.rint(self.v))
+    def __float__(self): return float(self.v)
+
+
+class _LegacyNp:
+    """``np`` as the MC-EMD functions see it: ``np.array(tensor)`` widens float32/float16 rows
+    to float64.  Under the pinned NumPy 1.26 every expression those functions build from the rows
+    (array minus int64 array at E3:1523, and scalar minus Python int at E4:1547-1557) is already
+    promoted to float64; under NumPy 2 the scalar ones would stay float32.  Widening at the
+    source reproduces the pinned behaviour exactly (float32 -> float64 is exact)."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    def array(self, x, *a, **k):
+        out = np.array(x, *a, **k)
+        if out.dtype in (np.float32, np.float16):
+            out = out.astype(np.float64)
+        return out
+
+
+def legacy_box(b):
+    return [LegacyF32(x) for x in b]
+
+
 # --------------------------------------------------------------------------- inputs
 def procedural_image(seed, C, H, W):
     """Smooth field + small noise in [-1,1]; the tests rebuild it from the same formula."""
@@ -168,7 +228,9 @@ def gen_boxes(ref, out):
                           [3, 7, 12, 28], [250, 250, 261, 301], [400, 380, 505, 511], [1, 1, 4, 2]], dtype=np.float32)
     res = {}
     for tag, coef, ratio in (("c05_r1", 0.5, 1), ("c11_r1", 1.1, 1), ("c05_r12", 0.5, 1.2)):
-        res["expanded_" + tag] = np.array([ns["expand_bbox"](b, expand_coef=coef, target_ratio=ratio) for b in boxes], dtype=np.int64)
+        res["expanded_" + tag] = np.array([ns["expand_bbox"](legacy_box(b), expand_coef=coef, target_ratio=ratio) for b in boxes], dtype=np.int64)
+        # what NumPy 2 would make of the same call (all-float32 arithmetic); stored to document the delta
+        res["expanded_nep50_" + tag] = np.array([ns["expand_bbox"](b, expand_coef=coef, target_ratio=ratio) for b in boxes], dtype=np.int64)
     m, F = 96, 3
     multi = np.zeros((m, F, 4), dtype=np.float32)
     counts = rng.integers(1, F + 1, size=m)
@@ -182,7 +244,7 @@ def gen_boxes(ref, out):
     counts[1] = 2
     picked = []
     for i in range(m):
-        faces = [{"bbox": multi[i, k]} for k in range(counts[i])]
+        faces = [{"bbox": legacy_box(multi[i, k])} for k in range(counts[i])]
         f = ns["get_largest_face_app"](faces, dim_max=512, dim_min=0)
         picked.append([k for k in range(counts[i]) if f is faces[k]][0])
     np.savez_compressed(os.path.join(out, "boxes.npz"), boxes=boxes, multi=multi, counts=counts.astype(np.int64),
@@ -322,7 +384,7 @@ def gen_assign_mc(ref, out):
     for tag, path, fn, widths in (("e3", E3, "generate_dynamic_targets_gender_race", (2, 4)),
                                   ("e4", E4, "generate_dynamic_targets_gender_race_age", (2, 4, 2))):
         rec = _Recorder()
-        ns = make_namespace(rec)
+        ns = make_namespace(rec, {"np": _LegacyNp()})
         compile_into(ns, lift(os.path.join(ref, path), [fn]).values())
         res = {}
         cases = [(40, 0.0, 1, 100), (24, 0.2, 1, 100), (48, 0.1, 2, 50), (33, 0.1, 4, 25), (6, 1.0, 1, 10), (1, 0.0, 1, 10),

@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fairguide.h declares; host-side
+logic (collectives over gloo with world_size 2; the no-fallback rule)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fairguide.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import fairguide
+    lib = fairguide._lib.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/fairguide.h but not exported"
+        assert s in fairguide._lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(fairguide._lib.SIGNATURES) == set(syms)
+    assert lib.fg_abi_version() == 1
+    assert b"invalid" in lib.fg_error_string(-1)
+
+
+def test_library_is_sm100a_only():
+    import fairguide
+    out = subprocess.run(["cuobjdump", "-lelf", fairguide._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback():
+    """Ops refuse CPU tensors instead of silently computing something else."""
+    import fairguide
+    with pytest.raises(RuntimeError):
+        fairguide.ops.crop_resize_fwd(torch.zeros(1, 3, 8, 8), torch.zeros(1, 4, dtype=torch.int64), None, (4, 4), None)
+    with pytest.raises(RuntimeError):
+        fairguide.generate_dynamic_targets(torch.rand(4, 2), w_uncertainty=True)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "finetune-fair-diffusion_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            for line in src.splitlines():
+                if re.match(r"\s*(from|import)\s+oracle\b", line):
+                    # the only permitted import is inside smoke_check (the oracle as checker)
+                    assert fn == "pipeline.py" and "opipe" in line, (fn, line)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import fairguide
+from fairguide import dist as fdist
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+n = 5
+x = torch.arange(n * 3, dtype=torch.float32).view(n, 3) + 100 * rank
+allx, others = fairguide.customized_all_gather(x, None, return_tensor_other_processes=True)
+assert allx.shape == (world * n, 3) and torch.equal(allx[rank * n:(rank + 1) * n], x)
+assert others.shape == ((world - 1) * n, 3) and not (others == x[0, 0]).any()
+b = torch.tensor([True, False, True, True, False]) if rank == 0 else torch.tensor([False] * 5)
+assert torch.equal(fairguide.customized_all_gather(b)[rank * n:(rank + 1) * n], b)
+class Acc: num_processes = world; local_process_index = rank; device = "cpu"
+assert torch.equal(fairguide.customized_all_gather(x, Acc()), allx)
+ind = torch.tensor([True, True, False, True, True])
+pg = torch.rand(n, 2) + rank; pr = torch.rand(n, 4) + rank
+ind_all, (pg_all, pr_all) = fdist.gather_probs(ind, [pg, pr])
+assert ind_all.shape == (world * n,) and torch.equal(pg_all[rank * n:(rank + 1) * n], pg) and torch.equal(pr_all[rank * n:(rank + 1) * n], pr)
+assert torch.equal(ind_all[rank * n:(rank + 1) * n], ind)
+c = torch.full((7, 8), rank + 1, dtype=torch.int32)
+fdist.all_reduce_counts(c)
+assert (c == sum(range(1, world + 1))).all()
+t = torch.arange(world * n); u = torch.linspace(0, 0.4, world * n)
+loc = fairguide.threshold_and_slice(t.clone(), u, 0.2, n, rank)
+assert loc.shape == (n,)
+dist.destroy_process_group()
+print("worker", rank, "ok")
+"""
+
+
+def test_collectives_gloo_world2(tmp_path):
+    port = 29000 + os.getpid() % 1000
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out

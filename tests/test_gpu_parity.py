@@ -1,0 +1,401 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Bars (BASELINE.json north_star): integer / index / target-class outputs bit-exact; crops, losses
+and gradients within 1e-3 relative in fp32 and 2e-2 in bf16 (tolerances are written at each assert).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests._golden import CROP_CASES, load, peaked_probs, procedural_image
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import fairguide
+    assert fairguide._lib.lib().fg_abi_version() == 1      # native library loaded, or the module fails
+    return fairguide
+
+
+def close(a, b, rtol, atol):
+    np.testing.assert_allclose(a.detach().float().cpu().numpy(), np.asarray(b, dtype=np.float32), rtol=rtol, atol=atol)
+
+
+# ----------------------------------------------------------------------------- boxes
+def test_boxes_golden(fg):
+    g = load("boxes")
+    boxes = torch.tensor(g["boxes"], device=DEV).view(-1, 1, 4)
+    for tag, coef, ratio in (("c05_r1", 0.5, 1), ("c11_r1", 1.1, 1), ("c05_r12", 0.5, 1.2)):
+        ind, out = fg.select_and_expand(boxes, None, 512, coef, ratio)
+        assert ind.all()
+        assert np.array_equal(out.cpu().numpy(), g["expanded_" + tag])
+    multi, counts = torch.tensor(g["multi"], device=DEV), torch.tensor(g["counts"], device=DEV, dtype=torch.int32)
+    ind, out = fg.select_and_expand(multi, counts, 512, 0.5, 1)
+    from oracle import boxes as oboxes
+    expect = np.array([oboxes.expand_bbox(g["multi"][i, g["picked"][i]], 0.5, 1) for i in range(multi.shape[0])])
+    assert np.array_equal(out.cpu().numpy(), expect)
+    assert fg.expand_bbox(g["boxes"][3], 0.5, 1) == g["expanded_c05_r1"][3].tolist()
+
+
+def test_boxes_random_and_noface(fg):
+    from oracle import boxes as oboxes
+    rng = np.random.default_rng(3)
+    n, F = 4096, 3
+    c = rng.uniform(-60, 572, size=(n, F, 2)); s = rng.uniform(4, 400, size=(n, F, 2))
+    cand = np.concatenate([c - s / 2, c + s / 2], axis=-1).astype(np.float32)
+    cand[:50] = np.round(cand[:50] * 2) / 2          # many exact .5 cases
+    counts = rng.integers(0, F + 1, size=n).astype(np.int32)
+    ind, out = fg.select_and_expand(torch.tensor(cand, device=DEV), torch.tensor(counts, device=DEV), 512)
+    ind_ref, out_ref = oboxes.select_and_expand(cand, counts, 512)
+    assert np.array_equal(ind.cpu().numpy(), ind_ref) and np.array_equal(out.cpu().numpy(), out_ref)
+
+
+# ----------------------------------------------------------------------------- crop / resize
+@pytest.mark.parametrize("idx", range(len(CROP_CASES)))
+def test_crop_face_golden(fg, idx):
+    g = load("crop")
+    seed, H, W, box, o = CROP_CASES[idx]
+    img = torch.tensor(procedural_image(seed, 3, H, W), device=DEV, requires_grad=True)
+    chip = fg.crop_face(img, list(box), [o, o], -1)
+    close(chip, g[f"chip_{idx}"], rtol=1e-3, atol=1e-5)                       # fp32 bar: 1e-3 relative
+    up = torch.tensor(procedural_image(seed + 100, 3, o, o), device=DEV)
+    (chip * up).sum().backward()
+    if H <= 128:
+        close(img.grad, g[f"grad_{idx}"], rtol=1e-3, atol=1e-5)
+    else:
+        close(img.grad[:, 192:256, 128:192], g[f"gradwin_{idx}"], rtol=1e-3, atol=1e-5)
+        s = g[f"gradsum_{idx}"]
+        assert abs(img.grad.double().sum().item() - s[0]) <= 1e-3 * s[1]
+
+
+def test_resize_small_golden(fg):
+    g = load("crop")
+    imgs = torch.tensor(procedural_image(31, 3, 512, 512)[None], device=DEV, requires_grad=True)
+    small = fg.resize_small(imgs, 224)
+    close(small[0], g["small"], rtol=1e-3, atol=1e-5)
+    up = torch.tensor(procedural_image(131, 3, 224, 224)[None], device=DEV)
+    (small * up).sum().backward()
+    close(imgs.grad[0][:, 192:256, 128:192], g["small_gradwin"], rtol=1e-3, atol=1e-5)
+
+
+def _random_boxes(rng, n, H, W):
+    c = rng.uniform(0.2 * W, 0.8 * W, size=(n, 2)); s = rng.uniform(0.1 * W, 0.9 * W, size=n)
+    b = np.stack([c[:, 0] - s / 2, c[:, 1] - s / 2, c[:, 0] + s / 2, c[:, 1] + s / 2], 1)
+    return np.rint(b).astype(np.int64)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_fused_crop_resize_and_image_grad_vs_oracle(fg, dtype, rtol):
+    from oracle import crop as ocrop, hooks as ohooks
+    rng = np.random.default_rng(5)
+    n, H, W, o = 9, 192, 192, 56
+    imgs = torch.tensor(np.stack([procedural_image(400 + i, 3, H, W) for i in range(n)])).to(dtype)
+    boxes = _random_boxes(rng, n, H, W)
+    boxes[1] = [-30, -20, 100, 110]; boxes[2] = [120, 100, 260, 240]; boxes[3] = [-40, -40, 230, 230]
+    boxes[4] = [300, 300, 400, 400]           # fully outside: defined as an all-fill chip
+    ind = np.ones(n, dtype=bool); ind[5] = False; boxes[5] = -1
+    box_ori = boxes + rng.integers(-8, 9, size=boxes.shape); box_ori[6] = -1
+    targets = [torch.tensor(rng.integers(-1, 2, size=n)), torch.tensor(rng.integers(-1, 4, size=n))]
+    preds = [torch.tensor(rng.integers(0, 2, size=n)), torch.tensor(rng.integers(0, 4, size=n))]
+    f2 = [0.2, 0.3]
+    gc = torch.tensor(rng.normal(size=(n, 3, o, o)).astype(np.float32)).to(dtype)
+    gs = torch.tensor(rng.normal(size=(n, 3, o, o)).astype(np.float32)).to(dtype)
+    # oracle (fp32 arithmetic on the same, possibly bf16-rounded, inputs)
+    x = imgs.float().clone().requires_grad_(True)
+    ok = ind.copy(); ok[4] = False
+    chips_ref = ocrop.crop_faces(x, torch.tensor(boxes), torch.tensor(ok), o, -1)
+    hooked = ohooks.apply_grad_hook_face(x, torch.where(torch.tensor(ind)[:, None], torch.tensor(boxes), torch.tensor(-1)),
+                                         torch.tensor(box_ori), targets, preds, f2)
+    small_ref = ocrop.resize_small(hooked, o)
+    ((chips_ref * gc.float()).sum() + (small_ref * gs.float()).sum()).backward()
+    # device
+    xd = imgs.to(DEV).requires_grad_(True)
+    bd, indd = torch.tensor(boxes, device=DEV), torch.tensor(ind, device=DEV)
+    region, scale, _ = fg.ops.guidance_factors(None, bd, torch.tensor(box_ori, device=DEV), [t.to(DEV) for t in targets],
+                                               [p.to(DEV) for p in preds], f2, None, False, H, W, want_weights=False)
+    chips, small = fg.crop_and_resize(xd, bd, indd, region, scale, o, o, -1)
+    atol = rtol * 1.0
+    close(chips, chips_ref.detach().numpy(), rtol, atol if dtype != torch.float32 else 1e-5)
+    close(small, small_ref.detach().numpy(), rtol, atol if dtype != torch.float32 else 1e-5)
+    (chips.float() * gc.to(DEV).float()).sum().add((small.float() * gs.to(DEV).float()).sum()).backward()
+    gref = x.grad.numpy()
+    close(xd.grad, gref, rtol, (1e-5 if dtype == torch.float32 else 2e-2) * np.abs(gref).max())
+
+
+def test_crop_adjoint_property_full_size(fg):
+    """<crop(x), g> == <x, crop_bwd(g)> at the BASELINE shapes (size-independent check of the
+    backward against the forward), plus linearity of the sampler in the image."""
+    n = 16
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.rand(n, 3, 512, 512, device=DEV, generator=gen) * 2 - 1
+    y = torch.rand(n, 3, 512, 512, device=DEV, generator=gen) * 2 - 1
+    rng = np.random.default_rng(0)
+    boxes = torch.tensor(_random_boxes(rng, n, 512, 512), device=DEV)
+    ind = torch.ones(n, dtype=torch.bool, device=DEV)
+    fwd = lambda im, fill: fg.ops.crop_resize_fwd(im, boxes, ind, (224, 224), (224, 224), fill)
+    cx, sx = fwd(x, 0.0)
+    gc = torch.randn(cx.shape, device=DEV, generator=gen); gs = torch.randn(sx.shape, device=DEV, generator=gen)
+    gi = fg.ops.image_grad(gc, gs, boxes, ind, None, None, tuple(x.shape), x.dtype, x.device)
+    lhs = (cx.double() * gc.double()).sum() + (sx.double() * gs.double()).sum()
+    rhs = (x.double() * gi.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-5 * (cx.double() * gc.double()).abs().sum().item()
+    cy, sy = fwd(y, 0.0)
+    cz, sz = fwd(0.25 * x - 1.5 * y, 0.0)
+    close(cz, (0.25 * cx - 1.5 * cy).cpu().numpy(), rtol=1e-4, atol=1e-5)
+    close(sz, (0.25 * sx - 1.5 * sy).cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- head
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_head_fwd_bwd_vs_torch(fg, dtype, rtol):
+    from oracle import head as ohead
+    torch.manual_seed(0)
+    m, d_in, d_hid, kh = 77, 960, 1280, 8
+    pooled = torch.randn(m, d_in).to(dtype)
+    w1 = (torch.randn(d_hid, d_in) / d_in ** 0.5).to(dtype); b1 = (torch.randn(d_hid) * 0.1).to(dtype)
+    w2 = (torch.randn(kh, d_hid) / d_hid ** 0.5).to(dtype); b2 = (torch.randn(kh) * 0.1).to(dtype)
+    x = pooled.float().clone().requires_grad_(True)
+    ref = ohead.mobilenet_head_reference(x, w1.float(), b1.float(), w2.float(), b2.float())
+    gl = torch.randn(m, kh)
+    (ref * gl).sum().backward()
+    xd = pooled.to(DEV).requires_grad_(True)
+    out = fg.autograd.Head.apply(xd, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
+    close(out, ref.detach().numpy(), rtol, rtol * float(ref.abs().max()))
+    (out * gl.to(DEV)).sum().backward()
+    close(xd.grad, x.grad.numpy(), rtol, rtol * float(x.grad.abs().max()))
+
+
+@pytest.mark.parametrize("tag,kind", [("e1", "gender"), ("e3", "gender_race"), ("e4", "gender_race_age")])
+def test_head_attributes_golden(fg, tag, kind):
+    g = load("heads")
+    sel = torch.tensor(g["selector"], device=DEV)
+    n = sel.shape[0]
+    stub = lambda x: torch.tensor(g[f"{tag}_logits_in"], device=DEV)
+    chips = torch.zeros(n, 1, device=DEV)
+    outs = fg.api._heads(kind, stub, chips, sel, -1)
+    for k, o in enumerate(outs):
+        ref = g[f"{tag}_sel_{k}"]
+        if o.dtype == torch.int64:
+            assert np.array_equal(o.cpu().numpy(), ref)                       # preds bit-exact
+        else:
+            close(o, ref, rtol=1e-5, atol=1e-6)
+    stub_full = lambda x: torch.tensor(g[f"{tag}_logits_in_full"], device=DEV)
+    outs = fg.api._heads(kind, stub_full, chips, None, -1)
+    for k, o in enumerate(outs):
+        ref = g[f"{tag}_nosel_{k}"]
+        assert tuple(o.shape) == ref.shape
+        if o.dtype == torch.int64:
+            assert np.array_equal(o.cpu().numpy(), ref)
+        else:
+            close(o, ref, rtol=1e-5, atol=1e-6)
+    outs = fg.api._heads(kind, stub, chips, torch.zeros(n, dtype=torch.bool, device=DEV), -1)
+    for k, o in enumerate(outs):
+        assert np.array_equal(o.cpu().numpy(), g[f"{tag}_empty_{k}"])
+
+
+def test_head_attributes_autograd(fg):
+    torch.manual_seed(1)
+    n = 13
+    sel = torch.rand(n) > 0.3
+    m = int(sel.sum())
+    lg = torch.randn(m, 6, requires_grad=True)
+    full = torch.ones(n, 6) * -1
+    full[sel] = lg
+    tg = torch.randint(0, 2, (n,)); tr = torch.randint(0, 4, (n,))
+    ref = (torch.nn.functional.cross_entropy(full[sel][:, :2], tg[sel], reduction="none").sum()
+           + torch.nn.functional.cross_entropy(full[sel][:, 2:], tr[sel], reduction="none").sum())
+    ref.backward()
+    lgd = lg.detach().to(DEV).requires_grad_(True)
+    outs = fg.api._heads("gender_race", lambda x: lgd, torch.zeros(n, 1, device=DEV), sel.to(DEV), -1)
+    face = sel.to(DEV)
+    loss = fg.fairness_ce_loss(outs[2], tg.to(DEV), face).clamp(min=0).sum() + fg.fairness_ce_loss(outs[5], tr.to(DEV), face).clamp(min=0).sum()
+    loss.backward()
+    close(lgd.grad, lg.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- fairness CE
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_fair_ce_vs_oracle(fg, dtype, rtol):
+    from oracle import loss as oloss
+    torch.manual_seed(2)
+    n, k = 257, 4
+    logits = (torch.randn(n, k) * 3).to(dtype)
+    targets = torch.randint(-1, k, (n,)); face = torch.rand(n) > 0.2
+    x = logits.float().clone().requires_grad_(True)
+    ref = oloss.fairness_ce(x, targets, face)
+    gl = torch.randn(n)
+    (ref * gl).sum().backward()
+    xd = logits.to(DEV).requires_grad_(True)
+    out = fg.fairness_ce_loss(xd, targets.to(DEV), face.to(DEV))
+    close(out, ref.detach().numpy(), rtol, rtol)
+    (out.float() * gl.to(DEV)).sum().backward()
+    close(xd.grad, x.grad.numpy(), rtol, rtol * 3)
+    assert ((out == -1).cpu() == ~(face & (targets != -1))).all()
+
+
+# ----------------------------------------------------------------------------- hooks / weights
+@pytest.mark.parametrize("tag", ["e1", "e3", "e4"])
+def test_hooks_and_weights_golden(fg, tag):
+    g = load("hooks")
+    A = {"e1": 1, "e3": 2, "e4": 3}[tag]
+    x = torch.tensor(g["images"], device=DEV, requires_grad=True)
+    args = []
+    for a in range(A):
+        args += [torch.tensor(g[f"{tag}_targets{a}"], device=DEV), torch.tensor(g[f"{tag}_preds{a}"], device=DEV),
+                 torch.full((x.shape[0], 2), 0.5, device=DEV)]
+    names = [["factor"], ["factor_gender", "factor_race"], ["factor_gender", "factor_race", "factor_age"]][A - 1]
+    f2 = dict(zip(names, g[f"{tag}_factors2"].tolist())); f1 = dict(zip(names, g[f"{tag}_factors1"].tolist()))
+    y = fg.apply_grad_hook_face(x, torch.tensor(g["box"], device=DEV), torch.tensor(g["box_ori"], device=DEV), *args, **f2)
+    assert np.array_equal(y.detach().cpu().numpy(), g[f"{tag}_forward"])              # identity forward
+    (y * torch.tensor(g["upstream"], device=DEV)).sum().backward()
+    close(x.grad, g[f"{tag}_grad"], rtol=1e-6, atol=0)
+    face = torch.tensor(~(g["box"] == -1).all(axis=1), device=DEV)
+    w = fg.gen_dynamic_weights(face, *args, **f1)
+    assert np.array_equal(w.cpu().numpy(), g[f"{tag}_weights"])
+
+
+# ----------------------------------------------------------------------------- assignment E1
+def test_assign_e1_golden(fg):
+    g = load("assign_e1")
+    for c in range(int(g["n_cases"])):
+        p = torch.tensor(g[f"probs_{c}"], device=DEV)
+        t, u = fg.generate_dynamic_targets(p, target_ratio=float(g[f"ratio_{c}"]), w_uncertainty=True)
+        assert np.array_equal(t.cpu().numpy(), g[f"targets_{c}"])                     # bit-exact targets
+        close(u, g[f"unc_{c}"], rtol=1e-5, atol=1e-7)
+        assert torch.equal(fg.generate_dynamic_targets(p, target_ratio=float(g[f"ratio_{c}"])), t)
+
+
+@pytest.mark.parametrize("n", [1000, 4096])
+def test_assign_e1_large_vs_oracle(fg, n):
+    from oracle import assign as oassign
+    rng = np.random.default_rng(n)
+    p = peaked_probs(rng, n, 2, 1.5)
+    p[rng.uniform(size=n) < 0.05] = -1
+    t_ref, u_ref = oassign.generate_dynamic_targets(torch.tensor(p), 0.5, True)
+    t, u = fg.generate_dynamic_targets(torch.tensor(p, device=DEV), 0.5, True)
+    assert torch.equal(t.cpu(), t_ref)
+    close(u, u_ref.numpy(), rtol=1e-5, atol=1e-7)
+    t_ref = t_ref.clone(); t_ref[u_ref > 0.2] = -1
+    t2, _ = fg.generate_dynamic_targets(torch.tensor(p, device=DEV), 0.5, True, uncertainty_threshold=0.2)
+    assert torch.equal(t2.cpu(), t_ref)
+
+
+# ----------------------------------------------------------------------------- assignment E3/E4
+def _problem(seed, N, K):
+    from oracle import emd as oemd
+    rng = np.random.default_rng(seed)
+    pg, pr = peaked_probs(rng, N, 2, 2.0), peaked_probs(rng, N, 4, 2.0)
+    pa = peaked_probs(rng, N, 2, 2.0) if K == 16 else None
+    return pg, pr, pa, oemd.cost_matrix_c(pg, pr, pa), rng
+
+
+@pytest.mark.parametrize("N,K", [(1, 8), (5, 8), (64, 16), (300, 8), (1024, 16), (4096, 8)])
+def test_ot_cost_and_single_solve_vs_oracle(fg, N, K):
+    from oracle import emd as oemd
+    pg, pr, pa, M, rng = _problem(N * 7 + K, N, K)
+    t = lambda a: None if a is None else torch.tensor(a, device=DEV)
+    Md = fg.ops.ot_cost_matrix(t(pg), t(pr), t(pa), N)
+    assert np.array_equal(Md.cpu().numpy(), M)                                        # fp64, bit-exact
+    q = np.full(K, 1.0 / K) if K == 8 else np.tile([0.75, 0.25], 8) / 8
+    for trial in range(3):
+        b = rng.multinomial(N, q if trial < 2 else rng.dirichlet(np.ones(K)))
+        assign, ws = fg.ops.ot_solve_single(Md, b)
+        st = ws.status()
+        assert st[0] == 0, st
+        assert np.array_equal(assign.cpu().numpy(), oemd.assign_c(M, b))              # bit-exact plan
+
+
+@pytest.mark.parametrize("tag", ["e3", "e4"])
+def test_assign_mc_golden(fg, tag):
+    """Golden vectors from the reference's own function bodies, including simulated world sizes
+    2 and 4: each rank's counts come from its own draws and are summed like the all-reduce."""
+    g = load("assign_" + tag)
+    n_attr = 2 if tag == "e3" else 3
+    K = 8 if tag == "e3" else 16
+    for c in range(int(g["n_cases"])):
+        probs = [torch.tensor(g[f"probs{k}_{c}"], device=DEV) for k in range(n_attr)]
+        world, S = int(g[f"world_{c}"]), int(g[f"S_{c}"])
+        valid = ((probs[0] != -1).all(-1) * (probs[1] != -1).all(-1))
+        nv = int(valid.sum())
+        ws = fg.ops.OtWorkspace(probs[0].shape[0], K, S, DEV)
+        total = None
+        for r in range(world if nv > 0 else 1):
+            rands = tuple(torch.tensor(g[f"rand{k}_r{r}_{c}"], device=DEV) for k in range(n_attr)) if nv > 0 else ()
+            cnt = fg.ops.ot_plan_counts(probs[0], probs[1], probs[2] if n_attr == 3 else None, rands, nv, ws)
+            assert ws.status()[0] == 0
+            total = cnt if total is None else total + cnt
+        ts, us = fg.ops.ot_targets(total, probs[0], probs[1], nv, ws, -1.0, True)
+        for a in range(n_attr):
+            assert np.array_equal(ts[a].cpu().numpy(), g[f"out{2 * a}_{c}"]), (tag, c, a)      # bit-exact targets
+            assert np.array_equal(us[a].cpu().numpy(), g[f"out{2 * a + 1}_{c}"]), (tag, c, a)  # same fp32 op order
+        # fused thresholding == reference's two lines
+        ts2, _ = fg.ops.ot_targets(total, probs[0], probs[1], nv, ws, 0.2, True)
+        for a in range(n_attr):
+            ref = g[f"out{2 * a}_{c}"].copy(); ref[g[f"out{2 * a + 1}_{c}"] > np.float32(0.2)] = -1
+            assert np.array_equal(ts2[a].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("N,kind,S", [(512, "e3", 100), (1024, "e4", 100), (4096, "e3", 16)])
+def test_assign_mc_large_vs_oracle(fg, N, kind, S):
+    from oracle import assign as oassign
+    n_attr = 2 if kind == "e3" else 3
+    K = 8 if kind == "e3" else 16
+    rng = np.random.default_rng(N)
+    probs = [peaked_probs(rng, N, w, 1.5) for w in ([2, 4] if n_attr == 2 else [2, 4, 2])]
+    miss = rng.uniform(size=N) < 0.05
+    for p in probs:
+        p[miss] = -1
+    nv = int((~miss).sum())
+    g = torch.Generator().manual_seed(N)
+    rands = tuple(torch.rand(S, nv, generator=g) for _ in range(n_attr))
+    fn = oassign.generate_dynamic_targets_gender_race if n_attr == 2 else oassign.generate_dynamic_targets_gender_race_age
+    ref = fn(*[torch.tensor(p) for p in probs], True, S, rand_tensors=rands, literal=False)
+    api_fn = fg.generate_dynamic_targets_gender_race if n_attr == 2 else fg.generate_dynamic_targets_gender_race_age
+    out = api_fn(*[torch.tensor(p, device=DEV) for p in probs], True, S, rand_tensors=tuple(r.to(DEV) for r in rands), num_valid=nv)
+    for a in range(2 * n_attr):
+        assert torch.equal(out[a].cpu(), ref[a]), (kind, N, a)
+    # plan invariants at full size: every row assigned exactly S times; column sums = summed histograms
+    outs, counts, ws = fg.api._mc_targets(tuple(torch.tensor(p, device=DEV) for p in probs), True, S,
+                                          tuple(r.to(DEV) for r in rands), nv, None, None, return_counts=True)
+    assert ws.status()[0] == 0
+    assert (counts.sum(1) == S).all()
+    hist = oassign.draw_histograms(*rands).sum(0)
+    assert np.array_equal(counts.sum(0).cpu().numpy(), hist)
+
+
+def test_assign_mc_no_valid_rows(fg):
+    pg = torch.full((6, 2), -1.0, device=DEV); pr = torch.full((6, 4), -1.0, device=DEV)
+    out = fg.generate_dynamic_targets_gender_race(pg, pr, True, 10)
+    assert all((o == -1).all() for o in out) and out[0].dtype == torch.int64 and out[1].dtype == torch.float32
+
+
+def test_epilogue_matches_torch_cuda_ops(fg):
+    """The fp32 epilogue order (E3:1536-1553) was pinned on torch-CPU sums; document here that the
+    torch-CUDA reductions the reference actually ran agree on the decisive quantity."""
+    rng = np.random.default_rng(0)
+    for K, T in ((8, 100), (8, 800), (16, 400)):
+        c = rng.multinomial(T, rng.dirichlet(np.ones(K) * 0.3, size=20000)).astype(np.int32)
+        n = c.shape[0]
+        pg = torch.rand(n, 2, device=DEV); pr = torch.rand(n, 4, device=DEV)
+        ws = fg.ops.OtWorkspace(n, K, 0, DEV)
+        cnt = torch.tensor(c, device=DEV)
+        # run compaction through plan_counts with S = 0 so the workspace holds pos[]
+        fg.ops.ot_plan_counts(pg, pr, torch.rand(n, 2, device=DEV) if K == 16 else None, (), n, ws)
+        ts, us = fg.ops.ot_targets(cnt, pg, pr, n, ws, -1.0, True)
+        tp = cnt.float(); tp = tp / tp[0, :].sum()
+        if K == 8:
+            mg = torch.cat([tp[:, :4].sum(-1, keepdim=True), tp[:, 4:].sum(-1, keepdim=True)], -1)
+        else:
+            mg = torch.cat([tp[:, :8].sum(-1, keepdim=True), tp[:, 8:].sum(-1, keepdim=True)], -1)
+        ref_u = 1 - mg.max(-1).values
+        agree = (us[0] == ref_u).float().mean().item()
+        assert agree > 0.999, agree      # informational bound; exact equality is asserted against the CPU oracle
+
+
+# ----------------------------------------------------------------------------- whole path
+def test_pipeline_smoke_vs_oracle(fg):
+    from fairguide import pipeline
+    assert pipeline.smoke_check("cuda:0")
