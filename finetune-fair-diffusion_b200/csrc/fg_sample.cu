@@ -14,6 +14,7 @@
 // job 2i+1 = chip_i.  Both jobs of an image are adjacent in block order, so the second read of
 // the image region is served by the 126 MB L2 and HBM sees each image once.
 #include "fg_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -197,6 +198,8 @@ __global__ void region_scale_kernel(const T* __restrict__ g_in, const int32_t* _
     }
 }
 
+#include "fg_sample_tiled.cuh"
+
 // ------------------------------------------------------------------------------ factors
 // python slice semantics: a negative stop counts from the end (E1:1594-1597 with a -1 box)
 __device__ __forceinline__ int slice_stop(long long stop, int size) {
@@ -276,6 +279,46 @@ extern "C" int fg_crop_resize_fwd(const void* images, int n, int C, int H, int W
     if (chips && (!boxes || chip_h <= 0 || chip_w <= 0)) return FG_ERR_INVALID_ARG;
     if (small && (small_h <= 0 || small_w <= 0)) return FG_ERR_INVALID_ARG;
     if (n == 0 || (!chips && !small)) return FG_OK;
+    {
+        // tiled path: rows must be 16-byte granular and fit the per-row shared-memory budget
+        const size_t esz = dtype == FG_F32 ? 4 : 2;
+        const size_t row_bytes = (size_t)W * esz;
+        const int slots = 2 * TOH * C;
+        const int stages = dtype == FG_F32 ? 2 : 4;
+        const size_t smem = 128 + (size_t)stages * slots * row_bytes;
+        const bool aligned = (row_bytes % 16 == 0) && ((uintptr_t)images % 16 == 0);
+        if (aligned && slots <= 32 && smem <= 100 * 1024 && getenv("FG_FORCE_GENERIC") == nullptr) {
+            FwdParams p;
+            p.images = images; p.n = n; p.C = C; p.H = H; p.W = W;
+            p.boxes = (const long long*)boxes; p.ind = indicators;
+            p.chips = chips; p.ch = chip_h; p.cw = chip_w; p.small = small; p.sh = small_h; p.sw = small_w;
+            p.fill = fill_value;
+            p.tiles_small = small ? (small_h + TOH - 1) / TOH : 0;
+            p.tiles_chip = chips ? (chip_h + TOH - 1) / TOH : 0;
+            p.total_tiles = (long long)n * (p.tiles_small + p.tiles_chip);
+            p.row_bytes = (int)row_bytes;
+            long long grid = p.total_tiles < 2LL * FG_NUM_SMS ? p.total_tiles : 2LL * FG_NUM_SMS;
+            cudaError_t e = cudaSuccess;
+            switch (dtype) {
+                case FG_F32:
+                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) sample_fwd_tiled_kernel<float, 2><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
+                    break;
+                case FG_BF16:
+                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) sample_fwd_tiled_kernel<__nv_bfloat16, 4><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
+                    break;
+                case FG_F16:
+                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) sample_fwd_tiled_kernel<__half, 4><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
+                    break;
+                default: return FG_ERR_DTYPE;
+            }
+            if (e != cudaSuccess) return (int)e;
+            FG_LAUNCH_CHECK();
+            return FG_OK;
+        }
+    }
     int txc = chips ? (chip_w + 31) / 32 : 0, tc = chips ? txc * ((chip_h + 7) / 8) : 0;
     int txs = small ? (small_w + 31) / 32 : 0, ts = small ? txs * ((small_h + 7) / 8) : 0;
     long long blocks = (long long)n * (tc + ts);
@@ -300,6 +343,40 @@ extern "C" int fg_image_grad(const void* g_chips, const void* g_small,
     if ((region == nullptr) != (scale == nullptr)) return FG_ERR_INVALID_ARG;
     if (n == 0) return FG_OK;
     if (n > 65535) return FG_ERR_LIMIT;
+    {
+        const int esz = dtype == FG_F32 ? 4 : 2;
+        const int V = 16 / esz;
+        const int owmax = (g_small ? small_w : 0) > (g_chips ? chip_w : 0) ? (g_small ? small_w : 0) : (g_chips ? chip_w : 0);
+        const size_t smem = (size_t)(2 * W + 2 * BTH) * sizeof(Tab) + (size_t)2 * C * BTH * owmax * sizeof(float);
+        const bool aligned = (W % V == 0) && ((uintptr_t)g_images % 16 == 0);
+        const bool short_ok = chip_h < 32000 && chip_w < 32000 && small_h < 32000 && small_w < 32000;
+        if (aligned && short_ok && smem <= 100 * 1024 && getenv("FG_FORCE_GENERIC") == nullptr) {
+            BwdParams p;
+            p.g_chips = g_chips; p.g_small = g_small; p.boxes = (const long long*)boxes; p.ind = indicators;
+            p.region = region; p.scale = scale; p.g_images = g_images;
+            p.n = n; p.C = C; p.H = H; p.W = W; p.ch = chip_h; p.cw = chip_w; p.sh = small_h; p.sw = small_w;
+            dim3 grid((H + BTH - 1) / BTH, n);
+            cudaError_t e = cudaSuccess;
+            switch (dtype) {
+                case FG_F32:
+                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) image_grad_tiled_kernel<float><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
+                    break;
+                case FG_BF16:
+                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) image_grad_tiled_kernel<__nv_bfloat16><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
+                    break;
+                case FG_F16:
+                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) image_grad_tiled_kernel<__half><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
+                    break;
+                default: return FG_ERR_DTYPE;
+            }
+            if (e != cudaSuccess) return (int)e;
+            FG_LAUNCH_CHECK();
+            return FG_OK;
+        }
+    }
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
     FG_DISPATCH_DTYPE(dtype, T,
         image_grad_kernel<T><<<grid, block, 0, fg_stream(stream)>>>(

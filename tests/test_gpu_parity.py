@@ -125,6 +125,34 @@ def test_fused_crop_resize_and_image_grad_vs_oracle(fg, dtype, rtol):
     close(xd.grad, gref, rtol, (1e-5 if dtype == torch.float32 else 2e-2) * np.abs(gref).max())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,W,o", [(512, 512, 224), (96, 80, 33), (77, 61, 20)])
+def test_tiled_and_generic_kernels_agree(fg, dtype, H, W, o, monkeypatch):
+    """The shared-memory-tiled kernels (used when rows are 16-byte granular) and the generic
+    kernels (any shape) implement the same sampler: outputs must agree to rounding."""
+    rng = np.random.default_rng(H)
+    n = 6
+    x = (torch.rand(n, 3, H, W, device=DEV) * 2 - 1).to(dtype)
+    boxes = torch.tensor(_random_boxes(rng, n, H, W), device=DEV)
+    boxes[0] = torch.tensor([-W // 4, -H // 5, W + 9, H + 3]); boxes[1] = torch.tensor([W // 3, H // 3, W // 3 + 5, H // 3 + 4])
+    ind = torch.tensor([True, True, True, False, True, True], device=DEV)
+    region = torch.tensor([[3, 2, W - 5, H - 7]] * n, dtype=torch.int32, device=DEV)
+    scale = torch.full((n,), 0.3, device=DEV)
+    gc = torch.randn(n, 3, o, o, device=DEV).to(dtype); gs = torch.randn(n, 3, o, o, device=DEV).to(dtype)
+    outs = []
+    for force in ("", "1"):
+        if force:
+            monkeypatch.setenv("FG_FORCE_GENERIC", "1")
+        else:
+            monkeypatch.delenv("FG_FORCE_GENERIC", raising=False)
+        c, s = fg.ops.crop_resize_fwd(x, boxes, ind, (o, o), (o, o), -1.0)
+        g = fg.ops.image_grad(gc, gs, boxes, ind, region, scale, tuple(x.shape), dtype, x.device)
+        outs.append((c.float().cpu(), s.float().cpu(), g.float().cpu()))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=tol, atol=tol * max(1.0, float(b.abs().max()))), (a - b).abs().max()
+
+
 def test_crop_adjoint_property_full_size(fg):
     """<crop(x), g> == <x, crop_bwd(g)> at the BASELINE shapes (size-independent check of the
     backward against the forward), plus linearity of the sampler in the image."""
@@ -165,7 +193,10 @@ def test_head_fwd_bwd_vs_torch(fg, dtype, rtol):
     out = fg.autograd.Head.apply(xd, w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
     close(out, ref.detach().numpy(), rtol, rtol * float(ref.abs().max()))
     (out * gl.to(DEV)).sum().backward()
-    close(xd.grad, x.grad.numpy(), rtol, rtol * float(x.grad.abs().max()))
+    # bf16: hidden activations are stored in bf16 (2^-9 relative each) before the 1280-term reduction
+    close(xd.grad, x.grad.numpy(), rtol, (1.0 if dtype == torch.float32 else 2.0) * rtol * float(x.grad.abs().max()))
+    rel = (xd.grad.float().cpu() - x.grad).norm() / x.grad.norm()
+    assert rel < rtol, rel
 
 
 @pytest.mark.parametrize("tag,kind", [("e1", "gender"), ("e3", "gender_race"), ("e4", "gender_race_age")])
@@ -391,8 +422,11 @@ def test_epilogue_matches_torch_cuda_ops(fg):
         else:
             mg = torch.cat([tp[:, :8].sum(-1, keepdim=True), tp[:, 8:].sum(-1, keepdim=True)], -1)
         ref_u = 1 - mg.max(-1).values
-        agree = (us[0] == ref_u).float().mean().item()
-        assert agree > 0.999, agree      # informational bound; exact equality is asserted against the CPU oracle
+        # Measured on B200 / torch 2.11: torch-CUDA sums 4 elements as (a0+a2)+(a1+a3) while torch-CPU
+        # (the oracle, and the golden vectors) sums left to right, so ~15-40 % of rows differ in the last
+        # ulp (tools/probe_sum_order.py).  The kernel follows the CPU order that the golden vectors pin;
+        # the values must still agree to 1 ulp with what the reference's CUDA run would produce.
+        close(us[0], ref_u.cpu().numpy(), rtol=0, atol=1.2e-7)
 
 
 # ----------------------------------------------------------------------------- whole path
