@@ -201,46 +201,57 @@ struct SolverSmem {
 // Recompute w[k][l], wi[k][l] for the classes l in `mask` by scanning the rows currently in class k.
 __device__ void rescan_class(SolverSmem& sm, const uint8_t* sigma, const double* __restrict__ M, int N, int K,
                              int k, unsigned mask) {
-    unsigned long long best[KP];
-    int besti[KP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mask &= ~(1u << k);
+    while (mask) {                                   // block-uniform; up to 4 target classes per pass
+        int ls[4]; int nl = 0;
 #pragma unroll
-    for (int l = 0; l < KP; l++) { best[l] = KEY_INF; besti[l] = 0x7fffffff; }
-    for (int i = threadIdx.x; i < N; i += SOLVER_THREADS) {
-        if (sigma[i] != k) continue;
-        const double* row = M + (size_t)i * K;
-        double mk = row[k];
+        for (int j = 0; j < 4; j++) {
+            if (mask) { ls[j] = __ffs(mask) - 1; mask &= mask - 1; nl = j + 1; } else ls[j] = ls[0];
+        }
+        double bestd[4]; int besti[4];
 #pragma unroll
-        for (int l = 0; l < KP; l++) {
-            if (l < K && ((mask >> l) & 1u)) {
-                unsigned long long key = dkey(__dsub_rn(row[l], mk));
-                if (key < best[l]) { best[l] = key; besti[l] = i; }     // rows visited in increasing order
+        for (int j = 0; j < 4; j++) { bestd[j] = INFINITY; besti[j] = 0x7fffffff; }
+        for (int i = threadIdx.x; i < N; i += SOLVER_THREADS) {
+            if (sigma[i] != k) continue;
+            const double* row = M + (size_t)i * K;
+            const double mk = row[k];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < nl) {
+                    const double d = __dsub_rn(row[ls[j]], mk);
+                    if (d < bestd[j] || besti[j] == 0x7fffffff) { bestd[j] = d; besti[j] = i; }   // rows come in increasing order
+                }
             }
         }
-    }
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int l = 0; l < KP; l++) {
-        if (!((mask >> l) & 1u)) continue;                               // block-uniform
-        unsigned hi = (unsigned)(best[l] >> 32);
-        unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-        unsigned lo = hi == mhi ? (unsigned)best[l] : 0xffffffffu;
-        unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
-        unsigned cand = (hi == mhi && lo == mlo) ? (unsigned)besti[l] : 0x7fffffffu;
-        unsigned mi = __reduce_min_sync(0xffffffffu, cand);
-        if (lane == 0) { sm.red_key[warp][l] = ((unsigned long long)mhi << 32) | mlo; sm.red_idx[warp][l] = (int)mi; }
-    }
-    __syncthreads();
-    if (threadIdx.x < KP && ((mask >> threadIdx.x) & 1u)) {
-        int l = threadIdx.x;
-        unsigned long long bk = KEY_INF; int bi = 0x7fffffff;
-        for (int wq = 0; wq < SOLVER_WARPS; wq++) {
-            unsigned long long kk = sm.red_key[wq][l]; int ii = sm.red_idx[wq][l];
-            if (kk < bk || (kk == bk && ii < bi)) { bk = kk; bi = ii; }
+        for (int j = 0; j < 4; j++) {
+            if (j >= nl) break;                        // block-uniform
+            const unsigned long long key = besti[j] == 0x7fffffff ? KEY_INF : dkey(bestd[j]);
+            const unsigned hi = (unsigned)(key >> 32);
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+            const unsigned cand = (hi == mhi && lo == mlo) ? (unsigned)besti[j] : 0x7fffffffu;
+            const unsigned mi = __reduce_min_sync(0xffffffffu, cand);
+            if (lane == 0) { sm.red_key[warp][j] = ((unsigned long long)mhi << 32) | mlo; sm.red_idx[warp][j] = (int)mi; }
         }
-        if (bi == 0x7fffffff) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
-        else { sm.w[k][l] = dunkey(bk); sm.wi[k][l] = bi; }
+        __syncthreads();
+        if (threadIdx.x < nl) {
+            const int j = threadIdx.x;
+            int l = ls[0];
+#pragma unroll
+            for (int q = 1; q < 4; q++) if (q == j) l = ls[q];
+            unsigned long long bk = KEY_INF; int bi = 0x7fffffff;
+            for (int wq = 0; wq < SOLVER_WARPS; wq++) {
+                const unsigned long long kk = sm.red_key[wq][j]; const int ii = sm.red_idx[wq][j];
+                if (kk < bk || (kk == bk && ii < bi)) { bk = kk; bi = ii; }
+            }
+            if (bi == 0x7fffffff) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
+            else { sm.w[k][l] = dunkey(bk); sm.wi[k][l] = bi; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 // warp 0: shortest path from the over-full classes to the cheapest under-full class
@@ -294,15 +305,22 @@ __device__ void find_path(SolverSmem& sm, int K) {
 // mode 1: start from sigma_in (the base assignment)
 // demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x]
 __global__ void __launch_bounds__(SOLVER_THREADS)
-ot_solve_kernel(const double* __restrict__ M, int N, int K, int mode,
+ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
                 const uint8_t* __restrict__ sigma_in, double* __restrict__ prices,
                 Demand demand_by_value, const int* __restrict__ hist,
                 uint8_t* __restrict__ sigma_out, int32_t* __restrict__ assign_out,
-                int32_t* __restrict__ counts, int* __restrict__ status, int status_slot) {
+                int32_t* __restrict__ counts, int* __restrict__ status, int status_slot, int m_in_smem) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     uint8_t* sigma = dyn_smem + sizeof(SolverSmem);
     const int tid = threadIdx.x;
+    // the cost matrix is re-read on every repair step: keep it in shared memory when it fits
+    const double* M = M_global;
+    if (m_in_smem) {
+        double* Ms = reinterpret_cast<double*>(sigma + (((size_t)N + 15) / 16) * 16);
+        for (int e = tid; e < N * K; e += SOLVER_THREADS) Ms[e] = M_global[e];
+        M = Ms;
+    }
 
     if (tid < KP) {
         sm.cnt[tid] = 0;
@@ -566,10 +584,18 @@ rank_split_kernel(const T* __restrict__ probs, int n_all, double ratio, float th
     if (unc) unc[i] = from_f32<T>(uf);
 }
 
-static int solver_smem_bytes(int N) { return (int)(sizeof(SolverSmem) + fg_align_up((size_t)N, 16)); }
+// shared memory of one solver CTA: control block + assignment bytes (+ the cost matrix when it fits)
+static bool solver_m_fits(int N, int K) {
+    return sizeof(SolverSmem) + fg_align_up((size_t)N, 16) + (size_t)N * K * sizeof(double) <= 200 * 1024;
+}
+static int solver_smem_bytes(int N, int K) {
+    size_t b = sizeof(SolverSmem) + fg_align_up((size_t)N, 16);
+    if (solver_m_fits(N, K)) b += (size_t)N * K * sizeof(double);
+    return (int)b;
+}
 
-static int solver_prepare(int N) {
-    int bytes = solver_smem_bytes(N);
+static int solver_prepare(int N, int K) {
+    int bytes = solver_smem_bytes(N, K);
     if (bytes > 227 * 1024) return FG_ERR_LIMIT;
     if (bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -594,7 +620,7 @@ static void expected_demand(int n, int K, Demand* d) {
 
 // base assignment: coarse-to-fine over growing prefixes, each level warm-started by the previous prices
 static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) {
-    int rc = solver_prepare(N);
+    int rc = solver_prepare(N, K);
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(w.prices, 0, KP * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
@@ -605,8 +631,9 @@ static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) 
         int n = levels[q];
         Demand d; expected_demand(n, K, &d);
         bool last = q == nl - 1;
-        ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n), st>>>(M, n, K, 0, nullptr, w.prices, d, nullptr,
-                                                                         last ? w.sigma0 : nullptr, nullptr, nullptr, w.status, 2);
+        ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, 0, nullptr, w.prices, d, nullptr,
+                                                                            last ? w.sigma0 : nullptr, nullptr, nullptr, w.status, 2,
+                                                                            solver_m_fits(n, K) ? 1 : 0);
         FG_LAUNCH_CHECK();
     }
     return FG_OK;
@@ -647,8 +674,9 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int rc = launch_base(w.M, n_valid, K, w, st);
     if (rc) return rc;
     Demand none = {};
-    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid), st>>>(w.M, n_valid, K, 1, w.sigma0, nullptr, none, w.hist,
-                                                                          nullptr, nullptr, counts, w.status, 3);
+    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, n_valid, K, 1, w.sigma0, nullptr, none, w.hist,
+                                                                             nullptr, nullptr, counts, w.status, 3,
+                                                                             solver_m_fits(n_valid, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -684,8 +712,8 @@ extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* 
     if (e != cudaSuccess) return (int)e;
     int rc = launch_base(M, n, K, w, st);      // exercises the coarse-to-fine path as well
     if (rc) return rc;
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n), st>>>(M, n, K, 1, w.sigma0, nullptr, d, nullptr, nullptr, assign,
-                                                                      nullptr, w.status, 3);
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, 1, w.sigma0, nullptr, d, nullptr, nullptr, assign,
+                                                                         nullptr, w.status, 3, solver_m_fits(n, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

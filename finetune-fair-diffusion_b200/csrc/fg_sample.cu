@@ -268,6 +268,76 @@ __global__ void factors_kernel(const uint8_t* __restrict__ face, const long long
     }
 }
 
+// ------------------------------------------------------------------------------ tiled launches
+constexpr int FG_NOT_TILED = 0x7ffffff0;     // shape not covered by the tiled kernels: use the generic ones
+
+template <typename T, int STAGES>
+static int launch_fwd_tiled_t(const FwdParams& p, size_t smem, unsigned grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<T, 3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    sample_fwd_tiled_kernel<T, 3, STAGES><<<grid, FWD_THREADS, smem, st>>>(p);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, const int64_t* boxes, const uint8_t* indicators,
+                            void* chips, int chip_h, int chip_w, void* small, int small_h, int small_w,
+                            float fill_value, int dtype, cudaStream_t st) {
+    const size_t esz = dtype == FG_F32 ? 4 : 2;
+    const size_t row_bytes = (size_t)W * esz;
+    const int stages = dtype == FG_F32 ? 2 : 4;
+    const size_t meta = ((size_t)stages * sizeof(FwdMeta) + 127) / 128 * 128;
+    const size_t smem = 128 + meta + (size_t)stages * 2 * TOH * 3 * row_bytes;
+    FwdParams p;
+    p.tiles_small = small ? (small_h + TOH - 1) / TOH : 0;
+    p.tiles_chip = chips ? (chip_h + TOH - 1) / TOH : 0;
+    const long long total = (long long)n * (p.tiles_small + p.tiles_chip);
+    const bool ok = C == 3 && (row_bytes % 16 == 0) && ((uintptr_t)images % 16 == 0) && smem <= 110 * 1024 && total < 0x7fffffffLL;
+    if (!ok) return FG_NOT_TILED;
+    p.images = images; p.n = n; p.C = C; p.H = H; p.W = W;
+    p.boxes = (const long long*)boxes; p.ind = indicators;
+    p.chips = chips; p.ch = chip_h; p.cw = chip_w; p.small = small; p.sh = small_h; p.sw = small_w;
+    p.fill = fill_value; p.total_tiles = (int)total;
+    const unsigned grid = (unsigned)(total < 2LL * FG_NUM_SMS ? total : 2LL * FG_NUM_SMS);   // persistent, 2 CTAs per SM
+    switch (dtype) {
+        case FG_F32: return launch_fwd_tiled_t<float, 2>(p, smem, grid, st);
+        case FG_BF16: return launch_fwd_tiled_t<__nv_bfloat16, 4>(p, smem, grid, st);
+        case FG_F16: return launch_fwd_tiled_t<__half, 4>(p, smem, grid, st);
+        default: return FG_ERR_DTYPE;
+    }
+}
+
+template <typename T>
+static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(image_grad_tiled_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    image_grad_tiled_kernel<T, 3><<<grid, 256, smem, st>>>(p, owp);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+static int launch_bwd_tiled(const void* g_chips, const void* g_small, const int64_t* boxes, const uint8_t* indicators,
+                            const int32_t* region, const float* scale, void* g_images, int n, int C, int H, int W,
+                            int chip_h, int chip_w, int small_h, int small_w, int dtype, cudaStream_t st) {
+    const int sw = g_small ? small_w : 0, cw = g_chips ? chip_w : 0;
+    const int owp = (sw > cw ? sw : cw) + TPAD;
+    const size_t smem = (size_t)2 * BSUB * BTH * sizeof(Tab) + (size_t)2 * 3 * BTH * owp * sizeof(float);
+    const bool ok = C == 3 && W <= 512 && (W % 2 == 0) && ((uintptr_t)g_images % 16 == 0) && smem <= 100 * 1024 &&
+                    (!g_small || (small_w <= W && small_h <= H));
+    if (!ok) return FG_NOT_TILED;
+    BwdParams p;
+    p.g_chips = g_chips; p.g_small = g_small; p.boxes = (const long long*)boxes; p.ind = indicators;
+    p.region = region; p.scale = scale; p.g_images = g_images;
+    p.n = n; p.C = C; p.H = H; p.W = W; p.ch = chip_h; p.cw = chip_w; p.sh = small_h; p.sw = small_w;
+    dim3 grid((H + BSUB * BTH - 1) / (BSUB * BTH), n);
+    switch (dtype) {
+        case FG_F32: return launch_bwd_tiled_t<float>(p, owp, smem, grid, st);
+        case FG_BF16: return launch_bwd_tiled_t<__nv_bfloat16>(p, owp, smem, grid, st);
+        case FG_F16: return launch_bwd_tiled_t<__half>(p, owp, smem, grid, st);
+        default: return FG_ERR_DTYPE;
+    }
+}
+
 }  // namespace
 
 extern "C" int fg_crop_resize_fwd(const void* images, int n, int C, int H, int W,
@@ -279,45 +349,10 @@ extern "C" int fg_crop_resize_fwd(const void* images, int n, int C, int H, int W
     if (chips && (!boxes || chip_h <= 0 || chip_w <= 0)) return FG_ERR_INVALID_ARG;
     if (small && (small_h <= 0 || small_w <= 0)) return FG_ERR_INVALID_ARG;
     if (n == 0 || (!chips && !small)) return FG_OK;
-    {
-        // tiled path: rows must be 16-byte granular and fit the per-row shared-memory budget
-        const size_t esz = dtype == FG_F32 ? 4 : 2;
-        const size_t row_bytes = (size_t)W * esz;
-        const int slots = 2 * TOH * C;
-        const int stages = dtype == FG_F32 ? 2 : 4;
-        const size_t smem = 128 + (size_t)stages * slots * row_bytes;
-        const bool aligned = (row_bytes % 16 == 0) && ((uintptr_t)images % 16 == 0);
-        if (aligned && slots <= 32 && smem <= 100 * 1024 && getenv("FG_FORCE_GENERIC") == nullptr) {
-            FwdParams p;
-            p.images = images; p.n = n; p.C = C; p.H = H; p.W = W;
-            p.boxes = (const long long*)boxes; p.ind = indicators;
-            p.chips = chips; p.ch = chip_h; p.cw = chip_w; p.small = small; p.sh = small_h; p.sw = small_w;
-            p.fill = fill_value;
-            p.tiles_small = small ? (small_h + TOH - 1) / TOH : 0;
-            p.tiles_chip = chips ? (chip_h + TOH - 1) / TOH : 0;
-            p.total_tiles = (long long)n * (p.tiles_small + p.tiles_chip);
-            p.row_bytes = (int)row_bytes;
-            long long grid = p.total_tiles < 2LL * FG_NUM_SMS ? p.total_tiles : 2LL * FG_NUM_SMS;
-            cudaError_t e = cudaSuccess;
-            switch (dtype) {
-                case FG_F32:
-                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) sample_fwd_tiled_kernel<float, 2><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
-                    break;
-                case FG_BF16:
-                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) sample_fwd_tiled_kernel<__nv_bfloat16, 4><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
-                    break;
-                case FG_F16:
-                    e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) sample_fwd_tiled_kernel<__half, 4><<<(unsigned)grid, FWD_THREADS, smem, fg_stream(stream)>>>(p);
-                    break;
-                default: return FG_ERR_DTYPE;
-            }
-            if (e != cudaSuccess) return (int)e;
-            FG_LAUNCH_CHECK();
-            return FG_OK;
-        }
+    if (getenv("FG_FORCE_GENERIC") == nullptr) {
+        int rc = launch_fwd_tiled(images, n, C, H, W, boxes, indicators, chips, chip_h, chip_w, small, small_h, small_w,
+                                  fill_value, dtype, fg_stream(stream));
+        if (rc != FG_NOT_TILED) return rc;
     }
     int txc = chips ? (chip_w + 31) / 32 : 0, tc = chips ? txc * ((chip_h + 7) / 8) : 0;
     int txs = small ? (small_w + 31) / 32 : 0, ts = small ? txs * ((small_h + 7) / 8) : 0;
@@ -343,39 +378,10 @@ extern "C" int fg_image_grad(const void* g_chips, const void* g_small,
     if ((region == nullptr) != (scale == nullptr)) return FG_ERR_INVALID_ARG;
     if (n == 0) return FG_OK;
     if (n > 65535) return FG_ERR_LIMIT;
-    {
-        const int esz = dtype == FG_F32 ? 4 : 2;
-        const int V = 16 / esz;
-        const int owmax = (g_small ? small_w : 0) > (g_chips ? chip_w : 0) ? (g_small ? small_w : 0) : (g_chips ? chip_w : 0);
-        const size_t smem = (size_t)(2 * W + 2 * BTH) * sizeof(Tab) + (size_t)2 * C * BTH * owmax * sizeof(float);
-        const bool aligned = (W % V == 0) && ((uintptr_t)g_images % 16 == 0);
-        const bool short_ok = chip_h < 32000 && chip_w < 32000 && small_h < 32000 && small_w < 32000;
-        if (aligned && short_ok && smem <= 100 * 1024 && getenv("FG_FORCE_GENERIC") == nullptr) {
-            BwdParams p;
-            p.g_chips = g_chips; p.g_small = g_small; p.boxes = (const long long*)boxes; p.ind = indicators;
-            p.region = region; p.scale = scale; p.g_images = g_images;
-            p.n = n; p.C = C; p.H = H; p.W = W; p.ch = chip_h; p.cw = chip_w; p.sh = small_h; p.sw = small_w;
-            dim3 grid((H + BTH - 1) / BTH, n);
-            cudaError_t e = cudaSuccess;
-            switch (dtype) {
-                case FG_F32:
-                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) image_grad_tiled_kernel<float><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
-                    break;
-                case FG_BF16:
-                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) image_grad_tiled_kernel<__nv_bfloat16><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
-                    break;
-                case FG_F16:
-                    e = cudaFuncSetAttribute(image_grad_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) image_grad_tiled_kernel<__half><<<grid, 256, smem, fg_stream(stream)>>>(p, owmax);
-                    break;
-                default: return FG_ERR_DTYPE;
-            }
-            if (e != cudaSuccess) return (int)e;
-            FG_LAUNCH_CHECK();
-            return FG_OK;
-        }
+    if (getenv("FG_FORCE_GENERIC") == nullptr) {
+        int rc = launch_bwd_tiled(g_chips, g_small, boxes, indicators, region, scale, g_images, n, C, H, W,
+                                  chip_h, chip_w, small_h, small_w, dtype, fg_stream(stream));
+        if (rc != FG_NOT_TILED) return rc;
     }
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, n);
     FG_DISPATCH_DTYPE(dtype, T,

@@ -1,29 +1,32 @@
 // Tiled, shared-memory-staged versions of the two HBM-bound kernels.  Included by fg_sample.cu
-// inside its anonymous namespace (uses Axis / axis_index / Box / load_box / candidates / axis_weight).
+// inside its anonymous namespace (uses Axis / axis_index / Box / load_box / axis_weight / gather_grid).
 //
 // FORWARD  sample_fwd_tiled_kernel
 //   Persistent CTAs, 8 warps: warps 0-6 compute, warp 7 produces.  A tile is TOH = 4 output rows of
 //   one job (small_i or chip_i), full output width, all channels.  An output row needs exactly two
 //   source rows (i0, i1), so a tile needs 2*TOH*C row segments; the producer warp fetches each with
 //   one bulk async copy (cp.async.bulk global->shared, completion on an mbarrier; UBLKCP in SASS)
-//   into a STAGES-deep ring, so the HBM reads of tile k+1.. overlap the arithmetic of tile k.  Rows
-//   keep their absolute x position in shared memory; pixels outside the image are detected from
-//   coordinates and read `fill`.  Tiles are numbered image-major with small_i and chip_i adjacent,
-//   so the second pass over an image's pixels hits L2.
+//   into a STAGES-deep ring, so the HBM reads of tiles k+1.. overlap the arithmetic of tile k.  The
+//   producer also decodes the tile (image, box, scales, row taps) once and hands that to the consumers
+//   through shared memory.  Rows keep their absolute x position in shared memory; pixels outside the
+//   image are detected from coordinates and read `fill`.  Tiles are numbered image-major with small_i
+//   and chip_i adjacent, so the second pass over an image's pixels hits L2.
 //
 // BACKWARD  image_grad_tiled_kernel
-//   One CTA per (image, 8 source rows), all columns and channels.  Bilinear resampling is separable,
-//   so the gather runs in two stages through shared memory:
+//   One CTA per (image, 32 source rows), processed as 4 sub-tiles of 8 rows.  Bilinear resampling is
+//   separable, so the gather runs in two stages through shared memory:
 //     stage 1 (vertical)   t[g][c][r][ox] = sum_oy wy(oy, y_r) * G_g[c][oy][ox]      coalesced G reads
 //     stage 2 (horizontal) out[c][y_r][x] = s(x,y) * sum_ox wx_s * t_small + sum_ox wx_c * t_chip
-//   with per-CTA tables of (first output index, count, weights) per source x and per source row,
-//   built with the exact forward index function.  Every image-gradient element is written once with
-//   16-byte stores; no atomics, so the result is run-to-run deterministic.
+//   A thread owns two adjacent image columns for the whole CTA: their tap tables (first output index,
+//   up to 4 weights, built with the exact forward index function) live in registers and are reused
+//   for 32 rows x 3 channels.  Every image-gradient element is written exactly once; no atomics, so
+//   the result is run-to-run deterministic.
 #pragma once
 
 constexpr int TOH = 4;                      // output rows per forward tile
 constexpr int FWD_CONSUMER_WARPS = 7;       // 224 threads = one 224-wide output row per pass
-constexpr int FWD_THREADS = (FWD_CONSUMER_WARPS + 1) * 32;
+constexpr int FWD_CONSUMERS = FWD_CONSUMER_WARPS * 32;
+constexpr int FWD_THREADS = FWD_CONSUMERS + 32;
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,41 +60,35 @@ struct FwdParams {
     void* small; int sh, sw;
     float fill;
     int tiles_small, tiles_chip;      // row tiles per job
-    long long total_tiles;
-    int row_bytes;                    // W * sizeof(T), multiple of 16
+    int total_tiles;
 };
 
-struct FwdTile {
-    int img, oy0, oh, ow;
-    bool is_small;
-    Box b;
+// one per ring stage: written by the producer (lane 0) before it arrives on `full`
+struct __align__(16) FwdMeta {
+    int ok;                 // 0: the whole tile is `fill`
+    int inside;             // 1: every tap of the tile lies inside the image
+    int x0, bw;
+    float sx;
+    int rows;               // valid output rows in this tile (<= TOH)
+    int ow;
+    int out_row_stride;     // = ow
+    long long out_plane;    // = oh * ow
+    unsigned long long out; // pointer to out[img][0][oy0][0]
+    int ya[TOH], yb[TOH];   // absolute image rows of the two taps
+    float l0[TOH], l1[TOH];
 };
 
-__device__ __forceinline__ FwdTile decode_tile(const FwdParams& p, long long t) {
-    FwdTile f;
-    int per_image = p.tiles_small + p.tiles_chip;
-    f.img = (int)(t / per_image);
-    int r = (int)(t - (long long)f.img * per_image);
-    f.is_small = r < p.tiles_small;
-    if (f.is_small) {
-        f.oy0 = r * TOH; f.oh = p.sh; f.ow = p.sw;
-        f.b.x0 = 0; f.b.y0 = 0; f.b.x1 = p.W; f.b.y1 = p.H; f.b.ok = true;
-    } else {
-        f.oy0 = (r - p.tiles_small) * TOH; f.oh = p.ch; f.ow = p.cw;
-        f.b = load_box(p.boxes, p.ind, f.img, p.H, p.W);
-    }
-    return f;
-}
-
-template <typename T, int STAGES>
+template <typename T, int C, int STAGES>
 __global__ void __launch_bounds__(FWD_THREADS)
 sample_fwd_tiled_kernel(const FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + STAGES;
-    uint8_t* ring = smem + 128;
-    const int slots = 2 * TOH * p.C;
-    const int stage_bytes = slots * p.row_bytes;
+    FwdMeta* meta = reinterpret_cast<FwdMeta*>(smem + 128);
+    uint8_t* ring = smem + 128 + ((STAGES * sizeof(FwdMeta) + 127) / 128) * 128;
+    constexpr int SLOTS = 2 * TOH * C;
+    const int W = p.W;
+    const int stage_elems = SLOTS * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -101,41 +98,61 @@ sample_fwd_tiled_kernel(const FwdParams p) {
     __syncthreads();
 
     const T* images = reinterpret_cast<const T*>(p.images);
-    const size_t iplane = (size_t)p.H * p.W;
+    const size_t iplane = (size_t)p.H * W;
     constexpr int EPV = 16 / (int)sizeof(T);          // elements per 16 bytes
+    const int per_image = p.tiles_small + p.tiles_chip;
 
     if (warp == FWD_CONSUMER_WARPS) {
         // ------------------------------------------------------------------ producer warp
         int k = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
-            int s = k % STAGES;
-            uint32_t ph = (uint32_t)((k / STAGES) & 1);
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
+            const int s = k % STAGES;
+            const uint32_t ph = (uint32_t)((k / STAGES) & 1);
             if (k >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
-            FwdTile f = decode_tile(p, t);
-            uint32_t bytes = 0; const T* src = nullptr; uint8_t* dst = nullptr;
-            if (f.b.ok && lane < slots) {
-                int c = lane / (2 * TOH), slot = lane - c * 2 * TOH;
-                int r = slot >> 1, which = slot & 1;
-                int oy = f.oy0 + r;
-                if (oy < f.oh) {
-                    int bw = f.b.x1 - f.b.x0, bh = f.b.y1 - f.b.y0;
-                    Axis ay = axis_index(oy, (float)bh / (float)f.oh, bh);
-                    int yy = f.b.y0 + (which ? ay.i1 : ay.i0);
-                    Axis a0 = axis_index(0, (float)bw / (float)f.ow, bw);
-                    Axis a1 = axis_index(f.ow - 1, (float)bw / (float)f.ow, bw);
-                    int xs = f.b.x0 + a0.i0, xe = f.b.x0 + a1.i1 + 1;
-                    xs = xs < 0 ? 0 : xs; xe = xe > p.W ? p.W : xe;
-                    xs = (xs / EPV) * EPV; xe = ((xe + EPV - 1) / EPV) * EPV;
-                    if (xe > p.W) xe = p.W;                     // W*sizeof(T) is a multiple of 16
-                    if (yy >= 0 && yy < p.H && xe > xs) {
-                        bytes = (uint32_t)(xe - xs) * sizeof(T);
-                        src = images + ((size_t)f.img * p.C + c) * iplane + (size_t)yy * p.W + xs;
-                        dst = ring + (size_t)s * stage_bytes + (size_t)lane * p.row_bytes + (size_t)xs * sizeof(T);
-                    }
+            // decode (all lanes, uniform)
+            const int img = t / per_image;
+            const int rt = t - img * per_image;
+            const bool is_small = rt < p.tiles_small;
+            Box b; int oy0, oh, ow;
+            if (is_small) { oy0 = rt * TOH; oh = p.sh; ow = p.sw; b.x0 = 0; b.y0 = 0; b.x1 = W; b.y1 = p.H; b.ok = true; }
+            else { oy0 = (rt - p.tiles_small) * TOH; oh = p.ch; ow = p.cw; b = load_box(p.boxes, p.ind, img, p.H, W); }
+            const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
+            const float sx = (float)bw / (float)ow, sy = (float)bh / (float)oh;
+            const int rows = min(TOH, oh - oy0);
+            // this lane's row tap: lane -> (c, r, which)
+            uint32_t bytes = 0; const T* src = nullptr; T* dst = nullptr;
+            Axis ay; ay.i0 = ay.i1 = 0; ay.l0 = ay.l1 = 0.f;
+            const int c = lane / (2 * TOH), slot = lane - c * 2 * TOH, r = slot >> 1, which = slot & 1;
+            if (b.ok && lane < SLOTS && r < rows) {
+                ay = axis_index(oy0 + r, sy, bh);
+                const int yy = b.y0 + (which ? ay.i1 : ay.i0);
+                Axis a0 = axis_index(0, sx, bw), a1 = axis_index(ow - 1, sx, bw);
+                int xs = b.x0 + a0.i0, xe = b.x0 + a1.i1 + 1;
+                xs = xs < 0 ? 0 : xs; xe = xe > W ? W : xe;
+                xs = (xs / EPV) * EPV; xe = ((xe + EPV - 1) / EPV) * EPV;
+                if (xe > W) xe = W;                         // W*sizeof(T) is a multiple of 16
+                if (yy >= 0 && yy < p.H && xe > xs) {
+                    bytes = (uint32_t)(xe - xs) * sizeof(T);
+                    src = images + ((size_t)img * C + c) * iplane + (size_t)yy * W + xs;
+                    dst = reinterpret_cast<T*>(ring) + (size_t)s * stage_elems + (size_t)lane * W + xs;
                 }
+            }
+            // metadata: lanes 0,2,4,6 (c = 0, which = 0) hold the row taps of rows 0..3
+            FwdMeta& m = meta[s];
+            if (lane < 2 * TOH && which == 0) {
+                m.ya[r] = b.y0 + ay.i0; m.yb[r] = b.y0 + ay.i1; m.l0[r] = ay.l0; m.l1[r] = ay.l1;
+            }
+            if (lane == 0) {
+                m.ok = b.ok ? 1 : 0;
+                m.inside = (b.x0 >= 0 && b.y0 >= 0 && b.x1 <= W && b.y1 <= p.H) ? 1 : 0;
+                m.x0 = b.x0; m.bw = bw; m.sx = sx; m.rows = rows; m.ow = ow; m.out_row_stride = ow;
+                m.out_plane = (long long)oh * ow;
+                T* base = reinterpret_cast<T*>(is_small ? p.small : p.chips) + ((size_t)img * C * oh + oy0) * ow;
+                m.out = reinterpret_cast<unsigned long long>(base);
             }
             uint32_t total = bytes;
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            __syncwarp();                                    // metadata stores precede the arrive
             if (lane == 0) mbar_arrive_expect_tx(&full[s], total);
             __syncwarp();
             if (bytes) bulk_g2s(dst, src, bytes, &full[s]);
@@ -143,45 +160,69 @@ sample_fwd_tiled_kernel(const FwdParams p) {
     } else {
         // ------------------------------------------------------------------ consumer warps
         const int ctid = threadIdx.x;                  // 0..223
+        const float fill = p.fill;
         int k = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
-            int s = k % STAGES;
-            uint32_t ph = (uint32_t)((k / STAGES) & 1);
-            FwdTile f = decode_tile(p, t);
-            T* out = reinterpret_cast<T*>(f.is_small ? p.small : p.chips) + (size_t)f.img * p.C * f.oh * f.ow;
-            const size_t oplane = (size_t)f.oh * f.ow;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
+            const int s = k % STAGES;
+            const uint32_t ph = (uint32_t)((k / STAGES) & 1);
             mbar_wait(&full[s], ph);
-            if (!f.b.ok) {
-                T fv = from_f32<T>(p.fill);
-                for (int ox = ctid; ox < f.ow; ox += FWD_CONSUMER_WARPS * 32)
-                    for (int r = 0; r < TOH; r++)
-                        if (f.oy0 + r < f.oh)
-                            for (int c = 0; c < p.C; c++) out[c * oplane + (size_t)(f.oy0 + r) * f.ow + ox] = fv;
-            } else {
-                const int bw = f.b.x1 - f.b.x0, bh = f.b.y1 - f.b.y0;
-                const float sx = (float)bw / (float)f.ow, sy = (float)bh / (float)f.oh;
-                const uint8_t* st = ring + (size_t)s * stage_bytes;
-                for (int ox = ctid; ox < f.ow; ox += FWD_CONSUMER_WARPS * 32) {
-                    Axis ax = axis_index(ox, sx, bw);
-                    int xa = f.b.x0 + ax.i0, xb = f.b.x0 + ax.i1;
-                    bool xa_in = xa >= 0 && xa < p.W, xb_in = xb >= 0 && xb < p.W;
+            const FwdMeta& m = meta[s];
+            T* out = reinterpret_cast<T*>(m.out);
+            const int ow = m.ow, rows = m.rows;
+            const long long oplane = m.out_plane;
+            if (!m.ok) {
+                const T fv = from_f32<T>(fill);
+                for (int ox = ctid; ox < ow; ox += FWD_CONSUMERS)
+                    for (int r = 0; r < rows; r++)
 #pragma unroll
-                    for (int r = 0; r < TOH; r++) {
-                        int oy = f.oy0 + r;
-                        if (oy >= f.oh) break;
-                        Axis ay = axis_index(oy, sy, bh);
-                        int ya = f.b.y0 + ay.i0, yb = f.b.y0 + ay.i1;
-                        bool ya_in = ya >= 0 && ya < p.H, yb_in = yb >= 0 && yb < p.H;
-                        for (int c = 0; c < p.C; c++) {
-                            const T* ra = reinterpret_cast<const T*>(st + (size_t)(c * 2 * TOH + 2 * r) * p.row_bytes);
-                            const T* rb = reinterpret_cast<const T*>(st + (size_t)(c * 2 * TOH + 2 * r + 1) * p.row_bytes);
-                            float v00 = (ya_in && xa_in) ? to_f32(ra[xa]) : p.fill;
-                            float v01 = (ya_in && xb_in) ? to_f32(ra[xb]) : p.fill;
-                            float v10 = (yb_in && xa_in) ? to_f32(rb[xa]) : p.fill;
-                            float v11 = (yb_in && xb_in) ? to_f32(rb[xb]) : p.fill;
-                            float top = ax.l0 * v00 + ax.l1 * v01;
-                            float bot = ax.l0 * v10 + ax.l1 * v11;
-                            out[c * oplane + (size_t)oy * f.ow + ox] = from_f32<T>(ay.l0 * top + ay.l1 * bot);
+                        for (int c = 0; c < C; c++) out[c * oplane + r * ow + ox] = fv;
+            } else {
+                const T* st = reinterpret_cast<const T*>(ring) + (size_t)s * stage_elems;
+                const int x0 = m.x0, bw = m.bw;
+                const float sx = m.sx;
+                if (m.inside) {
+                    for (int ox = ctid; ox < ow; ox += FWD_CONSUMERS) {
+                        const Axis ax = axis_index(ox, sx, bw);
+                        const int xa = x0 + ax.i0, xb = x0 + ax.i1;
+#pragma unroll
+                        for (int r = 0; r < TOH; r++) {
+                            if (r < rows) {
+                                const float l0 = m.l0[r], l1 = m.l1[r];
+#pragma unroll
+                                for (int c = 0; c < C; c++) {
+                                    const T* ra = st + (c * 2 * TOH + 2 * r) * W;
+                                    const T* rb = ra + W;
+                                    const float top = ax.l0 * to_f32(ra[xa]) + ax.l1 * to_f32(ra[xb]);
+                                    const float bot = ax.l0 * to_f32(rb[xa]) + ax.l1 * to_f32(rb[xb]);
+                                    out[c * oplane + r * ow + ox] = from_f32<T>(l0 * top + l1 * bot);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int ox = ctid; ox < ow; ox += FWD_CONSUMERS) {
+                        const Axis ax = axis_index(ox, sx, bw);
+                        const int xa = x0 + ax.i0, xb = x0 + ax.i1;
+                        const bool xa_in = xa >= 0 && xa < W, xb_in = xb >= 0 && xb < W;
+#pragma unroll
+                        for (int r = 0; r < TOH; r++) {
+                            if (r < rows) {
+                                const float l0 = m.l0[r], l1 = m.l1[r];
+                                const int ya = m.ya[r], yb = m.yb[r];
+                                const bool ya_in = ya >= 0 && ya < p.H, yb_in = yb >= 0 && yb < p.H;
+#pragma unroll
+                                for (int c = 0; c < C; c++) {
+                                    const T* ra = st + (c * 2 * TOH + 2 * r) * W;
+                                    const T* rb = ra + W;
+                                    const float v00 = (ya_in && xa_in) ? to_f32(ra[xa]) : fill;
+                                    const float v01 = (ya_in && xb_in) ? to_f32(ra[xb]) : fill;
+                                    const float v10 = (yb_in && xa_in) ? to_f32(rb[xa]) : fill;
+                                    const float v11 = (yb_in && xb_in) ? to_f32(rb[xb]) : fill;
+                                    const float top = ax.l0 * v00 + ax.l1 * v01;
+                                    const float bot = ax.l0 * v10 + ax.l1 * v11;
+                                    out[c * oplane + r * ow + ox] = from_f32<T>(l0 * top + l1 * bot);
+                                }
+                            }
                         }
                     }
                 }
@@ -193,34 +234,48 @@ sample_fwd_tiled_kernel(const FwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------- backward
-constexpr int BTH = 8;            // source rows per CTA
-constexpr int TABW = 3;           // weights kept per table entry; longer runs take the generic path
+constexpr int BTH = 8;            // source rows per sub-tile
+constexpr int BSUB = 4;           // sub-tiles per CTA
+constexpr int TABW = 4;           // tap weights kept per table entry
+constexpr int TPAD = 4;           // padding of the t rows so that lo + TABW - 1 stays in the row
 
-struct __align__(16) Tab {
-    short lo;      // first contributing output index
-    short n;       // number of contributing outputs (lo .. lo+n-1); 0 = none
+struct Tab {
+    int lo;        // first contributing output index
+    int n;         // number of contributing outputs; 0 = none; > TABW = too many for the fast path
     float w[TABW];
 };
 
-// contributions of an output axis (out_size samples of an in_size-long virtual box) to box coordinate p
+// Outputs of an axis (out_size samples of an in_size-long virtual box) whose 2-tap footprint covers box
+// coordinate p:  exactly those with i0(o) in {p-1, p}; contiguous because i0 is monotone in o.
 __device__ __forceinline__ Tab make_tab(int p, float scale, int in_size, int out_size) {
-    Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = 0.f;
+    Tab t; t.lo = 0; t.n = 0;
+#pragma unroll
+    for (int q = 0; q < TABW; q++) t.w[q] = 0.f;
     if (p < 0 || p >= in_size) return t;
-    Span s = candidates(p, scale, out_size);
-    int first = -1, last = -1;
-    for (int o = s.lo; o <= s.hi; o++) {
-        float w = axis_weight(o, p, scale, in_size);
-        if (w != 0.f) { if (first < 0) first = o; last = o; }
+    int o = (int)floorf(((float)p - 0.5f) / scale - 0.5f) - 2;
+    o = o < 0 ? 0 : o;
+    while (o < out_size && axis_index(o, scale, in_size).i0 < p - 1) o++;
+    int n = 0, first = -1;
+    for (; o < out_size; o++) {
+        Axis a = axis_index(o, scale, in_size);
+        if (a.i0 > p) break;
+        float w = (a.i0 == p ? a.l0 : 0.f) + (a.i1 == p ? a.l1 : 0.f);
+        if (first < 0) { if (w == 0.f) continue; first = o; }
+        if (n < TABW) t.w[n] = w;
+        n++;
     }
     if (first < 0) return t;
-    t.lo = (short)first; t.n = (short)(last - first + 1);
-    for (int q = 0; q < TABW && first + q <= last; q++) t.w[q] = axis_weight(first + q, p, scale, in_size);
+    t.lo = first; t.n = n;
     return t;
 }
 
-// table entries are 16 B; a thread reads V consecutive entries, so the index is XOR-swizzled within
-// groups of 8 to keep the 16-byte shared-memory reads of a warp conflict-free
-__device__ __forceinline__ int tswz(int e) { return e ^ ((e >> 3) & 7); }
+// out-of-line copy of the generic 2-D gather for the rare slow paths (keeps their registers out of the hot loop)
+template <typename T>
+__device__ __noinline__ void gather_grid_cold(const T* g, int C, int oh, int ow, int px, int py, int bw, int bh, float* acc) {
+    float a[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
+    gather_grid<T>(g, C, oh, ow, px, py, bw, bh, a);
+    for (int c = 0; c < FG_MAXC; c++) acc[c] = a[c];
+}
 
 struct BwdParams {
     const void* g_chips; const void* g_small;
@@ -230,141 +285,198 @@ struct BwdParams {
     int n, C, H, W, ch, cw, sh, sw;
 };
 
-// dynamic smem: Tab xtab[2][W]; Tab ytab[2][BTH]; float t[2][C][BTH][OWMAX]
-template <typename T>
-__global__ void __launch_bounds__(256)
-image_grad_tiled_kernel(const BwdParams p, int owmax) {
+template <typename T> struct Pack2;
+template <> struct Pack2<float> { using type = float2; static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); } };
+template <> struct Pack2<__nv_bfloat16> { using type = __nv_bfloat162; static __device__ __forceinline__ __nv_bfloat162 make(float a, float b) { return __floats2bfloat162_rn(a, b); } };
+template <> struct Pack2<__half> { using type = __half2; static __device__ __forceinline__ __half2 make(float a, float b) { return __floats2half2_rn(a, b); } };
+
+// dynamic smem: Tab ytab[2][BSUB*BTH]; float tb[2][C][BTH][owp]
+template <typename T, int C>
+__global__ void __launch_bounds__(256, 3)
+image_grad_tiled_kernel(const BwdParams p, int owp) {
     extern __shared__ __align__(16) uint8_t smem[];
-    Tab* xtab = reinterpret_cast<Tab*>(smem);                 // [2][W]
-    Tab* ytab = xtab + 2 * p.W;                                // [2][BTH]
-    float* tb = reinterpret_cast<float*>(ytab + 2 * BTH);      // [2][C][BTH][owmax]
+    Tab* ytab = reinterpret_cast<Tab*>(smem);                              // [2][BSUB*BTH]
+    float* tb = reinterpret_cast<float*>(ytab + 2 * BSUB * BTH);           // [2][C][BTH][owp]
     const int img = blockIdx.y;
-    const int y0 = blockIdx.x * BTH;
+    const int ybase = blockIdx.x * (BSUB * BTH);
     const int tid = threadIdx.x;
+    const int W = p.W, H = p.H;
     const bool has_s = p.g_small != nullptr;
-    Box b; b.ok = false;
-    if (p.g_chips) b = load_box(p.boxes, p.ind, img, p.H, p.W);
-    // tile rows that can receive chip gradient at all
-    const bool chip_rows = b.ok && y0 < b.y1 && y0 + BTH > b.y0;
+    Box b; b.ok = false; b.x0 = b.y0 = b.x1 = b.y1 = 0;
+    if (p.g_chips) b = load_box(p.boxes, p.ind, img, H, W);
     const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
-    const float ssx = (float)p.W / (float)p.sw, ssy = (float)p.H / (float)p.sh;
-    const float csx = chip_rows ? (float)bw / (float)p.cw : 1.f, csy = chip_rows ? (float)bh / (float)p.ch : 1.f;
+    const float ssx = (float)W / (float)p.sw, ssy = (float)H / (float)p.sh;
+    const float csx = b.ok ? (float)bw / (float)p.cw : 1.f, csy = b.ok ? (float)bh / (float)p.ch : 1.f;
+    // boxes so small that more than TABW outputs land on one source pixel take the direct 2-D gather
+    // (decided up front from the scale; a count above TABW found while building the tables also
+    // switches the CTA to that path, see `overflow` below)
+    bool chip_slow = b.ok && (csx < 0.51f || csy < 0.51f);
+    bool chip_fast = b.ok && !chip_slow;
 
-    for (int x = tid; x < p.W; x += 256) {
-        if (has_s) xtab[tswz(x)] = make_tab(x, ssx, p.W, p.sw);
-        if (chip_rows) xtab[p.W + tswz(x)] = make_tab(x - b.x0, csx, bw, p.cw);
-    }
-    if (tid < BTH) {
-        int y = y0 + tid;
-        if (has_s) ytab[tid] = make_tab(y < p.H ? y : -1, ssy, p.H, p.sh);
-        if (chip_rows) ytab[BTH + tid] = make_tab(y < p.H ? y - b.y0 : -1, csy, bh, p.ch);
-    }
-    __syncthreads();
-
-    // ---- stage 1: vertical pass, coalesced along ox
-    for (int g = 0; g < 2; g++) {
-        if (g == 0 ? !has_s : !chip_rows) continue;
-        const int oh = g == 0 ? p.sh : p.ch, ow = g == 0 ? p.sw : p.cw;
-        const T* G = reinterpret_cast<const T*>(g == 0 ? p.g_small : p.g_chips) + (size_t)img * p.C * oh * ow;
-        const float scl = g == 0 ? ssy : csy;
-        const int in_size = g == 0 ? p.H : bh;
-        const int items = BTH * ow;
-        for (int it = tid; it < items; it += 256) {
-            int r = it / ow, ox = it - r * ow;
-            Tab ty = ytab[g * BTH + r];
-            float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
-            if (ty.n > 0) {
-                if (ty.n <= TABW) {
-                    for (int q = 0; q < ty.n; q++) {
-                        const T* row = G + (size_t)(ty.lo + q) * ow + ox;
-#pragma unroll
-                        for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c] += ty.w[q] * to_f32(row[(size_t)c * oh * ow]);
-                    }
-                } else {
-                    int py = (y0 + r) - (g == 0 ? 0 : b.y0);
-                    for (int q = 0; q < ty.n; q++) {
-                        float w = axis_weight(ty.lo + q, py, scl, in_size);
-                        const T* row = G + (size_t)(ty.lo + q) * ow + ox;
-#pragma unroll
-                        for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c] += w * to_f32(row[(size_t)c * oh * ow]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < FG_MAXC; c++) if (c < p.C) tb[((size_t)(g * p.C + c) * BTH + r) * owmax + ox] = acc[c];
+    // t rows are read TABW wide from `lo` with zero weights past the last tap: no stale NaNs allowed
+    for (int e = tid; e < 2 * C * BTH * owp; e += 256) tb[e] = 0.f;
+    int too_many = 0;
+    for (int e = tid; e < 2 * BSUB * BTH; e += 256) {
+        int g = e / (BSUB * BTH), r = e - g * (BSUB * BTH);
+        int y = ybase + r;
+        Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+        if (y < H) {
+            if (g == 0) { if (has_s) t = make_tab(y, ssy, H, p.sh); }
+            else if (chip_fast) t = make_tab(y - b.y0, csy, bh, p.ch);
         }
+        if (t.n > TABW) too_many |= 1 << g;
+        ytab[e] = t;
     }
-    __syncthreads();
-
-    // ---- stage 2: horizontal pass, V consecutive x per thread, 16-byte stores
-    constexpr int V = 16 / (int)sizeof(T);
+    // this thread's two image columns: tap tables in registers for the whole CTA
+    const int x_a = 2 * tid;                      // host guarantees W <= 512 and W even
+    Tab xs[2], xc[2];
+    bool in_reg_x[2];
     int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0; float rs = 1.f;
     if (p.region) {
         rx0 = p.region[4 * img]; ry0 = p.region[4 * img + 1]; rx1 = p.region[4 * img + 2]; ry1 = p.region[4 * img + 3];
         rs = p.scale[img];
     }
-    const int vec_per_row = p.W / V;                   // host guarantees W % V == 0
-    T* gout = reinterpret_cast<T*>(p.g_images) + (size_t)img * p.C * p.H * p.W;
-    for (int it = tid; it < BTH * vec_per_row; it += 256) {
-        int r = it / vec_per_row, xv = (it - r * vec_per_row) * V;
-        int y = y0 + r;
-        if (y >= p.H) continue;
-        const bool row_in_region = y >= ry0 && y < ry1;
-        float acc[FG_MAXC][V];
 #pragma unroll
-        for (int c = 0; c < FG_MAXC; c++)
+    for (int v = 0; v < 2; v++) {
+        const int x = x_a + v;
+        xs[v].lo = 0; xs[v].n = 0; xc[v].lo = 0; xc[v].n = 0;
 #pragma unroll
-            for (int v = 0; v < V; v++) acc[c][v] = 0.f;
+        for (int q = 0; q < TABW; q++) { xs[v].w[q] = 0.f; xc[v].w[q] = 0.f; }
+        if (x < W) {
+            if (has_s) xs[v] = make_tab(x, ssx, W, p.sw);
+            if (chip_fast) xc[v] = make_tab(x - b.x0, csx, bw, p.cw);
+        }
+        in_reg_x[v] = x >= rx0 && x < rx1;
+        // keep lo + TABW - 1 inside the padded t row even for entries without taps
+        if (xs[v].n == 0) xs[v].lo = 0;
+        if (xc[v].n == 0) xc[v].lo = 0;
+    }
+    if (xs[0].n > TABW || xs[1].n > TABW) too_many |= 1;
+    if (xc[0].n > TABW || xc[1].n > TABW) too_many |= 2;
+    const bool small_slow = __syncthreads_or(too_many & 1) != 0;      // also orders the ytab / tb writes
+    if (__syncthreads_or(too_many & 2) != 0) { chip_slow = true; chip_fast = false; }
+    const bool has_s_fast = has_s && !small_slow;
+    const bool s_wide = __syncthreads_or((xs[0].n > 2) | (xs[1].n > 2)) != 0;
+    const bool c_wide = __syncthreads_or((xc[0].n > 2) | (xc[1].n > 2)) != 0;
+    const bool warp_has_chip = __any_sync(0xffffffffu, (xc[0].n | xc[1].n) != 0);
+
+    T* gout = reinterpret_cast<T*>(p.g_images) + (size_t)img * C * H * W;
+    const size_t iplane = (size_t)H * W;
+    const int tstride_c = BTH * owp;              // channel stride inside tb
+    const int tstride_g = C * tstride_c;          // grid stride
+
+    for (int sub = 0; sub < BSUB; sub++) {
+        const int y0 = ybase + sub * BTH;
+        if (y0 >= H) break;
+        const bool chip_rows = chip_fast && y0 < b.y1 && y0 + BTH > b.y0;
+        // ---- stage 1: vertical pass; a thread owns one output column, the row loop is warp-uniform
+        for (int g = 0; g < 2; g++) {
+            if (g == 0 ? !has_s_fast : !chip_rows) continue;
+            const int oh = g == 0 ? p.sh : p.ch, ow = g == 0 ? p.sw : p.cw;
+            const T* G = reinterpret_cast<const T*>(g == 0 ? p.g_small : p.g_chips) + (size_t)img * C * oh * ow;
+            const size_t gplane = (size_t)oh * ow;
+            for (int ox = tid; ox < ow; ox += 256) {
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-            int x = xv + v;
-            if (has_s) {
-                Tab tx = xtab[tswz(x)];
-                if (tx.n > 0) {
-                    float s = (row_in_region && x >= rx0 && x < rx1) ? rs : 1.f;
-                    const float* tr = tb + (size_t)r * owmax + tx.lo;
-                    if (tx.n <= TABW) {
-                        for (int q = 0; q < tx.n; q++) {
-                            float w = tx.w[q] * s;
+                for (int r = 0; r < BTH; r++) {
+                    const Tab& ty = ytab[g * BSUB * BTH + sub * BTH + r];
+                    float acc[C];
 #pragma unroll
-                            for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c][v] += w * tr[(size_t)c * BTH * owmax + q];
-                        }
-                    } else {
-                        for (int q = 0; q < tx.n; q++) {
-                            float w = axis_weight(tx.lo + q, x, ssx, p.W) * s;
+                    for (int c = 0; c < C; c++) acc[c] = 0.f;
+                    const int n = ty.n;                        // warp-uniform
+                    for (int q = 0; q < n; q++) {
+                        const float w = ty.w[q];
+                        const T* row = G + (size_t)(ty.lo + q) * ow + ox;
 #pragma unroll
-                            for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c][v] += w * tr[(size_t)c * BTH * owmax + q];
-                        }
+                        for (int c = 0; c < C; c++) acc[c] += w * to_f32(row[c * gplane]);
                     }
-                }
-            }
-            if (chip_rows) {
-                Tab tx = xtab[p.W + tswz(x)];
-                if (tx.n > 0) {
-                    const float* tr = tb + ((size_t)p.C * BTH + r) * owmax + tx.lo;
-                    if (tx.n <= TABW) {
-                        for (int q = 0; q < tx.n; q++) {
-                            float w = tx.w[q];
 #pragma unroll
-                            for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c][v] += w * tr[(size_t)c * BTH * owmax + q];
-                        }
-                    } else {
-                        for (int q = 0; q < tx.n; q++) {
-                            float w = axis_weight(tx.lo + q, x - b.x0, csx, bw);
-#pragma unroll
-                            for (int c = 0; c < FG_MAXC; c++) if (c < p.C) acc[c][v] += w * tr[(size_t)c * BTH * owmax + q];
-                        }
-                    }
+                    for (int c = 0; c < C; c++) tb[g * tstride_g + c * tstride_c + r * owp + ox] = acc[c];
                 }
             }
         }
+        __syncthreads();
+
+        // ---- stage 2: horizontal pass for this thread's two columns
+        if (x_a < W) {
+#pragma unroll 2
+            for (int r = 0; r < BTH; r++) {
+                const int y = y0 + r;
+                if (y >= H) break;
+                const bool row_reg = y >= ry0 && y < ry1;
+                float o0[C], o1[C];
 #pragma unroll
-        for (int c = 0; c < FG_MAXC; c++) {
-            if (c >= p.C) break;
-            T packed[V];
+                for (int c = 0; c < C; c++) { o0[c] = 0.f; o1[c] = 0.f; }
+                if (small_slow) {
+                    // not reachable for a downscaling resize; kept so that any shape is computed correctly
+                    const T* G = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * p.sh * p.sw;
 #pragma unroll
-            for (int v = 0; v < V; v++) packed[v] = from_f32<T>(acc[c][v]);
-            *reinterpret_cast<int4*>(gout + ((size_t)c * p.H + y) * p.W + xv) = *reinterpret_cast<const int4*>(packed);
+                    for (int v = 0; v < 2; v++) {
+                        const int x = x_a + v;
+                        if (x < W) {
+                            float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
+                            gather_grid_cold<T>(G, C, p.sh, p.sw, x, y, W, H, acc);
+                            const float s = (row_reg && in_reg_x[v]) ? rs : 1.f;
+#pragma unroll
+                            for (int c = 0; c < C; c++) { if (v == 0) o0[c] = acc[c] * s; else o1[c] = acc[c] * s; }
+                        }
+                    }
+                }
+                if (has_s_fast) {
+                    const float* t0 = tb + r * owp + xs[0].lo;
+                    const float* t1 = tb + r * owp + xs[1].lo;
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        o0[c] = xs[0].w[0] * t0[c * tstride_c] + xs[0].w[1] * t0[c * tstride_c + 1];
+                        o1[c] = xs[1].w[0] * t1[c * tstride_c] + xs[1].w[1] * t1[c * tstride_c + 1];
+                    }
+                    if (s_wide) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[c] += xs[0].w[2] * t0[c * tstride_c + 2] + xs[0].w[3] * t0[c * tstride_c + 3];
+                            o1[c] += xs[1].w[2] * t1[c * tstride_c + 2] + xs[1].w[3] * t1[c * tstride_c + 3];
+                        }
+                    }
+                    const float s0 = (row_reg && in_reg_x[0]) ? rs : 1.f, s1 = (row_reg && in_reg_x[1]) ? rs : 1.f;
+#pragma unroll
+                    for (int c = 0; c < C; c++) { o0[c] *= s0; o1[c] *= s1; }
+                }
+                if (chip_rows && warp_has_chip) {
+                    const float* t0 = tb + tstride_g + r * owp + xc[0].lo;
+                    const float* t1 = tb + tstride_g + r * owp + xc[1].lo;
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        o0[c] += xc[0].w[0] * t0[c * tstride_c] + xc[0].w[1] * t0[c * tstride_c + 1];
+                        o1[c] += xc[1].w[0] * t1[c * tstride_c] + xc[1].w[1] * t1[c * tstride_c + 1];
+                    }
+                    if (c_wide) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[c] += xc[0].w[2] * t0[c * tstride_c + 2] + xc[0].w[3] * t0[c * tstride_c + 3];
+                            o1[c] += xc[1].w[2] * t1[c * tstride_c + 2] + xc[1].w[3] * t1[c * tstride_c + 3];
+                        }
+                    }
+                }
+                if (chip_slow) {
+                    // rare: tiny box, direct 2-D gather from G (generic kernel's routine)
+                    const T* G = reinterpret_cast<const T*>(p.g_chips) + (size_t)img * C * p.ch * p.cw;
+#pragma unroll
+                    for (int v = 0; v < 2; v++) {
+                        const int x = x_a + v;
+                        if (x >= b.x0 && x < b.x1 && y >= b.y0 && y < b.y1) {
+                            float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
+                            gather_grid_cold<T>(G, C, p.ch, p.cw, x - b.x0, y - b.y0, bw, bh, acc);
+#pragma unroll
+                            for (int c = 0; c < C; c++) { if (v == 0) o0[c] += acc[c]; else o1[c] += acc[c]; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    using P2 = Pack2<T>;
+                    *reinterpret_cast<typename P2::type*>(gout + c * iplane + (size_t)y * W + x_a) = P2::make(o0[c], o1[c]);
+                }
+            }
         }
+        __syncthreads();
     }
 }
