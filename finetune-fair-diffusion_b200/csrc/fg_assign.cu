@@ -182,28 +182,40 @@ cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __
 struct Demand { int b[KP]; };
 
 struct SolverSmem {
-    double w[KP][KP];
-    int wi[KP][KP];
+    double w[KP][KP];          // w[k][l] = min over rows i currently in k of M[i,l] - M[i,k]
+    int wi[KP][KP];            // the row that attains it (lowest index on ties), -1 if k is empty
     double dist[KP];
     double price[KP];
     int pred[KP];
     int cnt[KP];
     int b[KP];
-    unsigned long long red_key[SOLVER_WARPS][KP];
-    int red_idx[SOLVER_WARPS][KP];
     int path[KP + 1];
     int moved[KP + 1];
     unsigned need[KP + 1];
     int path_len;
+    int cont[2];               // loop-continue flag, double buffered by iteration parity
     int status;
 };
 
-// Recompute w[k][l], wi[k][l] for the classes l in `mask` by scanning the rows currently in class k.
-__device__ void rescan_class(SolverSmem& sm, const uint8_t* sigma, const double* __restrict__ M, int N, int K,
-                             int k, unsigned mask) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// dynamic shared memory behind the control block
+struct SolverViews {
+    uint8_t* sigma;            // [N]      class of every row
+    uint16_t* pos;             // [N]      position of the row inside its class list
+    uint16_t* members;         // [K][N]   unordered member list per class
+    double* Ms;                // [N][K]   cost matrix copy (only when it fits)
+};
+
+__host__ __device__ inline size_t solver_off_pos(int N) { return sizeof(SolverSmem) + (((size_t)N + 15) / 16) * 16; }
+__host__ __device__ inline size_t solver_off_members(int N) { return solver_off_pos(N) + (((size_t)N * 2 + 15) / 16) * 16; }
+__host__ __device__ inline size_t solver_off_M(int N, int K) { return solver_off_members(N) + (((size_t)N * K * 2 + 15) / 16) * 16; }
+
+// One warp recomputes w[k][l], wi[k][l] for the classes l in `mask` from the member list of class k.
+__device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* __restrict__ M, int N, int K, int k, unsigned mask) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = sm.cnt[k];
+    const uint16_t* mem = v.members + (size_t)k * N;
     mask &= ~(1u << k);
-    while (mask) {                                   // block-uniform; up to 4 target classes per pass
+    while (mask) {                                   // warp-uniform; up to 4 target classes per pass
         int ls[4]; int nl = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -212,21 +224,22 @@ __device__ void rescan_class(SolverSmem& sm, const uint8_t* sigma, const double*
         double bestd[4]; int besti[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { bestd[j] = INFINITY; besti[j] = 0x7fffffff; }
-        for (int i = threadIdx.x; i < N; i += SOLVER_THREADS) {
-            if (sigma[i] != k) continue;
+        for (int t = lane; t < cnt; t += 32) {
+            const int i = mem[t];
             const double* row = M + (size_t)i * K;
             const double mk = row[k];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (j < nl) {
                     const double d = __dsub_rn(row[ls[j]], mk);
-                    if (d < bestd[j] || besti[j] == 0x7fffffff) { bestd[j] = d; besti[j] = i; }   // rows come in increasing order
+                    // the list is unordered: ties resolve to the lowest row index explicitly
+                    if (besti[j] == 0x7fffffff || d < bestd[j] || (d == bestd[j] && i < besti[j])) { bestd[j] = d; besti[j] = i; }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (j >= nl) break;                        // block-uniform
+            if (j >= nl) break;                        // warp-uniform
             const unsigned long long key = besti[j] == 0x7fffffff ? KEY_INF : dkey(bestd[j]);
             const unsigned hi = (unsigned)(key >> 32);
             const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
@@ -234,24 +247,14 @@ __device__ void rescan_class(SolverSmem& sm, const uint8_t* sigma, const double*
             const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
             const unsigned cand = (hi == mhi && lo == mlo) ? (unsigned)besti[j] : 0x7fffffffu;
             const unsigned mi = __reduce_min_sync(0xffffffffu, cand);
-            if (lane == 0) { sm.red_key[warp][j] = ((unsigned long long)mhi << 32) | mlo; sm.red_idx[warp][j] = (int)mi; }
-        }
-        __syncthreads();
-        if (threadIdx.x < nl) {
-            const int j = threadIdx.x;
-            int l = ls[0];
-#pragma unroll
-            for (int q = 1; q < 4; q++) if (q == j) l = ls[q];
-            unsigned long long bk = KEY_INF; int bi = 0x7fffffff;
-            for (int wq = 0; wq < SOLVER_WARPS; wq++) {
-                const unsigned long long kk = sm.red_key[wq][j]; const int ii = sm.red_idx[wq][j];
-                if (kk < bk || (kk == bk && ii < bi)) { bk = kk; bi = ii; }
+            if (lane == 0) {
+                const int l = ls[j];
+                if (mi == 0x7fffffffu) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
+                else { sm.w[k][l] = dunkey(((unsigned long long)mhi << 32) | mlo); sm.wi[k][l] = (int)mi; }
             }
-            if (bi == 0x7fffffff) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
-            else { sm.w[k][l] = dunkey(bk); sm.wi[k][l] = bi; }
         }
-        __syncthreads();
     }
+    __syncwarp();
 }
 
 // warp 0: shortest path from the over-full classes to the cheapest under-full class
@@ -261,7 +264,7 @@ __device__ void find_path(SolverSmem& sm, int K) {
     bool surplus = l < K && sm.cnt[l] > sm.b[l];
     bool deficit = l < K && sm.cnt[l] < sm.b[l];
     unsigned def_mask = __ballot_sync(0xffffffffu, deficit && half == 0);
-    if (def_mask == 0) { if (lane == 0) sm.path_len = 0; return; }
+    if (def_mask == 0) { if (lane == 0) sm.path_len = 0; __syncwarp(); return; }
     if (half == 0) { sm.dist[l] = surplus ? 0.0 : INFINITY; sm.pred[l] = -1; }
     __syncwarp();
     for (int round = 0; round < KP; round++) {
@@ -292,18 +295,28 @@ __device__ void find_path(SolverSmem& sm, int K) {
     unsigned cand = (hi == mhi && lo == mlo && half == 0 && deficit) ? (unsigned)l : 0xffu;
     unsigned t = __reduce_min_sync(0xffffffffu, cand);
     if (lane == 0) {
-        if (t >= (unsigned)K || !(sm.dist[t] < INFINITY)) { sm.status |= ST_NO_PATH; sm.path_len = 0; return; }
-        int rev[KP + 1]; int len = 0; int node = (int)t;
-        while (node >= 0 && len <= KP) { rev[len++] = node; node = sm.pred[node]; }
-        if (len > KP || len < 2) { sm.status |= ST_PATH_OVERFLOW; sm.path_len = 0; return; }
-        for (int q = 0; q < len; q++) sm.path[q] = rev[len - 1 - q];
-        sm.path_len = len;
+        if (t >= (unsigned)K || !(sm.dist[t] < INFINITY)) { sm.status |= ST_NO_PATH; sm.path_len = 0; }
+        else {
+            int rev[KP + 1]; int len = 0; int node = (int)t;
+            while (node >= 0 && len <= KP) { rev[len++] = node; node = sm.pred[node]; }
+            if (len > KP || len < 2) { sm.status |= ST_PATH_OVERFLOW; sm.path_len = 0; }
+            else {
+                for (int q = 0; q < len; q++) sm.path[q] = rev[len - 1 - q];
+                sm.path_len = len;
+            }
+        }
     }
+    __syncwarp();
 }
 
 // mode 0: start from argmin_l (M[i,l] - price[l]) over rows [0,N)   (price = 0: greedy)
 // mode 1: start from sigma_in (the base assignment)
 // demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x]
+//
+// After the parallel set-up (initial assignment, member lists, first full scan of the class graph, one
+// class per warp) the repair loop runs entirely inside warp 0: shortest path, moves, list updates and
+// the re-scan of the classes that lost a row are all warp-synchronous, so a repair step costs no block
+// barrier besides the one that tells the other warps whether the loop is over.
 __global__ void __launch_bounds__(SOLVER_THREADS)
 ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
                 const uint8_t* __restrict__ sigma_in, double* __restrict__ prices,
@@ -312,14 +325,18 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
                 int32_t* __restrict__ counts, int* __restrict__ status, int status_slot, int m_in_smem) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
-    uint8_t* sigma = dyn_smem + sizeof(SolverSmem);
-    const int tid = threadIdx.x;
+    SolverViews v;
+    v.sigma = dyn_smem + sizeof(SolverSmem);
+    v.pos = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_pos(N));
+    v.members = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_members(N));
+    v.Ms = reinterpret_cast<double*>(dyn_smem + solver_off_M(N, K));
+    uint8_t* sigma = v.sigma;
+    const int tid = threadIdx.x, warp = tid >> 5;
     // the cost matrix is re-read on every repair step: keep it in shared memory when it fits
     const double* M = M_global;
     if (m_in_smem) {
-        double* Ms = reinterpret_cast<double*>(sigma + (((size_t)N + 15) / 16) * 16);
-        for (int e = tid; e < N * K; e += SOLVER_THREADS) Ms[e] = M_global[e];
-        M = Ms;
+        for (int e = tid; e < N * K; e += SOLVER_THREADS) v.Ms[e] = M_global[e];
+        M = v.Ms;
     }
 
     if (tid < KP) {
@@ -335,60 +352,76 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
         for (int k = 0; k < K; k++) { if (sm.b[k] < 0) sm.status |= ST_BAD_DEMAND; tot += sm.b[k]; }
         if (tot != N) sm.status |= ST_BAD_DEMAND;
     }
-    // initial assignment
+    // initial assignment + member lists (list order is arbitrary; no result depends on it)
     for (int i = tid; i < N; i += SOLVER_THREADS) {
         int s;
         if (mode == 1) s = sigma_in[i];
         else {
-            const double* row = M + (size_t)i * K;
+            const double* row = M_global + (size_t)i * K;
             double bv = INFINITY; s = 0;
-            for (int l = 0; l < K; l++) { double v = __dsub_rn(row[l], sm.price[l]); if (v < bv) { bv = v; s = l; } }
+            for (int l = 0; l < K; l++) { double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
         }
         sigma[i] = (uint8_t)s;
-        atomicAdd(&sm.cnt[s], 1);
+        int slot = atomicAdd(&sm.cnt[s], 1);
+        v.members[(size_t)s * N + slot] = (uint16_t)i;
+        v.pos[i] = (uint16_t)slot;
     }
     for (int e = tid; e < KP * KP; e += SOLVER_THREADS) { sm.w[e / KP][e % KP] = INFINITY; sm.wi[e / KP][e % KP] = -1; }
     __syncthreads();
-    const unsigned all_mask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+    const unsigned all_mask = (1u << K) - 1u;
+    int iters = 0;
     if (!(sm.status & ST_BAD_DEMAND)) {
-        for (int k = 0; k < K; k++) rescan_class(sm, sigma, M, N, K, k, all_mask & ~(1u << k));
-
-        int iters = 0;
+        for (int k = warp; k < K; k += SOLVER_WARPS) warp_rescan(sm, v, M, N, K, k, all_mask);
+        __syncthreads();
         const int max_iters = N + KP;
         for (;; iters++) {
-            if (tid < 32) find_path(sm, K);
-            __syncthreads();
-            int len = sm.path_len;
-            if (len == 0) break;
-            if (iters >= max_iters) { if (tid == 0) sm.status |= ST_ITER_CAP; break; }
-            if (tid == 0) {
-                for (int e = 0; e + 1 < len; e++) {
-                    int u = sm.path[e], v = sm.path[e + 1];
-                    int item = sm.wi[u][v];
-                    sm.moved[e] = item;
-                    unsigned need = 0;
-                    for (int l = 0; l < K; l++) if (l != u && sm.wi[u][l] == item) need |= 1u << l;
-                    sm.need[e] = need;
+            if (warp == 0) {
+                const int lane = tid;
+                find_path(sm, K);
+                int len = sm.path_len;
+                if (len > 0 && iters >= max_iters) { if (lane == 0) { sm.status |= ST_ITER_CAP; sm.path_len = 0; } len = 0; }
+                if (len > 0) {
+                    if (lane == 0) {
+                        for (int e = 0; e + 1 < len; e++) {
+                            const int u = sm.path[e], item = sm.wi[u][sm.path[e + 1]];
+                            sm.moved[e] = item;
+                            unsigned need = 0;
+                            for (int l = 0; l < K; l++) if (l != u && sm.wi[u][l] == item) need |= 1u << l;
+                            sm.need[e] = need;
+                        }
+                        for (int e = 0; e + 1 < len; e++) {
+                            const int u = sm.path[e], to = sm.path[e + 1], item = sm.moved[e];
+                            // unlink from u (swap with the last member), append to `to`
+                            const int p = v.pos[item], lastpos = sm.cnt[u] - 1;
+                            const uint16_t last = v.members[(size_t)u * N + lastpos];
+                            v.members[(size_t)u * N + p] = last; v.pos[last] = (uint16_t)p;
+                            sm.cnt[u] = lastpos;
+                            const int q = sm.cnt[to];
+                            v.members[(size_t)to * N + q] = (uint16_t)item; v.pos[item] = (uint16_t)q;
+                            sm.cnt[to] = q + 1;
+                            sigma[item] = (uint8_t)to;
+                        }
+                    }
+                    __syncwarp();
+                    for (int e = 0; e + 1 < len; e++) warp_rescan(sm, v, M, N, K, sm.path[e], sm.need[e]);
+                    // rows that arrived in path[e+1]: fold their outgoing differences into the minima
+                    if (lane < K) {
+                        const int l = lane;
+                        for (int e = 0; e + 1 < len; e++) {
+                            const int to = sm.path[e + 1], item = sm.moved[e];
+                            if (l == to) continue;
+                            const double* row = M + (size_t)item * K;
+                            const double d = __dsub_rn(row[l], row[to]);
+                            const double cur = sm.w[to][l];
+                            if (sm.wi[to][l] < 0 || d < cur || (d == cur && item < sm.wi[to][l])) { sm.w[to][l] = d; sm.wi[to][l] = item; }
+                        }
+                    }
+                    __syncwarp();
                 }
-                for (int e = 0; e + 1 < len; e++) sigma[sm.moved[e]] = (uint8_t)sm.path[e + 1];
-                sm.cnt[sm.path[0]]--;
-                sm.cnt[sm.path[len - 1]]++;
+                if (lane == 0) sm.cont[iters & 1] = len > 0 ? 1 : 0;
             }
             __syncthreads();
-            for (int e = 0; e + 1 < len; e++) rescan_class(sm, sigma, M, N, K, sm.path[e], sm.need[e]);
-            // rows that arrived in path[e+1]: fold their outgoing differences into the minima
-            if (tid < KP && tid < K) {
-                int l = tid;
-                for (int e = 0; e + 1 < len; e++) {
-                    int v = sm.path[e + 1], item = sm.moved[e];
-                    if (l == v) continue;
-                    const double* row = M + (size_t)item * K;
-                    double d = __dsub_rn(row[l], row[v]);
-                    double cur = sm.w[v][l];
-                    if (d < cur || (d == cur && item < sm.wi[v][l])) { sm.w[v][l] = d; sm.wi[v][l] = item; }
-                }
-            }
-            __syncthreads();
+            if (sm.cont[iters & 1] == 0) break;
         }
         if (tid == 0 && status) atomicAdd(&status[status_slot], iters);
     }
@@ -584,17 +617,19 @@ rank_split_kernel(const T* __restrict__ probs, int n_all, double ratio, float th
     if (unc) unc[i] = from_f32<T>(uf);
 }
 
-// shared memory of one solver CTA: control block + assignment bytes (+ the cost matrix when it fits)
+// shared memory of one solver CTA: control block, assignment bytes, list positions, member lists
+// (+ the cost matrix when it fits)
 static bool solver_m_fits(int N, int K) {
-    return sizeof(SolverSmem) + fg_align_up((size_t)N, 16) + (size_t)N * K * sizeof(double) <= 200 * 1024;
+    return solver_off_M(N, K) + (size_t)N * K * sizeof(double) <= 200 * 1024;
 }
 static int solver_smem_bytes(int N, int K) {
-    size_t b = sizeof(SolverSmem) + fg_align_up((size_t)N, 16);
+    size_t b = solver_off_M(N, K);
     if (solver_m_fits(N, K)) b += (size_t)N * K * sizeof(double);
     return (int)b;
 }
 
 static int solver_prepare(int N, int K) {
+    if (N > 65535) return FG_ERR_LIMIT;           // member lists index rows with 16 bits
     int bytes = solver_smem_bytes(N, K);
     if (bytes > 227 * 1024) return FG_ERR_LIMIT;
     if (bytes > 48 * 1024) {

@@ -375,22 +375,36 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
             const int oh = g == 0 ? p.sh : p.ch, ow = g == 0 ? p.sw : p.cw;
             const T* G = reinterpret_cast<const T*>(g == 0 ? p.g_small : p.g_chips) + (size_t)img * C * oh * ow;
             const size_t gplane = (size_t)oh * ow;
+            const int gpl = (int)gplane;                       // host guarantees C*oh*ow < 2^31
+            const int last_row = (oh - 1) * ow;
             for (int ox = tid; ox < ow; ox += 256) {
-#pragma unroll
+                const T* Gc = G + ox;
+                float* trow = tb + g * tstride_g + ox;
+                // two taps per source row cover every downscale; the loads of 4 rows are issued together
+#pragma unroll 4
                 for (int r = 0; r < BTH; r++) {
                     const Tab& ty = ytab[g * BSUB * BTH + sub * BTH + r];
+                    const int n = ty.n;                        // warp-uniform
+                    if (n == 0) {                              // nothing lands on this source row
+#pragma unroll
+                        for (int c = 0; c < C; c++) trow[c * tstride_c + r * owp] = 0.f;
+                        continue;
+                    }
+                    const int o0 = ty.lo * ow, o1 = min(o0 + ow, last_row);
+                    const float w0 = ty.w[0], w1 = ty.w[1];
                     float acc[C];
 #pragma unroll
-                    for (int c = 0; c < C; c++) acc[c] = 0.f;
-                    const int n = ty.n;                        // warp-uniform
-                    for (int q = 0; q < n; q++) {
-                        const float w = ty.w[q];
-                        const T* row = G + (size_t)(ty.lo + q) * ow + ox;
+                    for (int c = 0; c < C; c++) acc[c] = w0 * to_f32(Gc[o0 + c * gpl]) + w1 * to_f32(Gc[o1 + c * gpl]);
+                    if (n > 2) {
+                        for (int q = 2; q < n; q++) {
+                            const float w = ty.w[q];
+                            const int oq = o0 + q * ow;
 #pragma unroll
-                        for (int c = 0; c < C; c++) acc[c] += w * to_f32(row[c * gplane]);
+                            for (int c = 0; c < C; c++) acc[c] += w * to_f32(Gc[oq + c * gpl]);
+                        }
                     }
 #pragma unroll
-                    for (int c = 0; c < C; c++) tb[g * tstride_g + c * tstride_c + r * owp + ox] = acc[c];
+                    for (int c = 0; c < C; c++) trow[c * tstride_c + r * owp] = acc[c];
                 }
             }
         }
@@ -398,6 +412,7 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
 
         // ---- stage 2: horizontal pass for this thread's two columns
         if (x_a < W) {
+            T* const obase = gout + (size_t)y0 * W + x_a;
 #pragma unroll 2
             for (int r = 0; r < BTH; r++) {
                 const int y = y0 + r;
@@ -473,7 +488,7 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     using P2 = Pack2<T>;
-                    *reinterpret_cast<typename P2::type*>(gout + c * iplane + (size_t)y * W + x_a) = P2::make(o0[c], o1[c]);
+                    *reinterpret_cast<typename P2::type*>(obase + c * iplane + r * W) = P2::make(o0[c], o1[c]);
                 }
             }
         }
