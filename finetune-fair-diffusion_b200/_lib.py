@@ -89,11 +89,7 @@ KERNELS_PER_CALL = {
 
 def ot_levels(n_valid):
     """Number of base-solve launches fg_ot_plan_counts makes (csrc/fg_assign.cu launch_base)."""
-    levels, L = 1, 256
-    while L < n_valid and levels < 15:
-        levels += 1
-        L *= 4
-    return levels
+    return 1 if n_valid > 0 else 0
 
 
 def check(rc, what):

@@ -186,6 +186,11 @@ struct SolverSmem {
     int wi[KP][KP];            // the row that attains it (lowest index on ties), -1 if k is empty
     double dist[KP];
     double price[KP];
+    double best_price[KP];     // prices with the smallest count error seen by the price search
+    double step[KP];           // per-class adaptive step of the price search
+    int prev_sign[KP];
+    int best_resid;
+    int stop;
     int pred[KP];
     int cnt[KP];
     int b[KP];
@@ -265,27 +270,28 @@ __device__ void find_path(SolverSmem& sm, int K) {
     bool deficit = l < K && sm.cnt[l] < sm.b[l];
     unsigned def_mask = __ballot_sync(0xffffffffu, deficit && half == 0);
     if (def_mask == 0) { if (lane == 0) sm.path_len = 0; __syncwarp(); return; }
-    if (half == 0) { sm.dist[l] = surplus ? 0.0 : INFINITY; sm.pred[l] = -1; }
+    // Bellman-Ford, lane l owns node l; each round relaxes only from the nodes whose label changed in
+    // the previous round (warp-uniform loop over the set bits), lowest source index wins ties
+    double dist = surplus ? 0.0 : INFINITY;
+    int pred = -1;
+    if (half == 0) sm.dist[l] = dist;
+    unsigned changed = __ballot_sync(0xffffffffu, surplus && half == 0) & 0xffffu;
     __syncwarp();
-    for (int round = 0; round < KP; round++) {
-        double cur = sm.dist[l];
-        double best = cur; int bestk = -1;
-#pragma unroll
-        for (int j = 0; j < KP / 2; j++) {
-            int k = half + 2 * j;
-            double cand = sm.dist[k] + sm.w[k][l];
-            if (k != l && cand < best) { best = cand; bestk = k; }
+    for (int round = 0; round < KP && changed; round++) {
+        double nd = dist; int np = pred;
+        for (unsigned m = changed; m; m &= m - 1) {
+            const int k = __ffs(m) - 1;
+            const double cand = sm.dist[k] + sm.w[k][l];        // w[k][k] = +inf
+            if (cand < nd) { nd = cand; np = k; }
         }
-        double ob = __shfl_xor_sync(0xffffffffu, best, 16);
-        int ok = __shfl_xor_sync(0xffffffffu, bestk, 16);
-        if (ob < best || (ob == best && ok >= 0 && (bestk < 0 || ok < bestk))) { best = ob; bestk = ok; }
-        bool improved = bestk >= 0 && best < cur;
-        unsigned any = __ballot_sync(0xffffffffu, improved && half == 0);
+        const bool improved = half == 0 && nd < dist;
+        changed = __ballot_sync(0xffffffffu, improved) & 0xffffu;
         __syncwarp();
-        if (improved && half == 0) { sm.dist[l] = best; sm.pred[l] = bestk; }
+        if (improved) { dist = nd; pred = np; sm.dist[l] = nd; }
         __syncwarp();
-        if (!any) break;
     }
+    if (half == 0) sm.pred[l] = pred;
+    __syncwarp();
     // cheapest under-full class (lowest index on ties)
     unsigned long long key = (deficit && half == 0) ? dkey(sm.dist[l]) : KEY_INF;
     unsigned hi = (unsigned)(key >> 32);
@@ -309,20 +315,27 @@ __device__ void find_path(SolverSmem& sm, int K) {
     __syncwarp();
 }
 
-// mode 0: start from argmin_l (M[i,l] - price[l]) over rows [0,N)   (price = 0: greedy)
-// mode 1: start from sigma_in (the base assignment)
-// demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x]
+// One CTA solves one transport problem exactly.
 //
-// After the parallel set-up (initial assignment, member lists, first full scan of the class graph, one
-// class per warp) the repair loop runs entirely inside warp 0: shortest path, moves, list updates and
-// the re-scan of the classes that lost a row are all warp-synchronous, so a repair step costs no block
-// barrier besides the one that tells the other warps whether the loop is over.
+//  1. price search (all warps):  `dual_iters` rounds of sign-based dual ascent on the K class prices
+//     (each round: every row takes its cheapest class under the current prices, the class counts are
+//     compared with the demand, a price moves up/down by its own adaptive step -- grow 1.2x while the sign of
+//     the count error persists, halve when it flips).  ANY price vector yields an assignment that is optimal
+//     for its own class sizes, so this only has to get the sizes CLOSE to the demand; the best prices seen
+//     are kept.  It replaces ~N/5 sequential repair steps by a few fully parallel sweeps.
+//  2. exact finish (warp 0):  successive shortest paths on the class graph repair the remaining
+//     |count - demand|_1 / 2 units one at a time; shortest path, moves, list updates and the re-scan of the
+//     classes that lost a row are all warp-synchronous, so a repair step costs no block barrier besides the
+//     one that tells the other warps whether the loop is over.
+//
+// demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x].  prices_in == nullptr starts
+// from zero prices (the greedy assignment).  prices_out receives feasible optimal prices of the final state.
 __global__ void __launch_bounds__(SOLVER_THREADS)
-ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
-                const uint8_t* __restrict__ sigma_in, double* __restrict__ prices,
+ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
+                const double* __restrict__ prices_in, double* __restrict__ prices_out, int dual_iters, double step0,
                 Demand demand_by_value, const int* __restrict__ hist,
-                uint8_t* __restrict__ sigma_out, int32_t* __restrict__ assign_out,
-                int32_t* __restrict__ counts, int* __restrict__ status, int status_slot, int m_in_smem) {
+                int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
+                int* __restrict__ status, int status_slot, int m_in_smem) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
@@ -332,41 +345,75 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
     v.Ms = reinterpret_cast<double*>(dyn_smem + solver_off_M(N, K));
     uint8_t* sigma = v.sigma;
     const int tid = threadIdx.x, warp = tid >> 5;
-    // the cost matrix is re-read on every repair step: keep it in shared memory when it fits
+    // the cost matrix is re-read in every sweep and repair step: keep it in shared memory when it fits
     const double* M = M_global;
     if (m_in_smem) {
         for (int e = tid; e < N * K; e += SOLVER_THREADS) v.Ms[e] = M_global[e];
         M = v.Ms;
     }
-
     if (tid < KP) {
         sm.cnt[tid] = 0;
         sm.b[tid] = hist ? hist[blockIdx.x * KP + tid] : demand_by_value.b[tid];
-        sm.price[tid] = (mode == 0 && prices) ? prices[tid] : 0.0;
         if (tid >= K) sm.b[tid] = 0;
+        sm.price[tid] = (prices_in && tid < K) ? prices_in[tid] : 0.0;
+        sm.best_price[tid] = sm.price[tid];
+        sm.step[tid] = step0;
+        sm.prev_sign[tid] = 0;
     }
-    if (tid == 0) { sm.status = 0; sm.path_len = 0; }
+    if (tid == 0) { sm.status = 0; sm.path_len = 0; sm.best_resid = 0x7fffffff; sm.stop = 0; }
+    for (int e = tid; e < KP * KP; e += SOLVER_THREADS) { sm.w[e / KP][e % KP] = INFINITY; sm.wi[e / KP][e % KP] = -1; }
     __syncthreads();
     if (tid == 0) {
         long long tot = 0;
         for (int k = 0; k < K; k++) { if (sm.b[k] < 0) sm.status |= ST_BAD_DEMAND; tot += sm.b[k]; }
         if (tot != N) sm.status |= ST_BAD_DEMAND;
     }
-    // initial assignment + member lists (list order is arbitrary; no result depends on it)
-    for (int i = tid; i < N; i += SOLVER_THREADS) {
-        int s;
-        if (mode == 1) s = sigma_in[i];
-        else {
-            const double* row = M_global + (size_t)i * K;
-            double bv = INFINITY; s = 0;
-            for (int l = 0; l < K; l++) { double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+
+    // ---- 1. price search
+    for (int it = 0; it <= dual_iters; it++) {
+        for (int i = tid; i < N; i += SOLVER_THREADS) {
+            const double* row = M + (size_t)i * K;
+            double bv = INFINITY; int s = 0;
+            for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+            atomicAdd(&sm.cnt[s], 1);
         }
+        __syncthreads();
+        if (warp == 0) {
+            const int lane = tid;
+            const int err = lane < K ? sm.b[lane] - sm.cnt[lane] : 0;
+            int resid = err < 0 ? -err : err;
+            for (int o = 16; o > 0; o >>= 1) resid += __shfl_xor_sync(0xffffffffu, resid, o);
+            resid >>= 1;
+            const bool better = resid < sm.best_resid;                 // same value in every lane
+            __syncwarp();
+            if (better && lane < KP) sm.best_price[lane] = sm.price[lane];
+            if (lane == 0) {
+                if (better) sm.best_resid = resid;
+                sm.stop = (resid == 0 || it == dual_iters) ? 1 : 0;
+            }
+            if (lane < K && !(resid == 0 || it == dual_iters)) {
+                const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
+                double st = sm.step[lane];
+                const int ps = sm.prev_sign[lane];
+                if (sg * ps < 0) st *= 0.5; else if (sg * ps > 0) st *= 1.2;
+                sm.step[lane] = st; sm.prev_sign[lane] = sg;
+                sm.price[lane] += st * (double)sg;                     // too few rows -> cheaper class
+            }
+            if (lane < KP) sm.cnt[lane] = 0;
+        }
+        __syncthreads();
+        if (sm.stop) break;
+    }
+    // final assignment under the best prices + member lists (list order is arbitrary; no result depends on it)
+    for (int i = tid; i < N; i += SOLVER_THREADS) {
+        const double* row = M + (size_t)i * K;
+        double bv = INFINITY; int s = 0;
+        for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.best_price[l]); if (x < bv) { bv = x; s = l; } }
         sigma[i] = (uint8_t)s;
-        int slot = atomicAdd(&sm.cnt[s], 1);
+        const int slot = atomicAdd(&sm.cnt[s], 1);
         v.members[(size_t)s * N + slot] = (uint16_t)i;
         v.pos[i] = (uint16_t)slot;
     }
-    for (int e = tid; e < KP * KP; e += SOLVER_THREADS) { sm.w[e / KP][e % KP] = INFINITY; sm.wi[e / KP][e % KP] = -1; }
     __syncthreads();
     const unsigned all_mask = (1u << K) - 1u;
     int iters = 0;
@@ -381,14 +428,14 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
                 int len = sm.path_len;
                 if (len > 0 && iters >= max_iters) { if (lane == 0) { sm.status |= ST_ITER_CAP; sm.path_len = 0; } len = 0; }
                 if (len > 0) {
+                    for (int e = 0; e + 1 < len; e++) {
+                        // the row leaving u, and the targets l whose minimum w[u][l] it was holding
+                        const int u = sm.path[e], item = sm.wi[u][sm.path[e + 1]];
+                        const unsigned need = __ballot_sync(0xffffffffu, lane < K && lane != u && sm.wi[u][lane] == item);
+                        if (lane == 0) { sm.moved[e] = item; sm.need[e] = need; }
+                    }
+                    __syncwarp();
                     if (lane == 0) {
-                        for (int e = 0; e + 1 < len; e++) {
-                            const int u = sm.path[e], item = sm.wi[u][sm.path[e + 1]];
-                            sm.moved[e] = item;
-                            unsigned need = 0;
-                            for (int l = 0; l < K; l++) if (l != u && sm.wi[u][l] == item) need |= 1u << l;
-                            sm.need[e] = need;
-                        }
                         for (int e = 0; e + 1 < len; e++) {
                             const int u = sm.path[e], to = sm.path[e + 1], item = sm.moved[e];
                             // unlink from u (swap with the last member), append to `to`
@@ -428,10 +475,9 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
     __syncthreads();
 
     // outputs
-    if (sigma_out) for (int i = tid; i < N; i += SOLVER_THREADS) sigma_out[i] = sigma[i];
     if (assign_out) for (int i = tid; i < N; i += SOLVER_THREADS) assign_out[i] = sigma[i];
     if (counts) for (int i = tid; i < N; i += SOLVER_THREADS) atomicAdd(&counts[(size_t)i * K + sigma[i]], 1);
-    if (mode == 0 && prices) {
+    if (prices_out) {
         // feasible prices for the final state: v_l = min(0, min_k v_k + w[k][l]) (difference constraints)
         if (tid < 32) {
             int lane = tid;
@@ -447,7 +493,7 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K, int mode,
                 __syncwarp();
                 if (!any) break;
             }
-            if (lane < KP) prices[lane] = sm.dist[lane];
+            if (lane < KP) prices_out[lane] = sm.dist[lane];
         }
     }
     if (tid == 0 && sm.status && status) atomicOr(&status[0], sm.status);
@@ -630,13 +676,10 @@ static int solver_smem_bytes(int N, int K) {
 
 static int solver_prepare(int N, int K) {
     if (N > 65535) return FG_ERR_LIMIT;           // member lists index rows with 16 bits
-    int bytes = solver_smem_bytes(N, K);
-    if (bytes > 227 * 1024) return FG_ERR_LIMIT;
-    if (bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return FG_OK;
+    if (solver_smem_bytes(N, K) > 227 * 1024) return FG_ERR_LIMIT;
+    // the coarse levels may need more than the final one (their cost matrix fits): opt in to the maximum
+    cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e == cudaSuccess ? FG_OK : (int)e;
 }
 
 // expected demand for n rows: largest-remainder rounding of n*q
@@ -654,23 +697,22 @@ static void expected_demand(int n, int K, Demand* d) {
 }
 
 // base assignment: coarse-to-fine over growing prefixes, each level warm-started by the previous prices
+// price-search schedule: the base starts from zero prices (the greedy assignment), the draws from the
+// base's optimal prices and only have to absorb |b_s - b_base|
+constexpr int BASE_DUAL_ITERS = 40;
+constexpr double BASE_STEP0 = 0.03;
+constexpr int DRAW_DUAL_ITERS = 14;
+constexpr double DRAW_STEP0 = 0.01;
+
+// base problem: the expected demand; leaves its optimal prices in w.prices
 static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) {
     int rc = solver_prepare(N, K);
     if (rc) return rc;
-    cudaError_t e = cudaMemsetAsync(w.prices, 0, KP * sizeof(double), st);
-    if (e != cudaSuccess) return (int)e;
-    int levels[16]; int nl = 0;
-    for (long long L = 256; L < N && nl < 14; L *= 4) levels[nl++] = (int)L;
-    levels[nl++] = N;
-    for (int q = 0; q < nl; q++) {
-        int n = levels[q];
-        Demand d; expected_demand(n, K, &d);
-        bool last = q == nl - 1;
-        ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, 0, nullptr, w.prices, d, nullptr,
-                                                                            last ? w.sigma0 : nullptr, nullptr, nullptr, w.status, 2,
-                                                                            solver_m_fits(n, K) ? 1 : 0);
-        FG_LAUNCH_CHECK();
-    }
+    Demand d; expected_demand(N, K, &d);
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(N, K), st>>>(M, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0,
+                                                                        d, nullptr, nullptr, nullptr, w.status, 2,
+                                                                        solver_m_fits(N, K) ? 1 : 0);
+    FG_LAUNCH_CHECK();
     return FG_OK;
 }
 
@@ -709,8 +751,8 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int rc = launch_base(w.M, n_valid, K, w, st);
     if (rc) return rc;
     Demand none = {};
-    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, n_valid, K, 1, w.sigma0, nullptr, none, w.hist,
-                                                                             nullptr, nullptr, counts, w.status, 3,
+    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, n_valid, K, w.prices, nullptr, DRAW_DUAL_ITERS,
+                                                                             DRAW_STEP0, none, w.hist, nullptr, counts, w.status, 3,
                                                                              solver_m_fits(n_valid, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
     return FG_OK;
@@ -747,8 +789,9 @@ extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* 
     if (e != cudaSuccess) return (int)e;
     int rc = launch_base(M, n, K, w, st);      // exercises the coarse-to-fine path as well
     if (rc) return rc;
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, 1, w.sigma0, nullptr, d, nullptr, nullptr, assign,
-                                                                         nullptr, w.status, 3, solver_m_fits(n, K) ? 1 : 0);
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, w.prices, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0,
+                                                                         d, nullptr, assign, nullptr, w.status, 3,
+                                                                         solver_m_fits(n, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

@@ -325,6 +325,7 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
             else if (chip_fast) t = make_tab(y - b.y0, csy, bh, p.ch);
         }
         if (t.n > TABW) too_many |= 1 << g;
+        if (g == 0 && t.n > 1) too_many |= 4;          // the whole-image resize has more than one tap per source row
         ytab[e] = t;
     }
     // this thread's two image columns: tap tables in registers for the whole CTA
@@ -357,6 +358,9 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
     if (__syncthreads_or(too_many & 2) != 0) { chip_slow = true; chip_fast = false; }
     const bool has_s_fast = has_s && !small_slow;
     const bool s_wide = __syncthreads_or((xs[0].n > 2) | (xs[1].n > 2)) != 0;
+    // A resize that shrinks by 2x or more (512 -> 224 is 2.29x) puts at most ONE output on any source row or
+    // column: its gradient is a scaled gather straight from g_small, no vertical pass and no shared memory.
+    const bool small_direct = has_s_fast && __syncthreads_or((too_many & 4) | (xs[0].n > 1) | (xs[1].n > 1)) == 0;
     const bool c_wide = __syncthreads_or((xc[0].n > 2) | (xc[1].n > 2)) != 0;
     const bool warp_has_chip = __any_sync(0xffffffffu, (xc[0].n | xc[1].n) != 0);
 
@@ -371,7 +375,7 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
         const bool chip_rows = chip_fast && y0 < b.y1 && y0 + BTH > b.y0;
         // ---- stage 1: vertical pass; a thread owns one output column, the row loop is warp-uniform
         for (int g = 0; g < 2; g++) {
-            if (g == 0 ? !has_s_fast : !chip_rows) continue;
+            if (g == 0 ? (!has_s_fast || small_direct) : !chip_rows) continue;
             const int oh = g == 0 ? p.sh : p.ch, ow = g == 0 ? p.sw : p.cw;
             const T* G = reinterpret_cast<const T*>(g == 0 ? p.g_small : p.g_chips) + (size_t)img * C * oh * ow;
             const size_t gplane = (size_t)oh * ow;
@@ -436,7 +440,21 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
                         }
                     }
                 }
-                if (has_s_fast) {
+                if (small_direct) {
+                    const Tab& ty = ytab[sub * BTH + r];
+                    if (ty.n) {                                            // warp-uniform
+                        const T* Gs = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * p.sh * p.sw + ty.lo * p.sw;
+                        const int gpl_s = p.sh * p.sw;
+                        const float wy = ty.w[0];
+                        const float w0 = wy * xs[0].w[0] * ((row_reg && in_reg_x[0]) ? rs : 1.f);
+                        const float w1 = wy * xs[1].w[0] * ((row_reg && in_reg_x[1]) ? rs : 1.f);
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[c] = w0 * to_f32(Gs[c * gpl_s + xs[0].lo]);
+                            o1[c] = w1 * to_f32(Gs[c * gpl_s + xs[1].lo]);
+                        }
+                    }
+                } else if (has_s_fast) {
                     const float* t0 = tb + r * owp + xs[0].lo;
                     const float* t1 = tb + r * owp + xs[1].lo;
 #pragma unroll

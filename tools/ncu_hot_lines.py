@@ -36,5 +36,6 @@ for r in rows:
 tot = sum(d[0] for d in data) or 1
 toti = sum(d[1] for d in data) or 1
 print(f"# samples={tot} warp-instructions={toti}")
-for s, n, loc, text in sorted(data, reverse=True)[:top]:
+key = (lambda d: d[1]) if os.environ.get("BY_INST") else (lambda d: d[0])
+for s, n, loc, text in sorted(data, key=key, reverse=True)[:top]:
     print(f"{s:7d} {100 * s / tot:5.1f}%  inst={n:9d} {100 * n / toti:5.1f}%  {loc:26s} {text}")
