@@ -186,8 +186,9 @@ struct SolverSmem {
     int wi[KP][KP];            // the row that attains it (lowest index on ties), -1 if k is empty
     double dist[KP];
     double price[KP];
-    double best_price[KP];     // prices with the smallest count error seen by the price search
-    double step[KP];           // per-class adaptive step of the price search
+    float pricef[KP];          // price search state (fp32)
+    float best_pricef[KP];     // prices with the smallest count error seen by the price search
+    float step[KP];            // per-class adaptive step of the price search
     int prev_sign[KP];
     int best_resid;
     int stop;
@@ -207,7 +208,7 @@ struct SolverViews {
     uint8_t* sigma;            // [N]      class of every row
     uint16_t* pos;             // [N]      position of the row inside its class list
     uint16_t* members;         // [K][N]   unordered member list per class
-    double* Ms;                // [N][K]   cost matrix copy (only when it fits)
+    float* Mf;                 // [K][N]   fp32 copy of the cost matrix for the price search (when it fits)
 };
 
 __host__ __device__ inline size_t solver_off_pos(int N) { return sizeof(SolverSmem) + (((size_t)N + 15) / 16) * 16; }
@@ -226,9 +227,10 @@ __device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* 
         for (int j = 0; j < 4; j++) {
             if (mask) { ls[j] = __ffs(mask) - 1; mask &= mask - 1; nl = j + 1; } else ls[j] = ls[0];
         }
-        double bestd[4]; int besti[4];
+        // candidates are compared as order-preserving integer keys: FP64 compares issue slowly on this part
+        unsigned long long bestk[4]; int besti[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { bestd[j] = INFINITY; besti[j] = 0x7fffffff; }
+        for (int j = 0; j < 4; j++) { bestk[j] = KEY_INF; besti[j] = 0x7fffffff; }
         for (int t = lane; t < cnt; t += 32) {
             const int i = mem[t];
             const double* row = M + (size_t)i * K;
@@ -236,16 +238,16 @@ __device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* 
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (j < nl) {
-                    const double d = __dsub_rn(row[ls[j]], mk);
+                    const unsigned long long key = dkey(__dsub_rn(row[ls[j]], mk));
                     // the list is unordered: ties resolve to the lowest row index explicitly
-                    if (besti[j] == 0x7fffffff || d < bestd[j] || (d == bestd[j] && i < besti[j])) { bestd[j] = d; besti[j] = i; }
+                    if (key < bestk[j] || (key == bestk[j] && i < besti[j])) { bestk[j] = key; besti[j] = i; }
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (j >= nl) break;                        // warp-uniform
-            const unsigned long long key = besti[j] == 0x7fffffff ? KEY_INF : dkey(bestd[j]);
+            const unsigned long long key = bestk[j];
             const unsigned hi = (unsigned)(key >> 32);
             const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
             const unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
@@ -342,22 +344,23 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
     v.sigma = dyn_smem + sizeof(SolverSmem);
     v.pos = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_pos(N));
     v.members = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_members(N));
-    v.Ms = reinterpret_cast<double*>(dyn_smem + solver_off_M(N, K));
+    v.Mf = reinterpret_cast<float*>(dyn_smem + solver_off_M(N, K));
     uint8_t* sigma = v.sigma;
     const int tid = threadIdx.x, warp = tid >> 5;
-    // the cost matrix is re-read in every sweep and repair step: keep it in shared memory when it fits
+    // FP64 issues at a small fraction of the FP32 rate on this part, so the price search (a heuristic: any
+    // prices are admissible) runs in fp32 on a shared-memory copy of the costs; only the final assignment and
+    // the exact repair steps touch the fp64 matrix.
     const double* M = M_global;
-    if (m_in_smem) {
-        for (int e = tid; e < N * K; e += SOLVER_THREADS) v.Ms[e] = M_global[e];
-        M = v.Ms;
-    }
+    // class-major copy: lane i reads Mf[l*N + i], conflict-free (a row-major row per lane is a 16-way conflict)
+    if (m_in_smem) for (int e = tid; e < N * K; e += SOLVER_THREADS) { const int i = e / K, l = e - i * K; v.Mf[l * N + i] = (float)M_global[e]; }
     if (tid < KP) {
         sm.cnt[tid] = 0;
         sm.b[tid] = hist ? hist[blockIdx.x * KP + tid] : demand_by_value.b[tid];
         if (tid >= K) sm.b[tid] = 0;
         sm.price[tid] = (prices_in && tid < K) ? prices_in[tid] : 0.0;
-        sm.best_price[tid] = sm.price[tid];
-        sm.step[tid] = step0;
+        sm.pricef[tid] = (float)sm.price[tid];
+        sm.best_pricef[tid] = sm.pricef[tid];
+        sm.step[tid] = (float)step0;
         sm.prev_sign[tid] = 0;
     }
     if (tid == 0) { sm.status = 0; sm.path_len = 0; sm.best_resid = 0x7fffffff; sm.stop = 0; }
@@ -369,12 +372,16 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
         if (tot != N) sm.status |= ST_BAD_DEMAND;
     }
 
-    // ---- 1. price search
+    // ---- 1. price search (fp32)
     for (int it = 0; it <= dual_iters; it++) {
         for (int i = tid; i < N; i += SOLVER_THREADS) {
-            const double* row = M + (size_t)i * K;
-            double bv = INFINITY; int s = 0;
-            for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+            float bv = INFINITY; int s = 0;
+            if (m_in_smem) {
+                for (int l = 0; l < K; l++) { const float x = v.Mf[l * N + i] - sm.pricef[l]; if (x < bv) { bv = x; s = l; } }
+            } else {
+                const double* row = M_global + (size_t)i * K;
+                for (int l = 0; l < K; l++) { const float x = (float)row[l] - sm.pricef[l]; if (x < bv) { bv = x; s = l; } }
+            }
             atomicAdd(&sm.cnt[s], 1);
         }
         __syncthreads();
@@ -385,30 +392,33 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
             for (int o = 16; o > 0; o >>= 1) resid += __shfl_xor_sync(0xffffffffu, resid, o);
             resid >>= 1;
             const bool better = resid < sm.best_resid;                 // same value in every lane
+            const bool last = resid == 0 || it == dual_iters;
             __syncwarp();
-            if (better && lane < KP) sm.best_price[lane] = sm.price[lane];
+            if (better && lane < KP) sm.best_pricef[lane] = sm.pricef[lane];
             if (lane == 0) {
                 if (better) sm.best_resid = resid;
-                sm.stop = (resid == 0 || it == dual_iters) ? 1 : 0;
+                sm.stop = last ? 1 : 0;
             }
-            if (lane < K && !(resid == 0 || it == dual_iters)) {
+            if (lane < K && !last) {
                 const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
-                double st = sm.step[lane];
+                float st = sm.step[lane];
                 const int ps = sm.prev_sign[lane];
-                if (sg * ps < 0) st *= 0.5; else if (sg * ps > 0) st *= 1.2;
+                if (sg * ps < 0) st *= 0.5f; else if (sg * ps > 0) st *= 1.2f;
                 sm.step[lane] = st; sm.prev_sign[lane] = sg;
-                sm.price[lane] += st * (double)sg;                     // too few rows -> cheaper class
+                sm.pricef[lane] += st * (float)sg;                     // too few rows -> cheaper class
             }
             if (lane < KP) sm.cnt[lane] = 0;
         }
         __syncthreads();
         if (sm.stop) break;
     }
+    if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
+    __syncthreads();
     // final assignment under the best prices + member lists (list order is arbitrary; no result depends on it)
     for (int i = tid; i < N; i += SOLVER_THREADS) {
         const double* row = M + (size_t)i * K;
         double bv = INFINITY; int s = 0;
-        for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.best_price[l]); if (x < bv) { bv = x; s = l; } }
+        for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
         sigma[i] = (uint8_t)s;
         const int slot = atomicAdd(&sm.cnt[s], 1);
         v.members[(size_t)s * N + slot] = (uint16_t)i;
@@ -666,11 +676,11 @@ rank_split_kernel(const T* __restrict__ probs, int n_all, double ratio, float th
 // shared memory of one solver CTA: control block, assignment bytes, list positions, member lists
 // (+ the cost matrix when it fits)
 static bool solver_m_fits(int N, int K) {
-    return solver_off_M(N, K) + (size_t)N * K * sizeof(double) <= 200 * 1024;
+    return solver_off_M(N, K) + (size_t)N * K * sizeof(float) <= 220 * 1024;
 }
 static int solver_smem_bytes(int N, int K) {
     size_t b = solver_off_M(N, K);
-    if (solver_m_fits(N, K)) b += (size_t)N * K * sizeof(double);
+    if (solver_m_fits(N, K)) b += (size_t)N * K * sizeof(float);
     return (int)b;
 }
 
