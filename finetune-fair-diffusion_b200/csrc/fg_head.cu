@@ -9,6 +9,7 @@
 // GEMM-shaped work on the path (2.46 MFLOP per face); the tcgen05 version is in fg_head_tc.cu and
 // is selected for bf16/fp16 inputs when FG_HEAD_TC is enabled.
 #include "fg_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -115,10 +116,10 @@ head_logits_kernel(const T* __restrict__ pre, const T* __restrict__ w2, const T*
 }
 
 // g_pre[m,j] = hardswish'(pre[m,j]) * sum_k g_logits[m,k] * W2[k,j]
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 head_bwd_hidden_kernel(const float* __restrict__ g_logits, const T* __restrict__ pre, const T* __restrict__ w2,
-                       float* __restrict__ g_pre, int m, int d_hid, int k_head) {
+                       TO* __restrict__ g_pre, int m, int d_hid, int k_head) {
     extern __shared__ float gl[];            // [k_head] for this row
     int row = blockIdx.x;
     for (int k = threadIdx.x; k < k_head; k += blockDim.x) gl[k] = g_logits[(size_t)row * k_head + k];
@@ -126,7 +127,7 @@ head_bwd_hidden_kernel(const float* __restrict__ g_logits, const T* __restrict__
     for (int j = threadIdx.x; j < d_hid; j += blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < k_head; k++) s = fmaf(gl[k], to_f32(w2[(size_t)k * d_hid + j]), s);
-        g_pre[(size_t)row * d_hid + j] = s * hardswish_grad(to_f32(pre[(size_t)row * d_hid + j]));
+        g_pre[(size_t)row * d_hid + j] = from_f32<TO>(s * hardswish_grad(to_f32(pre[(size_t)row * d_hid + j])));
     }
 }
 
@@ -169,20 +170,69 @@ __global__ void head_attr_kernel(const float* __restrict__ logits, int m, int k_
     }
 }
 
+#include "fg_head_tc.cuh"
+
+// tensor-core path: 16-bit operands, K and N multiples of 64, 16-byte aligned rows
+static bool tc_ok(int dtype, int m, int d_in, int d_hid, int k_head, const void* a, const void* b) {
+    return (dtype == FG_BF16 || dtype == FG_F16) && m > 0 && d_in % 64 == 0 && d_hid % 64 == 0 && k_head <= 256 &&
+           ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && getenv("FG_HEAD_SIMT") == nullptr;
+}
+
+template <typename T>
+static int head_fwd_tc(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2, int m, int d_in,
+                       int d_hid, int k_head, void* hidden_pre, float* logits, float* part, cudaStream_t st) {
+    tc::Params p;
+    p.A = pooled; p.lda = d_in; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_hid; p.K = d_in;
+    p.bias = b1; p.out = hidden_pre; p.ldo = d_hid; p.w2 = w2; p.k_head = k_head; p.part = part;
+    const size_t smem = tc::smem_bytes(0, k_head);
+    cudaError_t e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM);
+    tc::head_gemm_tc_kernel<T, 0><<<grid, tc::THREADS, smem, st>>>(p);
+    const int tot = m * k_head;
+    tc::head_reduce_partials_kernel<T><<<(tot + 255) / 256, 256, 0, st>>>(part, (const T*)b2, d_hid / tc::BN, m, k_head, logits);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+template <typename T>
+static int head_bwd_tc(const float* g_logits, const void* hidden_pre, const void* w1, const void* w2, int m, int d_in, int d_hid,
+                       int k_head, void* g_pooled, void* g_pre16, cudaStream_t st) {
+    head_bwd_hidden_kernel<T, T><<<m, 256, k_head * sizeof(float), st>>>(g_logits, (const T*)hidden_pre, (const T*)w2, (T*)g_pre16,
+                                                                        m, d_hid, k_head);
+    tc::Params p;
+    p.A = g_pre16; p.lda = d_hid; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_in; p.K = d_hid;
+    p.bias = nullptr; p.out = g_pooled; p.ldo = d_in; p.w2 = nullptr; p.k_head = 0; p.part = nullptr;
+    const size_t smem = tc::smem_bytes(1, 0);
+    cudaError_t e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(d_in / tc::BN, (m + tc::BM - 1) / tc::BM);
+    tc::head_gemm_tc_kernel<T, 1><<<grid, tc::THREADS, smem, st>>>(p);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
 }  // namespace
 
 extern "C" size_t fg_head_workspace_bytes(int m, int d_in, int d_hid, int k_head, int dtype) {
-    (void)d_in; (void)k_head; (void)dtype;
-    return fg_align_up((size_t)(m > 0 ? m : 1) * d_hid * sizeof(float), 256);
+    (void)d_in; (void)dtype;
+    // backward: g_pre [m, d_hid] (fp32, or 16-bit on the tensor-core path); forward: partial logits [d_hid/64, m, k_head]
+    size_t rows = (size_t)(m > 0 ? m : 1);
+    size_t a = rows * d_hid * sizeof(float), b = (size_t)((d_hid + 63) / 64) * rows * k_head * sizeof(float);
+    return fg_align_up(a > b ? a : b, 256);
 }
 
 extern "C" int fg_head_fwd(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2,
                            int m, int d_in, int d_hid, int k_head, void* hidden_pre, float* logits,
                            void* workspace, size_t workspace_bytes, int dtype, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     if (m < 0 || d_in <= 0 || d_hid <= 0 || k_head <= 0) return FG_ERR_INVALID_ARG;
     if (!pooled || !w1 || !b1 || !w2 || !b2 || !hidden_pre || !logits) return FG_ERR_INVALID_ARG;
     if (m == 0) return FG_OK;
+    if (tc_ok(dtype, m, d_in, d_hid, k_head, pooled, w1)) {
+        if (!workspace || workspace_bytes < fg_head_workspace_bytes(m, d_in, d_hid, k_head, dtype)) return FG_ERR_WORKSPACE;
+        if (dtype == FG_BF16) return head_fwd_tc<__nv_bfloat16>(pooled, w1, b1, w2, b2, m, d_in, d_hid, k_head, hidden_pre, logits, (float*)workspace, fg_stream(stream));
+        return head_fwd_tc<__half>(pooled, w1, b1, w2, b2, m, d_in, d_hid, k_head, hidden_pre, logits, (float*)workspace, fg_stream(stream));
+    }
     dim3 grid((d_hid + 63) / 64, (m + 63) / 64);
     int groups = (k_head + 7) / 8;
     long long warps = (long long)m * groups;
@@ -202,10 +252,14 @@ extern "C" int fg_head_bwd(const float* g_logits, const void* hidden_pre, const 
     if (!g_logits || !hidden_pre || !w1 || !w2 || !g_pooled) return FG_ERR_INVALID_ARG;
     if (m == 0) return FG_OK;
     if (!workspace || workspace_bytes < fg_head_workspace_bytes(m, d_in, d_hid, k_head, dtype)) return FG_ERR_WORKSPACE;
+    if (tc_ok(dtype, m, d_in, d_hid, k_head, hidden_pre, w1)) {
+        if (dtype == FG_BF16) return head_bwd_tc<__nv_bfloat16>(g_logits, hidden_pre, w1, w2, m, d_in, d_hid, k_head, g_pooled, workspace, fg_stream(stream));
+        return head_bwd_tc<__half>(g_logits, hidden_pre, w1, w2, m, d_in, d_hid, k_head, g_pooled, workspace, fg_stream(stream));
+    }
     float* g_pre = (float*)workspace;
     dim3 grid((d_in + 63) / 64, (m + 63) / 64);
     FG_DISPATCH_DTYPE(dtype, T,
-        head_bwd_hidden_kernel<T><<<m, 256, k_head * sizeof(float), fg_stream(stream)>>>(
+        head_bwd_hidden_kernel<T, float><<<m, 256, k_head * sizeof(float), fg_stream(stream)>>>(
             g_logits, (const T*)hidden_pre, (const T*)w2, g_pre, m, d_hid, k_head);
         gemm_tile_kernel<float, T, T, false, false><<<grid, 256, 0, fg_stream(stream)>>>(
             g_pre, (const T*)w1, nullptr, (T*)g_pooled, m, d_in, d_hid));

@@ -1,0 +1,236 @@
+// Tensor-core (tcgen05 + TMEM) version of the head's dense projections for bf16 / fp16 inputs.
+// Included by fg_head.cu inside its anonymous namespace.
+//
+//   forward   pre[m, d_hid]  = pooled[m, d_in] * W1^T + b1            (Linear(960,1280), E1:929 classifier[0])
+//             part[t, m, k]  = sum_{n in tile t} hardswish(pre[m,n]) * W2[k,n]   (Hardswish + Linear(1280,K) fused
+//                                                                      into the epilogue, one partial per N tile)
+//   backward  g_pooled[m, d_in] = g_pre[m, d_hid] * W1                (frozen weights: no weight gradient)
+//
+// One CTA computes a 128 x 64 output tile: M = 128 rows live on the 128 TMEM lanes, the fp32 accumulator takes 64
+// TMEM columns, K advances 64 elements per shared-memory stage (4 tcgen05.mma of K = 16 each).  Operands are staged
+// by all 128 threads with 16-byte global loads into the canonical K-major, no-swizzle UMMA layout (8 x 16-byte core
+// matrices; LBO = stride between core matrices along K, SBO = stride between 8-row groups), two stages deep so the
+// loads of stage s+1 overlap the MMAs of stage s; completion is tracked with tcgen05.commit on mbarriers.  The
+// backward reads W1 with N contiguous and transposes it while staging.  The problem is tiny (2.5 GFLOP at m = 1024),
+// so the kernel is built for low latency and few launches, not for peak tensor throughput.
+#pragma once
+
+namespace tc {
+
+constexpr int BM = 128, BN = 64, BK = 64;
+constexpr int THREADS = 128;
+constexpr int A_STAGE = BM * BK * 2;            // bytes (16-bit operands)
+constexpr int B_STAGE = BN * BK * 2;
+constexpr int A_LBO = BM * 16, B_LBO = BN * 16; // K-direction stride between core matrices
+constexpr int SBO = 128;                        // M/N-direction stride between 8-row groups
+constexpr int TMEM_COLS = 64;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout NONE [61,64)
+    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t instr_desc(int a_fmt, int b_fmt) {
+    // cute::UMMA::InstrDescriptor: c_format F32 = 1 [4,6) | a_format [7,10) | b_format [10,13) | K-major A,B |
+    // n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
+                 :: "r"(s32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+template <typename T> struct Fmt;
+template <> struct Fmt<__nv_bfloat16> { static constexpr int code = 1; };
+template <> struct Fmt<__half> { static constexpr int code = 0; };
+
+struct Params {
+    const void* A; int lda;           // [M, K] row-major, 16-bit
+    const void* B; int ldb;           // MODE 0: [N, K] row-major (K contiguous); MODE 1: [K, N] row-major (N contiguous)
+    int M, N, K;
+    const void* bias;                 // MODE 0: b1 [N]
+    void* out; int ldo;               // MODE 0: pre [M, N]; MODE 1: g_pooled [M, N]
+    const void* w2; int k_head;       // MODE 0: W2 [k_head, N]
+    float* part;                      // MODE 0: [N/BN, M, k_head]
+};
+
+// dynamic smem: 2 x (A stage | B stage) | W2 tile fp32 [k_head][BN] | b1 tile [BN] | mbarriers | tmem slot
+template <typename T, int MODE>
+__global__ void __launch_bounds__(THREADS)
+head_gemm_tc_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stageA[2] = {smem, smem + A_STAGE + B_STAGE};
+    uint8_t* stageB[2] = {smem + A_STAGE, smem + 2 * A_STAGE + B_STAGE};
+    float* w2s = reinterpret_cast<float*>(smem + 2 * (A_STAGE + B_STAGE));
+    float* b1s = w2s + (MODE == 0 ? p.k_head * BN : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + BN);          // [0,1]: stage free, [2]: accumulator ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const T* A = reinterpret_cast<const T*>(p.A);
+    const T* B = reinterpret_cast<const T*>(p.B);
+
+    if (tid == 0) {
+        bar_init(&bars[0], 1); bar_init(&bars[1], 1); bar_init(&bars[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (MODE == 0) {
+        const T* w2 = reinterpret_cast<const T*>(p.w2);
+        const T* b1 = reinterpret_cast<const T*>(p.bias);
+        for (int e = tid; e < p.k_head * BN; e += THREADS) { int k = e / BN, n = e - k * BN; w2s[e] = to_f32(w2[(size_t)k * p.N + n0 + n]); }
+        for (int e = tid; e < BN; e += THREADS) b1s[e] = to_f32(b1[n0 + e]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code);
+
+    const int ksteps = p.K / BK;
+    for (int ks = 0; ks < ksteps; ks++) {
+        const int st = ks & 1;
+        if (ks >= 2) bar_wait(&bars[st], (uint32_t)(((ks >> 1) - 1) & 1));   // MMAs that read this stage are done
+        const int k0 = ks * BK;
+        // ---- stage A: 128 rows x 8 chunks of 8 elements
+#pragma unroll
+        for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (m0 + r < p.M) v = *reinterpret_cast<const int4*>(A + (size_t)(m0 + r) * p.lda + k0 + kc * 8);
+            *reinterpret_cast<int4*>(stageA[st] + kc * A_LBO + r * 16) = v;
+        }
+        // ---- stage B
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
+                const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
+                const int4 v = *reinterpret_cast<const int4*>(B + (size_t)(n0 + r) * p.ldb + k0 + kc * 8);
+                *reinterpret_cast<int4*>(stageB[st] + kc * B_LBO + r * 16) = v;
+            }
+        } else {
+            // B is [K, N] with N contiguous: read 8 consecutive n of one k, scatter them into 8 core-matrix rows
+#pragma unroll
+            for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
+                const int c = tid + THREADS * j, k = c >> 3, nc = c & 7;
+                const int4 v = *reinterpret_cast<const int4*>(B + (size_t)(k0 + k) * p.ldb + n0 + nc * 8);
+                const uint16_t* e = reinterpret_cast<const uint16_t*>(&v);
+                uint8_t* base = stageB[st] + (k >> 3) * B_LBO + nc * 128 + (k & 7) * 2;
+#pragma unroll
+                for (int q = 0; q < 8; q++) *reinterpret_cast<uint16_t*>(base + q * 16) = e[q];
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = s32(stageA[st]), b0 = s32(stageB[st]);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; kk++) {
+                const uint64_t ad = smem_desc(a0 + kk * 2 * A_LBO, A_LBO, SBO);
+                const uint64_t bd = smem_desc(b0 + kk * 2 * B_LBO, B_LBO, SBO);
+                mma_f16(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
+            }
+            mma_commit(&bars[st]);                                        // implies fence::before_thread_sync
+            if (ks == ksteps - 1) mma_commit(&bars[2]);
+        }
+    }
+    bar_wait(&bars[2], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: thread = output row (TMEM lane), 2 chunks of 32 columns
+    const int row = m0 + tid;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    T* out = reinterpret_cast<T*>(p.out);
+    if (MODE == 0) {
+        float part[8];
+        for (int kb = 0; kb < p.k_head; kb += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) part[q] = 0.f;
+            for (int ch = 0; ch < BN / 32; ch++) {
+                float v[32];
+                tmem_ld32(lane_base + ch * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float pre = round_to<T>(v[i] + b1s[ch * 32 + i]);
+                    const float r6 = fminf(fmaxf(pre + 3.f, 0.f), 6.f);
+                    v[i] = round_to<T>(pre * r6 * (1.f / 6.f));
+                    if (kb == 0 && row < p.M) out[(size_t)row * p.ldo + n0 + ch * 32 + i] = from_f32<T>(pre);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (kb + q < p.k_head) {
+                        const float* wr = w2s + (kb + q) * BN + ch * 32;
+                        float a = part[q];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) a = fmaf(v[i], wr[i], a);
+                        part[q] = a;
+                    }
+                }
+            }
+            if (row < p.M)
+                for (int q = 0; q < 8 && kb + q < p.k_head; q++)
+                    p.part[((size_t)blockIdx.x * p.M + row) * p.k_head + kb + q] = part[q];
+        }
+    } else {
+        for (int ch = 0; ch < BN / 32; ch++) {
+            float v[32];
+            tmem_ld32(lane_base + ch * 32, v);
+            if (row < p.M) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) out[(size_t)row * p.ldo + n0 + ch * 32 + i] = from_f32<T>(v[i]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// logits[m,k] = b2[k] + sum_t part[t,m,k]   (fixed order: deterministic)
+template <typename T>
+__global__ void head_reduce_partials_kernel(const float* __restrict__ part, const T* __restrict__ b2, int tiles, int m, int k_head,
+                                            float* __restrict__ logits) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m * k_head) return;
+    int k = e % k_head;
+    float s = 0.f;
+    for (int t = 0; t < tiles; t++) s += part[(size_t)t * m * k_head + e];
+    logits[e] = s + to_f32(b2[k]);
+}
+
+inline size_t smem_bytes(int mode, int k_head) {
+    return 2 * (A_STAGE + B_STAGE) + (mode == 0 ? (size_t)k_head * BN * 4 : 0) + BN * 4 + 3 * 8 + 16;
+}
+
+}  // namespace tc

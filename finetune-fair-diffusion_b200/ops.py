@@ -150,8 +150,10 @@ def head_fwd(pooled, w1, b1, w2, b2):
     w1, b1, w2, b2 = (x.to(dt).contiguous() for x in (w1, b1, w2, b2))
     hidden = torch.empty((m, d_hid), dtype=dt, device=pooled.device)
     logits = torch.empty((m, k_head), dtype=torch.float32, device=pooled.device)
+    nbytes = _lib.lib().fg_head_workspace_bytes(m, d_in, d_hid, k_head, _dt(pooled))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=pooled.device)
     check(_lib.lib().fg_head_fwd(_p(pooled), _p(w1), _p(b1), _p(w2), _p(b2), m, d_in, d_hid, k_head, _p(hidden), _p(logits),
-                                 None, 0, _dt(pooled), _stream()), "fg_head_fwd")
+                                 _p(ws), nbytes, _dt(pooled), _stream()), "fg_head_fwd")
     return logits, hidden
 
 

@@ -177,11 +177,13 @@ def test_crop_adjoint_property_full_size(fg):
 
 
 # ----------------------------------------------------------------------------- head
-@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
-def test_head_fwd_bwd_vs_torch(fg, dtype, rtol):
+@pytest.mark.parametrize("m,kh", [(77, 8), (300, 80), (1024, 6)])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2), (torch.float16, 5e-3)])
+def test_head_fwd_bwd_vs_torch(fg, dtype, rtol, m, kh):
+    """fp32 runs the fp32-accumulate CUDA-core GEMM, bf16/fp16 the tcgen05 kernel (UTCHMMA in SASS)."""
     from oracle import head as ohead
     torch.manual_seed(0)
-    m, d_in, d_hid, kh = 77, 960, 1280, 8
+    d_in, d_hid = 960, 1280
     pooled = torch.randn(m, d_in).to(dtype)
     w1 = (torch.randn(d_hid, d_in) / d_in ** 0.5).to(dtype); b1 = (torch.randn(d_hid) * 0.1).to(dtype)
     w2 = (torch.randn(kh, d_hid) / d_hid ** 0.5).to(dtype); b2 = (torch.randn(kh) * 0.1).to(dtype)
