@@ -196,7 +196,10 @@ def test_head_fwd_bwd_vs_torch(fg, dtype, rtol, m, kh):
     close(out, ref.detach().numpy(), rtol, rtol * float(ref.abs().max()))
     (out * gl.to(DEV)).sum().backward()
     # bf16: hidden activations are stored in bf16 (2^-9 relative each) before the 1280-term reduction
-    close(xd.grad, x.grad.numpy(), rtol, (1.0 if dtype == torch.float32 else 2.0) * rtol * float(x.grad.abs().max()))
+    # elementwise: hardswish' jumps at x = -3 (0 -> -0.5) and x = 3; a pre-activation stored in 16 bits can
+    # land on the other side of the kink than the fp32 reference, which moves single elements by a few percent
+    # of the largest gradient (torch's own 16-bit path has the same property).  The bar is the norm-wise error.
+    close(xd.grad, x.grad.numpy(), rtol, (rtol if dtype == torch.float32 else 0.05) * float(x.grad.abs().max()))
     rel = (xd.grad.float().cpu() - x.grad).norm() / x.grad.norm()
     assert rel < rtol, rel
 
