@@ -10,7 +10,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libfairguide.so")
+LIB_PATH = os.environ.get("FG_LIB", os.path.join(CSRC, "libfairguide.so"))   # FG_LIB: kernel-tuning builds only
 
 F32, BF16, F16 = 0, 1, 2
 

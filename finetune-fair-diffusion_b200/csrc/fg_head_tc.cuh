@@ -120,31 +120,41 @@ head_gemm_tc_kernel(const Params p) {
     const int ksteps = p.K / BK;
     for (int ks = 0; ks < ksteps; ks++) {
         const int st = ks & 1;
-        if (ks >= 2) bar_wait(&bars[st], (uint32_t)(((ks >> 1) - 1) & 1));   // MMAs that read this stage are done
         const int k0 = ks * BK;
+        // all global loads of this stage are issued before anything is stored (the stores go through generic
+        // pointers, so the compiler would otherwise keep each load behind the previous store), and before the wait
+        // for the stage to be free, so their latency overlaps the MMAs still reading it
+        int4 va[(BM * BK / 8) / THREADS], vb[(BN * BK / 8) / THREADS];
+#pragma unroll
+        for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
+            va[j] = make_int4(0, 0, 0, 0);
+            if (m0 + r < p.M) va[j] = __ldg(reinterpret_cast<const int4*>(A + (size_t)(m0 + r) * p.lda + k0 + kc * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j, r = c >> 3, q = c & 7;
+            if (MODE == 0) vb[j] = __ldg(reinterpret_cast<const int4*>(B + (size_t)(n0 + r) * p.ldb + k0 + q * 8));
+            else           vb[j] = __ldg(reinterpret_cast<const int4*>(B + (size_t)(k0 + r) * p.ldb + n0 + q * 8));
+        }
+        if (ks >= 2) bar_wait(&bars[st], (uint32_t)(((ks >> 1) - 1) & 1));   // MMAs that read this stage are done
         // ---- stage A: 128 rows x 8 chunks of 8 elements
 #pragma unroll
         for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
             const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
-            int4 v = make_int4(0, 0, 0, 0);
-            if (m0 + r < p.M) v = *reinterpret_cast<const int4*>(A + (size_t)(m0 + r) * p.lda + k0 + kc * 8);
-            *reinterpret_cast<int4*>(stageA[st] + kc * A_LBO + r * 16) = v;
+            *reinterpret_cast<int4*>(stageA[st] + kc * A_LBO + r * 16) = va[j];
         }
         // ---- stage B
-        if (MODE == 0) {
 #pragma unroll
-            for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
-                const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
-                const int4 v = *reinterpret_cast<const int4*>(B + (size_t)(n0 + r) * p.ldb + k0 + kc * 8);
-                *reinterpret_cast<int4*>(stageB[st] + kc * B_LBO + r * 16) = v;
-            }
-        } else {
-            // B is [K, N] with N contiguous: read 8 consecutive n of one k, scatter them into 8 core-matrix rows
-#pragma unroll
-            for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
-                const int c = tid + THREADS * j, k = c >> 3, nc = c & 7;
-                const int4 v = *reinterpret_cast<const int4*>(B + (size_t)(k0 + k) * p.ldb + n0 + nc * 8);
-                const uint16_t* e = reinterpret_cast<const uint16_t*>(&v);
+        for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j;
+            if (MODE == 0) {
+                const int r = c >> 3, kc = c & 7;
+                *reinterpret_cast<int4*>(stageB[st] + kc * B_LBO + r * 16) = vb[j];
+            } else {
+                // B is [K, N] with N contiguous: 8 consecutive n of one k go to 8 core-matrix rows
+                const int k = c >> 3, nc = c & 7;
+                const uint16_t* e = reinterpret_cast<const uint16_t*>(&vb[j]);
                 uint8_t* base = stageB[st] + (k >> 3) * B_LBO + nc * 128 + (k & 7) * 2;
 #pragma unroll
                 for (int q = 0; q < 8; q++) *reinterpret_cast<uint16_t*>(base + q * 16) = e[q];
@@ -179,13 +189,19 @@ head_gemm_tc_kernel(const Params p) {
             for (int q = 0; q < 8; q++) part[q] = 0.f;
             for (int ch = 0; ch < BN / 32; ch++) {
                 float v[32];
+                __align__(16) T prs[32];
                 tmem_ld32(lane_base + ch * 32, v);
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
                     const float pre = round_to<T>(v[i] + b1s[ch * 32 + i]);
                     const float r6 = fminf(fmaxf(pre + 3.f, 0.f), 6.f);
                     v[i] = round_to<T>(pre * r6 * (1.f / 6.f));
-                    if (kb == 0 && row < p.M) out[(size_t)row * p.ldo + n0 + ch * 32 + i] = from_f32<T>(pre);
+                    prs[i] = from_f32<T>(pre);
+                }
+                if (kb == 0 && row < p.M) {
+                    int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(prs)[q];
                 }
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
@@ -207,8 +223,12 @@ head_gemm_tc_kernel(const Params p) {
             float v[32];
             tmem_ld32(lane_base + ch * 32, v);
             if (row < p.M) {
+                __align__(16) T o16[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) out[(size_t)row * p.ldo + n0 + ch * 32 + i] = from_f32<T>(v[i]);
+                for (int i = 0; i < 32; i++) o16[i] = from_f32<T>(v[i]);
+                int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(o16)[q];
             }
         }
     }

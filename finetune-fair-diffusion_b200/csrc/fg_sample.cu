@@ -273,9 +273,16 @@ constexpr int FG_NOT_TILED = 0x7ffffff0;     // shape not covered by the tiled k
 
 template <typename T, int STAGES>
 static int launch_fwd_tiled_t(const FwdParams& p, size_t smem, unsigned grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<T, 3, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    sample_fwd_tiled_kernel<T, 3, STAGES><<<grid, FWD_THREADS, smem, st>>>(p);
+    cudaError_t e;
+    if (p.W == 512) {                              // the BASELINE image width: ring row offsets become immediates
+        e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<T, 3, STAGES, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sample_fwd_tiled_kernel<T, 3, STAGES, 512><<<grid, FWD_THREADS, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(sample_fwd_tiled_kernel<T, 3, STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sample_fwd_tiled_kernel<T, 3, STAGES, 0><<<grid, FWD_THREADS, smem, st>>>(p);
+    }
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -285,9 +292,10 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
                             float fill_value, int dtype, cudaStream_t st) {
     const size_t esz = dtype == FG_F32 ? 4 : 2;
     const size_t row_bytes = (size_t)W * esz;
-    const int stages = dtype == FG_F32 ? 2 : 4;
+    const int stages = dtype == FG_F32 ? 2 : 3;
+    const int rmax = dtype == FG_F32 ? 2 * TOH : 12;             // ring rows per channel (RMAX in the kernel)
     const size_t meta = ((size_t)stages * sizeof(FwdMeta) + 127) / 128 * 128;
-    const size_t smem = 128 + meta + (size_t)stages * 2 * TOH * 3 * row_bytes;
+    const size_t smem = 128 + meta + (size_t)stages * rmax * 3 * row_bytes;
     FwdParams p;
     p.tiles_small = small ? (small_h + TOH - 1) / TOH : 0;
     p.tiles_chip = chips ? (chip_h + TOH - 1) / TOH : 0;
@@ -301,8 +309,8 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
     const unsigned grid = (unsigned)(total < 2LL * FG_NUM_SMS ? total : 2LL * FG_NUM_SMS);   // persistent, 2 CTAs per SM
     switch (dtype) {
         case FG_F32: return launch_fwd_tiled_t<float, 2>(p, smem, grid, st);
-        case FG_BF16: return launch_fwd_tiled_t<__nv_bfloat16, 4>(p, smem, grid, st);
-        case FG_F16: return launch_fwd_tiled_t<__half, 4>(p, smem, grid, st);
+        case FG_BF16: return launch_fwd_tiled_t<__nv_bfloat16, 3>(p, smem, grid, st);
+        case FG_F16: return launch_fwd_tiled_t<__half, 3>(p, smem, grid, st);
         default: return FG_ERR_DTYPE;
     }
 }

@@ -53,6 +53,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+template <typename T> struct Pack2;
+template <> struct Pack2<float> { using type = float2; static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); } };
+template <> struct Pack2<__nv_bfloat16> { using type = __nv_bfloat162; static __device__ __forceinline__ __nv_bfloat162 make(float a, float b) { return __floats2bfloat162_rn(a, b); } };
+template <> struct Pack2<__half> { using type = __half2; static __device__ __forceinline__ __half2 make(float a, float b) { return __floats2half2_rn(a, b); } };
+
 struct FwdParams {
     const void* images; int n, C, H, W;
     const long long* boxes; const uint8_t* ind;
@@ -75,10 +80,11 @@ struct __align__(16) FwdMeta {
     long long out_plane;    // = oh * ow
     unsigned long long out; // pointer to out[img][0][oy0][0]
     int ya[TOH], yb[TOH];   // absolute image rows of the two taps
+    int sa[TOH], sb[TOH];   // ring row slots (per channel) holding those rows
     float l0[TOH], l1[TOH];
 };
 
-template <typename T, int C, int STAGES>
+template <typename T, int C, int STAGES, int WFIX>
 __global__ void __launch_bounds__(FWD_THREADS)
 sample_fwd_tiled_kernel(const FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -87,8 +93,13 @@ sample_fwd_tiled_kernel(const FwdParams p) {
     FwdMeta* meta = reinterpret_cast<FwdMeta*>(smem + 128);
     uint8_t* ring = smem + 128 + ((STAGES * sizeof(FwdMeta) + 127) / 128) * 128;
     constexpr int SLOTS = 2 * TOH * C;
+    // ring rows per channel and stage.  16-bit tiles are fetched "dense": the source rows an output tile touches are
+    // contiguous in the image, so ONE bulk copy per channel brings rows [first, last] at full width (3 copies per tile
+    // instead of 24 -- the copy engine, not HBM, was the limit with one copy per row).  Tiles whose row span exceeds
+    // RMAX (boxes taller than ~2.5x the chip) and fp32 tiles (rows are already 2 KB) use one copy per needed row.
+    constexpr int RMAX = sizeof(T) == 2 ? 12 : 2 * TOH;
     const int W = p.W;
-    const int stage_elems = SLOTS * W;
+    const int stage_elems = C * RMAX * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -119,28 +130,46 @@ sample_fwd_tiled_kernel(const FwdParams p) {
             const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
             const float sx = (float)bw / (float)ow, sy = (float)bh / (float)oh;
             const int rows = min(TOH, oh - oy0);
-            // this lane's row tap: lane -> (c, r, which)
+            // row taps of output row (lane & 3); the tile's source-row span
             uint32_t bytes = 0; const T* src = nullptr; T* dst = nullptr;
             Axis ay; ay.i0 = ay.i1 = 0; ay.l0 = ay.l1 = 0.f;
-            const int c = lane / (2 * TOH), slot = lane - c * 2 * TOH, r = slot >> 1, which = slot & 1;
-            if (b.ok && lane < SLOTS && r < rows) {
-                ay = axis_index(oy0 + r, sy, bh);
-                const int yy = b.y0 + (which ? ay.i1 : ay.i0);
-                Axis a0 = axis_index(0, sx, bw), a1 = axis_index(ow - 1, sx, bw);
-                int xs = b.x0 + a0.i0, xe = b.x0 + a1.i1 + 1;
-                xs = xs < 0 ? 0 : xs; xe = xe > W ? W : xe;
-                xs = (xs / EPV) * EPV; xe = ((xe + EPV - 1) / EPV) * EPV;
-                if (xe > W) xe = W;                         // W*sizeof(T) is a multiple of 16
-                if (yy >= 0 && yy < p.H && xe > xs) {
-                    bytes = (uint32_t)(xe - xs) * sizeof(T);
-                    src = images + ((size_t)img * C + c) * iplane + (size_t)yy * W + xs;
-                    dst = reinterpret_cast<T*>(ring) + (size_t)s * stage_elems + (size_t)lane * W + xs;
+            const int rl = lane & (TOH - 1);
+            if (b.ok && rl < rows) ay = axis_index(oy0 + rl, sy, bh);
+            const int y_first = b.y0 + __shfl_sync(0xffffffffu, ay.i0, 0);
+            const int y_last = b.y0 + __shfl_sync(0xffffffffu, ay.i1, rows - 1);
+            const int yf = y_first < 0 ? 0 : y_first, yl = y_last > p.H - 1 ? p.H - 1 : y_last;
+            const int span = yl - yf + 1;
+            const bool dense = RMAX > 2 * TOH && span <= RMAX;
+            if (b.ok && dense) {
+                if (lane < C && span > 0) {
+                    bytes = (uint32_t)span * (uint32_t)W * (uint32_t)sizeof(T);
+                    src = images + ((size_t)img * C + lane) * iplane + (size_t)yf * W;
+                    dst = reinterpret_cast<T*>(ring) + (size_t)s * stage_elems + (size_t)lane * RMAX * W;
+                }
+            } else if (b.ok && lane < SLOTS) {
+                // one copy per (channel, needed row): lane -> (c, r, which)
+                const int c = lane / (2 * TOH), slot = lane - c * 2 * TOH, r = slot >> 1, which = slot & 1;
+                if (r < rows) {
+                    const Axis ar = axis_index(oy0 + r, sy, bh);
+                    const int yy = b.y0 + (which ? ar.i1 : ar.i0);
+                    Axis a0 = axis_index(0, sx, bw), a1 = axis_index(ow - 1, sx, bw);
+                    int xs = b.x0 + a0.i0, xe = b.x0 + a1.i1 + 1;
+                    xs = xs < 0 ? 0 : xs; xe = xe > W ? W : xe;
+                    xs = (xs / EPV) * EPV; xe = ((xe + EPV - 1) / EPV) * EPV;
+                    if (xe > W) xe = W;                         // W*sizeof(T) is a multiple of 16
+                    if (yy >= 0 && yy < p.H && xe > xs) {
+                        bytes = (uint32_t)(xe - xs) * sizeof(T);
+                        src = images + ((size_t)img * C + c) * iplane + (size_t)yy * W + xs;
+                        dst = reinterpret_cast<T*>(ring) + (size_t)s * stage_elems + (size_t)(c * RMAX + slot) * W + xs;
+                    }
                 }
             }
-            // metadata: lanes 0,2,4,6 (c = 0, which = 0) hold the row taps of rows 0..3
+            // metadata: lanes 0..3 hold the row taps of rows 0..3
             FwdMeta& m = meta[s];
-            if (lane < 2 * TOH && which == 0) {
-                m.ya[r] = b.y0 + ay.i0; m.yb[r] = b.y0 + ay.i1; m.l0[r] = ay.l0; m.l1[r] = ay.l1;
+            if (lane < TOH) {
+                m.ya[lane] = b.y0 + ay.i0; m.yb[lane] = b.y0 + ay.i1; m.l0[lane] = ay.l0; m.l1[lane] = ay.l1;
+                m.sa[lane] = dense ? b.y0 + ay.i0 - yf : 2 * lane;
+                m.sb[lane] = dense ? b.y0 + ay.i1 - yf : 2 * lane + 1;
             }
             if (lane == 0) {
                 m.ok = b.ok ? 1 : 0;
@@ -180,7 +209,38 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                 const T* st = reinterpret_cast<const T*>(ring) + (size_t)s * stage_elems;
                 const int x0 = m.x0, bw = m.bw;
                 const float sx = m.sx;
-                if (m.inside) {
+                if (sizeof(T) == 2 && m.inside && (ow & 1) == 0) {
+                    // interior tile: a thread owns two adjacent output columns (packed store) and two of the
+                    // four rows; with WFIX the row offsets into the ring are compile-time constants
+                    constexpr int HALF = FWD_CONSUMERS / 2;
+                    const int hf = ctid / HALF, pr = ctid - hf * HALF;
+                    const int Wc = WFIX ? WFIX : W;
+                    using P2 = Pack2<T>;
+                    for (int pp = pr; pp < (ow >> 1); pp += HALF) {
+                        const int ox0 = 2 * pp;
+                        const Axis a0 = axis_index(ox0, sx, bw), a1 = axis_index(ox0 + 1, sx, bw);
+                        const T* p0a = st + x0 + a0.i0; const T* p0b = st + x0 + a0.i1;
+                        const T* p1a = st + x0 + a1.i0; const T* p1b = st + x0 + a1.i1;
+#pragma unroll
+                        for (int rr = 0; rr < TOH / 2; rr++) {
+                            const int r = hf * (TOH / 2) + rr;
+                            if (r < rows) {
+                                const float l0 = m.l0[r], l1 = m.l1[r];
+                                const int sa = m.sa[r] * Wc, sb = m.sb[r] * Wc;
+                                T* orow = out + r * ow + ox0;
+#pragma unroll
+                                for (int c = 0; c < C; c++) {
+                                    const int ra = c * RMAX * Wc + sa, rb = c * RMAX * Wc + sb;
+                                    const float t0 = a0.l0 * to_f32(p0a[ra]) + a0.l1 * to_f32(p0b[ra]);
+                                    const float b0 = a0.l0 * to_f32(p0a[rb]) + a0.l1 * to_f32(p0b[rb]);
+                                    const float t1 = a1.l0 * to_f32(p1a[ra]) + a1.l1 * to_f32(p1b[ra]);
+                                    const float b1 = a1.l0 * to_f32(p1a[rb]) + a1.l1 * to_f32(p1b[rb]);
+                                    *reinterpret_cast<typename P2::type*>(orow + c * oplane) = P2::make(l0 * t0 + l1 * b0, l0 * t1 + l1 * b1);
+                                }
+                            }
+                        }
+                    }
+                } else if (m.inside) {
                     for (int ox = ctid; ox < ow; ox += FWD_CONSUMERS) {
                         const Axis ax = axis_index(ox, sx, bw);
                         const int xa = x0 + ax.i0, xb = x0 + ax.i1;
@@ -190,8 +250,8 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                                 const float l0 = m.l0[r], l1 = m.l1[r];
 #pragma unroll
                                 for (int c = 0; c < C; c++) {
-                                    const T* ra = st + (c * 2 * TOH + 2 * r) * W;
-                                    const T* rb = ra + W;
+                                    const T* ra = st + (c * RMAX + m.sa[r]) * W;
+                                    const T* rb = st + (c * RMAX + m.sb[r]) * W;
                                     const float top = ax.l0 * to_f32(ra[xa]) + ax.l1 * to_f32(ra[xb]);
                                     const float bot = ax.l0 * to_f32(rb[xa]) + ax.l1 * to_f32(rb[xb]);
                                     out[c * oplane + r * ow + ox] = from_f32<T>(l0 * top + l1 * bot);
@@ -212,8 +272,8 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                                 const bool ya_in = ya >= 0 && ya < p.H, yb_in = yb >= 0 && yb < p.H;
 #pragma unroll
                                 for (int c = 0; c < C; c++) {
-                                    const T* ra = st + (c * 2 * TOH + 2 * r) * W;
-                                    const T* rb = ra + W;
+                                    const T* ra = st + (c * RMAX + m.sa[r]) * W;
+                                    const T* rb = st + (c * RMAX + m.sb[r]) * W;
                                     const float v00 = (ya_in && xa_in) ? to_f32(ra[xa]) : fill;
                                     const float v01 = (ya_in && xb_in) ? to_f32(ra[xb]) : fill;
                                     const float v10 = (yb_in && xa_in) ? to_f32(rb[xa]) : fill;
@@ -234,6 +294,14 @@ sample_fwd_tiled_kernel(const FwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------- backward
+#ifndef BWD_MINB
+#define BWD_MINB 4                // resident CTAs per SM the register allocation targets (latency-bound kernel)
+#endif
+#ifndef BWD_UNROLL
+#define BWD_UNROLL 4              // rows of the stage-2 loop in flight per thread
+#endif
+#define FG_PRAGMA_(x) _Pragma(#x)
+#define FG_UNROLL(n) FG_PRAGMA_(unroll n)
 constexpr int BTH = 8;            // source rows per sub-tile
 constexpr int BSUB = 4;           // sub-tiles per CTA
 constexpr int TABW = 4;           // tap weights kept per table entry
@@ -285,14 +353,9 @@ struct BwdParams {
     int n, C, H, W, ch, cw, sh, sw;
 };
 
-template <typename T> struct Pack2;
-template <> struct Pack2<float> { using type = float2; static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); } };
-template <> struct Pack2<__nv_bfloat16> { using type = __nv_bfloat162; static __device__ __forceinline__ __nv_bfloat162 make(float a, float b) { return __floats2bfloat162_rn(a, b); } };
-template <> struct Pack2<__half> { using type = __half2; static __device__ __forceinline__ __half2 make(float a, float b) { return __floats2half2_rn(a, b); } };
-
 // dynamic smem: Tab ytab[2][BSUB*BTH]; float tb[2][C][BTH][owp]
 template <typename T, int C>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, BWD_MINB)
 image_grad_tiled_kernel(const BwdParams p, int owp) {
     extern __shared__ __align__(16) uint8_t smem[];
     Tab* ytab = reinterpret_cast<Tab*>(smem);                              // [2][BSUB*BTH]
@@ -369,6 +432,18 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
     const int tstride_c = BTH * owp;              // channel stride inside tb
     const int tstride_g = C * tstride_c;          // grid stride
 
+    // ---- common case (>= 2x shrinking resize, box not tiny): stage 2 with byte offsets against warp-uniform bases
+    const bool fast_common = (small_direct || !has_s) && !small_slow && !chip_slow;
+    const unsigned so0 = (unsigned)xs[0].lo * (unsigned)sizeof(T), so1 = (unsigned)xs[1].lo * (unsigned)sizeof(T);
+    const float wxs0 = xs[0].w[0], wxs1 = xs[1].w[0];
+    const unsigned oo = (unsigned)x_a * (unsigned)sizeof(T);
+    const char* gs_img = reinterpret_cast<const char*>(p.g_small) + (size_t)img * C * p.sh * p.sw * sizeof(T);
+    char* go_img = reinterpret_cast<char*>(p.g_images) + (size_t)img * C * H * W * sizeof(T);
+    const unsigned gplb = (unsigned)(p.sh * p.sw) * (unsigned)sizeof(T), srowb = (unsigned)p.sw * (unsigned)sizeof(T);
+    const unsigned oplb = (unsigned)(H * W) * (unsigned)sizeof(T), orowb = (unsigned)W * (unsigned)sizeof(T);
+    const float* tc0 = tb + tstride_g + xc[0].lo;
+    const float* tc1 = tb + tstride_g + xc[1].lo;
+
     for (int sub = 0; sub < BSUB; sub++) {
         const int y0 = ybase + sub * BTH;
         if (y0 >= H) break;
@@ -415,7 +490,54 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
         __syncthreads();
 
         // ---- stage 2: horizontal pass for this thread's two columns
-        if (x_a < W) {
+        if (fast_common && x_a < W) {
+            const bool do_chip = chip_rows && warp_has_chip;
+FG_UNROLL(BWD_UNROLL)
+            for (int r = 0; r < BTH; r++) {
+                const int y = y0 + r;
+                if (y >= H) break;
+                float o0[C], o1[C];
+#pragma unroll
+                for (int c = 0; c < C; c++) { o0[c] = 0.f; o1[c] = 0.f; }
+                if (has_s) {
+                    const Tab& ty = ytab[sub * BTH + r];
+                    if (ty.n) {                                            // warp-uniform
+                        const bool row_reg = y >= ry0 && y < ry1;
+                        const float wy = ty.w[0];
+                        const float f0 = wy * wxs0 * ((row_reg && in_reg_x[0]) ? rs : 1.f);
+                        const float f1 = wy * wxs1 * ((row_reg && in_reg_x[1]) ? rs : 1.f);
+                        const char* grow = gs_img + (unsigned)ty.lo * srowb;             // warp-uniform
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[c] = f0 * to_f32(*reinterpret_cast<const T*>(grow + c * gplb + so0));
+                            o1[c] = f1 * to_f32(*reinterpret_cast<const T*>(grow + c * gplb + so1));
+                        }
+                    }
+                }
+                if (do_chip) {
+                    const float* t0 = tc0 + r * owp;
+                    const float* t1 = tc1 + r * owp;
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        o0[c] += xc[0].w[0] * t0[c * tstride_c] + xc[0].w[1] * t0[c * tstride_c + 1];
+                        o1[c] += xc[1].w[0] * t1[c * tstride_c] + xc[1].w[1] * t1[c * tstride_c + 1];
+                    }
+                    if (c_wide) {
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[c] += xc[0].w[2] * t0[c * tstride_c + 2] + xc[0].w[3] * t0[c * tstride_c + 3];
+                            o1[c] += xc[1].w[2] * t1[c * tstride_c + 2] + xc[1].w[3] * t1[c * tstride_c + 3];
+                        }
+                    }
+                }
+                char* orow = go_img + (unsigned)y * orowb;                                // warp-uniform
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    using P2 = Pack2<T>;
+                    *reinterpret_cast<typename P2::type*>(orow + c * oplb + oo) = P2::make(o0[c], o1[c]);
+                }
+            }
+        } else if (x_a < W) {
             T* const obase = gout + (size_t)y0 * W + x_a;
 #pragma unroll 2
             for (int r = 0; r < BTH; r++) {
