@@ -317,9 +317,17 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
 
 template <typename T>
 static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(image_grad_tiled_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    image_grad_tiled_kernel<T, 3><<<grid, 256, smem, st>>>(p, owp);
+    const bool spec = p.H == 512 && p.W == 512 && (!p.g_small || (p.sh == 224 && p.sw == 224)) && (!p.g_chips || (p.ch == 224 && p.cw == 224));
+    cudaError_t e;
+    if (spec) {
+        e = cudaFuncSetAttribute(image_grad_tiled_kernel<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        image_grad_tiled_kernel<T, 3, true><<<grid, 256, smem, st>>>(p, owp);
+    } else {
+        e = cudaFuncSetAttribute(image_grad_tiled_kernel<T, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        image_grad_tiled_kernel<T, 3, false><<<grid, 256, smem, st>>>(p, owp);
+    }
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -328,7 +336,8 @@ static int launch_bwd_tiled(const void* g_chips, const void* g_small, const int6
                             const int32_t* region, const float* scale, void* g_images, int n, int C, int H, int W,
                             int chip_h, int chip_w, int small_h, int small_w, int dtype, cudaStream_t st) {
     const int sw = g_small ? small_w : 0, cw = g_chips ? chip_w : 0;
-    const int owp = (sw > cw ? sw : cw) + TPAD;
+    int owp = (sw > cw ? sw : cw) + TPAD;
+    if (H == 512 && W == 512 && owp < 224 + TPAD) owp = 224 + TPAD;     // the specialised kernel assumes 224-wide rows
     const size_t smem = (size_t)2 * BSUB * BTH * sizeof(Tab) + (size_t)2 * 3 * BTH * owp * sizeof(float);
     const bool ok = C == 3 && W <= 512 && (W % 2 == 0) && ((uintptr_t)g_images % 16 == 0) && smem <= 100 * 1024 &&
                     (!g_small || (small_w <= W && small_h <= H));

@@ -354,22 +354,25 @@ struct BwdParams {
 };
 
 // dynamic smem: Tab ytab[2][BSUB*BTH]; float tb[2][C][BTH][owp]
-template <typename T, int C>
+// SPEC: the BASELINE shape (512x512 images, 224x224 chips and resized images) with every stride a compile-time constant
+template <typename T, int C, bool SPEC>
 __global__ void __launch_bounds__(256, BWD_MINB)
-image_grad_tiled_kernel(const BwdParams p, int owp) {
+image_grad_tiled_kernel(const BwdParams p, int owp_arg) {
     extern __shared__ __align__(16) uint8_t smem[];
     Tab* ytab = reinterpret_cast<Tab*>(smem);                              // [2][BSUB*BTH]
     float* tb = reinterpret_cast<float*>(ytab + 2 * BSUB * BTH);           // [2][C][BTH][owp]
     const int img = blockIdx.y;
     const int ybase = blockIdx.x * (BSUB * BTH);
     const int tid = threadIdx.x;
-    const int W = p.W, H = p.H;
+    const int W = SPEC ? 512 : p.W, H = SPEC ? 512 : p.H;
+    const int SH = SPEC ? 224 : p.sh, SW = SPEC ? 224 : p.sw, CH = SPEC ? 224 : p.ch, CW = SPEC ? 224 : p.cw;
+    const int owp = SPEC ? 224 + TPAD : owp_arg;
     const bool has_s = p.g_small != nullptr;
     Box b; b.ok = false; b.x0 = b.y0 = b.x1 = b.y1 = 0;
     if (p.g_chips) b = load_box(p.boxes, p.ind, img, H, W);
     const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
-    const float ssx = (float)W / (float)p.sw, ssy = (float)H / (float)p.sh;
-    const float csx = b.ok ? (float)bw / (float)p.cw : 1.f, csy = b.ok ? (float)bh / (float)p.ch : 1.f;
+    const float ssx = (float)W / (float)SW, ssy = (float)H / (float)SH;
+    const float csx = b.ok ? (float)bw / (float)CW : 1.f, csy = b.ok ? (float)bh / (float)CH : 1.f;
     // boxes so small that more than TABW outputs land on one source pixel take the direct 2-D gather
     // (decided up front from the scale; a count above TABW found while building the tables also
     // switches the CTA to that path, see `overflow` below)
@@ -384,8 +387,8 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
         int y = ybase + r;
         Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
         if (y < H) {
-            if (g == 0) { if (has_s) t = make_tab(y, ssy, H, p.sh); }
-            else if (chip_fast) t = make_tab(y - b.y0, csy, bh, p.ch);
+            if (g == 0) { if (has_s) t = make_tab(y, ssy, H, SH); }
+            else if (chip_fast) t = make_tab(y - b.y0, csy, bh, CH);
         }
         if (t.n > TABW) too_many |= 1 << g;
         if (g == 0 && t.n > 1) too_many |= 4;          // the whole-image resize has more than one tap per source row
@@ -407,8 +410,8 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
 #pragma unroll
         for (int q = 0; q < TABW; q++) { xs[v].w[q] = 0.f; xc[v].w[q] = 0.f; }
         if (x < W) {
-            if (has_s) xs[v] = make_tab(x, ssx, W, p.sw);
-            if (chip_fast) xc[v] = make_tab(x - b.x0, csx, bw, p.cw);
+            if (has_s) xs[v] = make_tab(x, ssx, W, SW);
+            if (chip_fast) xc[v] = make_tab(x - b.x0, csx, bw, CW);
         }
         in_reg_x[v] = x >= rx0 && x < rx1;
         // keep lo + TABW - 1 inside the padded t row even for entries without taps
@@ -437,9 +440,9 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
     const unsigned so0 = (unsigned)xs[0].lo * (unsigned)sizeof(T), so1 = (unsigned)xs[1].lo * (unsigned)sizeof(T);
     const float wxs0 = xs[0].w[0], wxs1 = xs[1].w[0];
     const unsigned oo = (unsigned)x_a * (unsigned)sizeof(T);
-    const char* gs_img = reinterpret_cast<const char*>(p.g_small) + (size_t)img * C * p.sh * p.sw * sizeof(T);
+    const char* gs_img = reinterpret_cast<const char*>(p.g_small) + (size_t)img * C * SH * SW * sizeof(T);
     char* go_img = reinterpret_cast<char*>(p.g_images) + (size_t)img * C * H * W * sizeof(T);
-    const unsigned gplb = (unsigned)(p.sh * p.sw) * (unsigned)sizeof(T), srowb = (unsigned)p.sw * (unsigned)sizeof(T);
+    const unsigned gplb = (unsigned)(SH * SW) * (unsigned)sizeof(T), srowb = (unsigned)SW * (unsigned)sizeof(T);
     const unsigned oplb = (unsigned)(H * W) * (unsigned)sizeof(T), orowb = (unsigned)W * (unsigned)sizeof(T);
     const float* tc0 = tb + tstride_g + xc[0].lo;
     const float* tc1 = tb + tstride_g + xc[1].lo;
@@ -451,7 +454,7 @@ image_grad_tiled_kernel(const BwdParams p, int owp) {
         // ---- stage 1: vertical pass; a thread owns one output column, the row loop is warp-uniform
         for (int g = 0; g < 2; g++) {
             if (g == 0 ? (!has_s_fast || small_direct) : !chip_rows) continue;
-            const int oh = g == 0 ? p.sh : p.ch, ow = g == 0 ? p.sw : p.cw;
+            const int oh = g == 0 ? SH : CH, ow = g == 0 ? SW : CW;
             const T* G = reinterpret_cast<const T*>(g == 0 ? p.g_small : p.g_chips) + (size_t)img * C * oh * ow;
             const size_t gplane = (size_t)oh * ow;
             const int gpl = (int)gplane;                       // host guarantees C*oh*ow < 2^31
@@ -549,13 +552,13 @@ FG_UNROLL(BWD_UNROLL)
                 for (int c = 0; c < C; c++) { o0[c] = 0.f; o1[c] = 0.f; }
                 if (small_slow) {
                     // not reachable for a downscaling resize; kept so that any shape is computed correctly
-                    const T* G = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * p.sh * p.sw;
+                    const T* G = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * SH * SW;
 #pragma unroll
                     for (int v = 0; v < 2; v++) {
                         const int x = x_a + v;
                         if (x < W) {
                             float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
-                            gather_grid_cold<T>(G, C, p.sh, p.sw, x, y, W, H, acc);
+                            gather_grid_cold<T>(G, C, SH, SW, x, y, W, H, acc);
                             const float s = (row_reg && in_reg_x[v]) ? rs : 1.f;
 #pragma unroll
                             for (int c = 0; c < C; c++) { if (v == 0) o0[c] = acc[c] * s; else o1[c] = acc[c] * s; }
@@ -565,8 +568,8 @@ FG_UNROLL(BWD_UNROLL)
                 if (small_direct) {
                     const Tab& ty = ytab[sub * BTH + r];
                     if (ty.n) {                                            // warp-uniform
-                        const T* Gs = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * p.sh * p.sw + ty.lo * p.sw;
-                        const int gpl_s = p.sh * p.sw;
+                        const T* Gs = reinterpret_cast<const T*>(p.g_small) + (size_t)img * C * SH * SW + ty.lo * SW;
+                        const int gpl_s = SH * SW;
                         const float wy = ty.w[0];
                         const float w0 = wy * xs[0].w[0] * ((row_reg && in_reg_x[0]) ? rs : 1.f);
                         const float w1 = wy * xs[1].w[0] * ((row_reg && in_reg_x[1]) ? rs : 1.f);
@@ -613,13 +616,13 @@ FG_UNROLL(BWD_UNROLL)
                 }
                 if (chip_slow) {
                     // rare: tiny box, direct 2-D gather from G (generic kernel's routine)
-                    const T* G = reinterpret_cast<const T*>(p.g_chips) + (size_t)img * C * p.ch * p.cw;
+                    const T* G = reinterpret_cast<const T*>(p.g_chips) + (size_t)img * C * CH * CW;
 #pragma unroll
                     for (int v = 0; v < 2; v++) {
                         const int x = x_a + v;
                         if (x >= b.x0 && x < b.x1 && y >= b.y0 && y < b.y1) {
                             float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
-                            gather_grid_cold<T>(G, C, p.ch, p.cw, x - b.x0, y - b.y0, bw, bh, acc);
+                            gather_grid_cold<T>(G, C, CH, CW, x - b.x0, y - b.y0, bw, bh, acc);
 #pragma unroll
                             for (int c = 0; c < C; c++) { if (v == 0) o0[c] += acc[c]; else o1[c] += acc[c]; }
                         }
