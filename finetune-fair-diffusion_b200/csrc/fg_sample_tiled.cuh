@@ -303,7 +303,7 @@ sample_fwd_tiled_kernel(const FwdParams p) {
 #define FG_PRAGMA_(x) _Pragma(#x)
 #define FG_UNROLL(n) FG_PRAGMA_(unroll n)
 constexpr int BTH = 8;            // source rows per sub-tile
-constexpr int BSUB = 4;           // sub-tiles per CTA
+constexpr int BSUB = 4;           // sub-tiles per CTA (32 rows; 64 and 128 rows measured slower: fewer CTAs, longer tail)
 constexpr int TABW = 4;           // tap weights kept per table entry
 constexpr int TPAD = 4;           // padding of the t rows so that lo + TABW - 1 stays in the row
 
