@@ -25,6 +25,7 @@
 // like POT's; ties resolve to the lowest row index / lowest class index, deterministically.
 #include "fg_common.cuh"
 #include <math.h>
+#include <cstdlib>
 
 namespace {
 
@@ -416,9 +417,23 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
     __syncthreads();
     // final assignment under the best prices + member lists (list order is arbitrary; no result depends on it)
     for (int i = tid; i < N; i += SOLVER_THREADS) {
-        const double* row = M + (size_t)i * K;
-        double bv = INFINITY; int s = 0;
-        for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+        int s = 0;
+        bool exact = true;
+        if (m_in_smem) {
+            // fp32 screen: the prices are fp32 values, so |fp32 reduced cost - fp64 reduced cost| <= 2 ulp(M) ~ 5e-7;
+            // when the runner-up is further away than that the fp64 argmin is the fp32 argmin
+            float b1 = INFINITY, b2 = INFINITY;
+            for (int l = 0; l < K; l++) {
+                const float x = v.Mf[l * N + i] - sm.best_pricef[l];
+                if (x < b1) { b2 = b1; b1 = x; s = l; } else if (x < b2) b2 = x;
+            }
+            exact = !(b2 - b1 > 8e-6f);
+        }
+        if (exact) {
+            const double* row = M + (size_t)i * K;
+            double bv = INFINITY; s = 0;
+            for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+        }
         sigma[i] = (uint8_t)s;
         const int slot = atomicAdd(&sm.cnt[s], 1);
         v.members[(size_t)s * N + slot] = (uint16_t)i;
@@ -709,10 +724,13 @@ static void expected_demand(int n, int K, Demand* d) {
 // base assignment: coarse-to-fine over growing prefixes, each level warm-started by the previous prices
 // price-search schedule: the base starts from zero prices (the greedy assignment), the draws from the
 // base's optimal prices and only have to absorb |b_s - b_base|
-constexpr int BASE_DUAL_ITERS = 40;
-constexpr double BASE_STEP0 = 0.03;
-constexpr int DRAW_DUAL_ITERS = 14;
-constexpr double DRAW_STEP0 = 0.01;
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
+// defaults; the FG_OT_* environment variables exist for tuning runs only (results do not depend on them)
+#define BASE_DUAL_ITERS env_int("FG_OT_BASE_ITERS", 40)
+#define BASE_STEP0 env_dbl("FG_OT_BASE_STEP", 0.03)
+#define DRAW_DUAL_ITERS env_int("FG_OT_DRAW_ITERS", 24)
+#define DRAW_STEP0 env_dbl("FG_OT_DRAW_STEP", 0.01)
 
 // base problem: the expected demand; leaves its optimal prices in w.prices
 static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) {
