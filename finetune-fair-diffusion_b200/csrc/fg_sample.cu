@@ -199,6 +199,7 @@ __global__ void region_scale_kernel(const T* __restrict__ g_in, const int32_t* _
 }
 
 #include "fg_sample_tiled.cuh"
+#include "fg_image_grad_staged.cuh"
 
 // ------------------------------------------------------------------------------ factors
 // python slice semantics: a negative stop counts from the end (E1:1594-1597 with a -1 box)
@@ -319,6 +320,20 @@ template <typename T>
 static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 grid, cudaStream_t st) {
     const bool spec = p.H == 512 && p.W == 512 && (!p.g_small || (p.sh == 224 && p.sw == 224)) && (!p.g_chips || (p.ch == 224 && p.cw == 224));
     cudaError_t e;
+    if constexpr (sizeof(T) == 2) {
+        // 16-bit gradients at the BASELINE shape: rows staged through shared memory by bulk async copies
+        static const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switch for kernel tuning runs
+        const bool aligned = ((uintptr_t)p.g_small % 16 == 0) && ((uintptr_t)p.g_chips % 16 == 0);
+        if (spec && aligned && !staged_off) {
+            constexpr int NSUB = BSUB;
+            using L = GsLayout<NSUB>;
+            e = cudaFuncSetAttribute(image_grad_staged_kernel<T, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+            if (e != cudaSuccess) return (int)e;
+            image_grad_staged_kernel<T, NSUB><<<dim3(512 / (NSUB * GS_ROWS), p.n), 256, L::total, st>>>(p);
+            FG_LAUNCH_CHECK();
+            return FG_OK;
+        }
+    }
     if (spec) {
         e = cudaFuncSetAttribute(image_grad_tiled_kernel<T, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

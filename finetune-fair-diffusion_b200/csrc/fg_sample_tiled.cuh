@@ -494,50 +494,75 @@ image_grad_tiled_kernel(const BwdParams p, int owp_arg) {
 
         // ---- stage 2: horizontal pass for this thread's two columns
         if (fast_common && x_a < W) {
+            // Rows go in groups of BWD_UNROLL: every g_small load of the group is issued before the first use
+            // (no branch inside the group, rows or columns without a tap load a valid dummy address and are
+            // zeroed by a select), so a thread keeps 6 * BWD_UNROLL gathers in flight instead of 6.
             const bool do_chip = chip_rows && warp_has_chip;
-FG_UNROLL(BWD_UNROLL)
-            for (int r = 0; r < BTH; r++) {
-                const int y = y0 + r;
-                if (y >= H) break;
-                float o0[C], o1[C];
-#pragma unroll
-                for (int c = 0; c < C; c++) { o0[c] = 0.f; o1[c] = 0.f; }
+            const bool k0 = xs[0].n != 0, k1 = xs[1].n != 0;
+            const float wxr0 = in_reg_x[0] ? wxs0 * rs : wxs0, wxr1 = in_reg_x[1] ? wxs1 * rs : wxs1;
+#pragma unroll 1
+            for (int r0 = 0; r0 < BTH; r0 += BWD_UNROLL) {
+                float o0[BWD_UNROLL][C], o1[BWD_UNROLL][C];
                 if (has_s) {
-                    const Tab& ty = ytab[sub * BTH + r];
-                    if (ty.n) {                                            // warp-uniform
-                        const bool row_reg = y >= ry0 && y < ry1;
-                        const float wy = ty.w[0];
-                        const float f0 = wy * wxs0 * ((row_reg && in_reg_x[0]) ? rs : 1.f);
-                        const float f1 = wy * wxs1 * ((row_reg && in_reg_x[1]) ? rs : 1.f);
-                        const char* grow = gs_img + (unsigned)ty.lo * srowb;             // warp-uniform
+                    T raw0[BWD_UNROLL][C], raw1[BWD_UNROLL][C];
+#pragma unroll
+                    for (int j = 0; j < BWD_UNROLL; j++) {
+                        const char* grow = gs_img + (unsigned)ytab[sub * BTH + r0 + j].lo * srowb;   // warp-uniform
 #pragma unroll
                         for (int c = 0; c < C; c++) {
-                            o0[c] = f0 * to_f32(*reinterpret_cast<const T*>(grow + c * gplb + so0));
-                            o1[c] = f1 * to_f32(*reinterpret_cast<const T*>(grow + c * gplb + so1));
+                            raw0[j][c] = *reinterpret_cast<const T*>(grow + c * gplb + so0);
+                            raw1[j][c] = *reinterpret_cast<const T*>(grow + c * gplb + so1);
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < BWD_UNROLL; j++) {
+                        const Tab& ty = ytab[sub * BTH + r0 + j];
+                        const int y = y0 + r0 + j;
+                        const bool row_reg = y >= ry0 && y < ry1, rk = ty.n != 0;
+                        const float wy = ty.w[0];
+                        const float f0 = wy * (row_reg ? wxr0 : wxs0), f1 = wy * (row_reg ? wxr1 : wxs1);
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            o0[j][c] = (rk && k0) ? f0 * to_f32(raw0[j][c]) : 0.f;
+                            o1[j][c] = (rk && k1) ? f1 * to_f32(raw1[j][c]) : 0.f;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BWD_UNROLL; j++)
+#pragma unroll
+                        for (int c = 0; c < C; c++) { o0[j][c] = 0.f; o1[j][c] = 0.f; }
                 }
                 if (do_chip) {
-                    const float* t0 = tc0 + r * owp;
-                    const float* t1 = tc1 + r * owp;
 #pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        o0[c] += xc[0].w[0] * t0[c * tstride_c] + xc[0].w[1] * t0[c * tstride_c + 1];
-                        o1[c] += xc[1].w[0] * t1[c * tstride_c] + xc[1].w[1] * t1[c * tstride_c + 1];
-                    }
-                    if (c_wide) {
+                    for (int j = 0; j < BWD_UNROLL; j++) {
+                        const float* t0 = tc0 + (r0 + j) * owp;
+                        const float* t1 = tc1 + (r0 + j) * owp;
 #pragma unroll
                         for (int c = 0; c < C; c++) {
-                            o0[c] += xc[0].w[2] * t0[c * tstride_c + 2] + xc[0].w[3] * t0[c * tstride_c + 3];
-                            o1[c] += xc[1].w[2] * t1[c * tstride_c + 2] + xc[1].w[3] * t1[c * tstride_c + 3];
+                            o0[j][c] += xc[0].w[0] * t0[c * tstride_c] + xc[0].w[1] * t0[c * tstride_c + 1];
+                            o1[j][c] += xc[1].w[0] * t1[c * tstride_c] + xc[1].w[1] * t1[c * tstride_c + 1];
+                        }
+                        if (c_wide) {
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                o0[j][c] += xc[0].w[2] * t0[c * tstride_c + 2] + xc[0].w[3] * t0[c * tstride_c + 3];
+                                o1[j][c] += xc[1].w[2] * t1[c * tstride_c + 2] + xc[1].w[3] * t1[c * tstride_c + 3];
+                            }
                         }
                     }
                 }
-                char* orow = go_img + (unsigned)y * orowb;                                // warp-uniform
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    using P2 = Pack2<T>;
-                    *reinterpret_cast<typename P2::type*>(orow + c * oplb + oo) = P2::make(o0[c], o1[c]);
+                for (int j = 0; j < BWD_UNROLL; j++) {
+                    const int y = y0 + r0 + j;
+                    if (SPEC || y < H) {
+                        char* orow = go_img + (unsigned)y * orowb;                            // warp-uniform
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            using P2 = Pack2<T>;
+                            *reinterpret_cast<typename P2::type*>(orow + c * oplb + oo) = P2::make(o0[j][c], o1[j][c]);
+                        }
+                    }
                 }
             }
         } else if (x_a < W) {
