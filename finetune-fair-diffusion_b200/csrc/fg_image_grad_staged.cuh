@@ -15,8 +15,11 @@
 //   bufS is double-buffered (stage 2 of sub-tile k reads it while k+1 arrives), sC is single-buffered (free
 //   once stage 1 is done).  The 512 -> 224 resize shrinks by more than 2x, so an image pixel receives at
 //   most ONE resized pixel per axis: the small branch is a scaled gather with no vertical pass.
-//   Rows without a tap point at a zero row, columns without a tap are zeroed by a select: a non-finite
-//   gradient never leaks into pixels it does not touch.
+//   Rows and columns without a tap read a zero row of the staging buffer: a non-finite gradient never leaks
+//   into pixels it does not touch, and the row loop has no per-lane branch.
+//   With the latency gone the kernel is bound by instruction issue, so the two row loops are written against
+//   32-bit shared-memory addresses (every offset an immediate once the 8 rows are unrolled) and specialised at
+//   compile time on "has a resized-image gradient / this warp overlaps the box / the box is upscaled".
 //   Boxes the staging buffer cannot hold (more than GS_CROWS chip rows per 8 image rows, i.e. boxes under
 //   ~115 px, or more than 4 taps per pixel) take the direct 2-D gather per pixel (correct, slow, rare).
 #pragma once
@@ -26,9 +29,12 @@ constexpr int GS_SROWS = 6;       // resized rows a sub-tile can touch (<= 5 at 
 constexpr int GS_CROWS = 16;      // chip rows staged per sub-tile
 constexpr int GS_OW = 224;        // width (and height) of both gradient grids
 constexpr int GS_TBW = GS_OW + TPAD;
+constexpr int GS_S_CH = (GS_SROWS + 1) * GS_OW * 2;     // bufS channel stride, bytes
+constexpr int GS_C_CH = GS_CROWS * GS_OW * 2;           // sC channel stride, bytes
+constexpr int GS_T_CH = GS_ROWS * GS_TBW * 4;           // tb channel stride, bytes
 
-struct GsRowS { int off; float wy; };              // element offset of the resized row inside a bufS channel, y weight
-struct GsRowC { int off; int n; float w[TABW]; };  // element offset of the first chip row inside an sC channel, taps
+struct __align__(16) GsRowS { int off; float wy; float wr; int pad; };   // byte offset of the resized row in a bufS channel; y weight; y weight if the row is in the scaled region else 0
+struct __align__(16) GsRowC { int off; int n; float w[TABW]; int pad[2]; };   // byte offset of the first chip row in an sC channel, taps
 struct GsSub { int s_first, s_count, c_first, c_count; };
 
 template <int NSUB> struct GsLayout {
@@ -39,12 +45,108 @@ template <int NSUB> struct GsLayout {
     static constexpr size_t rowC = rowS + ROWS * sizeof(GsRowS);
     static constexpr size_t tabs_end = rowC + ROWS * sizeof(GsRowC);
     static constexpr size_t bufS = (tabs_end + 127) / 128 * 128;
-    static constexpr size_t bufS_bytes = 2 * 3 * (GS_SROWS + 1) * GS_OW * 2;
+    static constexpr size_t bufS_bytes = 2 * 3 * GS_S_CH;
     static constexpr size_t sC = bufS + bufS_bytes;
-    static constexpr size_t sC_bytes = 3 * GS_CROWS * GS_OW * 2;
+    static constexpr size_t sC_bytes = 3 * GS_C_CH;
     static constexpr size_t tb = sC + sC_bytes;
-    static constexpr size_t total = tb + 3 * GS_ROWS * GS_TBW * sizeof(float);
+    static constexpr size_t total = tb + 3 * GS_T_CH;
 };
+
+// shared-memory accesses by 32-bit address (volatile: never merged or hoisted across the barriers)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+template <typename T> __device__ __forceinline__ float bits16_to_f32(uint32_t v);
+template <> __device__ __forceinline__ float bits16_to_f32<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <> __device__ __forceinline__ float bits16_to_f32<__half>(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)v)); }
+
+// stage 1 for one sub-tile: tb[c][r][ox] = sum_q w[r][q] * sC[c][off_r + q][ox]   (this thread: column ox)
+template <typename T>
+__device__ __forceinline__ void gs_stage1(uint32_t rec, uint32_t col, uint32_t tcol) {
+#pragma unroll
+    for (int r = 0; r < GS_ROWS; r++) {
+        const uint4 h = lds_v4(rec + r * 32);                 // off, n, w0, w1     (warp-uniform)
+        float acc[3] = {0.f, 0.f, 0.f};
+        const uint32_t a = col + h.x;
+        const int n = (int)h.y;
+        if (n > 0) {
+            const float w0 = __uint_as_float(h.z), w1 = __uint_as_float(h.w);
+            uint32_t v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] = lds_u16(a + c * GS_C_CH);
+            if (n > 1) {
+                uint32_t u[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) u[c] = lds_u16(a + c * GS_C_CH + GS_OW * 2);
+#pragma unroll
+                for (int c = 0; c < 3; c++) acc[c] = w1 * bits16_to_f32<T>(u[c]);
+                if (n > 2) {
+                    const uint4 h2 = lds_v4(rec + r * 32 + 16);   // w2, w3
+                    const float w2 = __uint_as_float(h2.x), w3 = __uint_as_float(h2.y);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[c] = fmaf(w2, bits16_to_f32<T>(lds_u16(a + c * GS_C_CH + 2 * GS_OW * 2)), acc[c]);
+                    if (n > 3) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) acc[c] = fmaf(w3, bits16_to_f32<T>(lds_u16(a + c * GS_C_CH + 3 * GS_OW * 2)), acc[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] = fmaf(w0, bits16_to_f32<T>(v[c]), acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) sts_f32(tcol + c * GS_T_CH + r * GS_TBW * 4, acc[c]);
+    }
+}
+
+struct GsCols {             // per-thread constants of its two image columns
+    uint32_t s0, s1;        // byte offset of the resized-gradient column inside a bufS buffer (the zero row when no tap)
+    uint32_t m0, m1;        // 1: add the row offset (column has a tap), 0: stay on the zero row
+    float ws0, wd0, ws1, wd1;   // x weight outside the scaled region; (x weight inside) - (x weight outside)
+    uint32_t t0, t1;        // shared address of tb[0][0][lo] for the chip taps
+    float w0[TABW], w1[TABW];
+};
+
+// stage 2 for one sub-tile: 8 image rows x this thread's two columns x 3 channels
+template <typename T, bool DO_S, bool DO_CHIP, bool C_WIDE>
+__device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_t sbuf, char* out) {
+    constexpr unsigned oplb = 512u * 512u * 2u, orowb = 512u * 2u;
+#pragma unroll
+    for (int r = 0; r < GS_ROWS; r++) {
+        float o0[3] = {0.f, 0.f, 0.f}, o1[3] = {0.f, 0.f, 0.f};
+        if (DO_S) {
+            const uint4 h = lds_v4(rec + r * 16);             // off, wy, wr      (warp-uniform)
+            const float wy = __uint_as_float(h.y), wr = __uint_as_float(h.z);
+            const float f0 = fmaf(wr, k.wd0, wy * k.ws0), f1 = fmaf(wr, k.wd1, wy * k.ws1);
+            const uint32_t a0 = sbuf + k.s0 + h.x * k.m0, a1 = sbuf + k.s1 + h.x * k.m1;
+            uint32_t v0[3], v1[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { v0[c] = lds_u16(a0 + c * GS_S_CH); v1[c] = lds_u16(a1 + c * GS_S_CH); }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { o0[c] = f0 * bits16_to_f32<T>(v0[c]); o1[c] = f1 * bits16_to_f32<T>(v1[c]); }
+        }
+        if (DO_CHIP) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint32_t a0 = k.t0 + c * GS_T_CH + r * GS_TBW * 4, a1 = k.t1 + c * GS_T_CH + r * GS_TBW * 4;
+                o0[c] = fmaf(k.w0[0], lds_f32(a0), o0[c]); o0[c] = fmaf(k.w0[1], lds_f32(a0 + 4), o0[c]);
+                o1[c] = fmaf(k.w1[0], lds_f32(a1), o1[c]); o1[c] = fmaf(k.w1[1], lds_f32(a1 + 4), o1[c]);
+                if (C_WIDE) {
+                    o0[c] = fmaf(k.w0[2], lds_f32(a0 + 8), o0[c]); o0[c] = fmaf(k.w0[3], lds_f32(a0 + 12), o0[c]);
+                    o1[c] = fmaf(k.w1[2], lds_f32(a1 + 8), o1[c]); o1[c] = fmaf(k.w1[3], lds_f32(a1 + 12), o1[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            using P2 = Pack2<T>;
+            *reinterpret_cast<typename P2::type*>(out + r * orowb + c * oplb) = P2::make(o0[c], o1[c]);
+        }
+    }
+}
 
 template <typename T, int NSUB>
 __global__ void __launch_bounds__(256, 3)
@@ -52,9 +154,6 @@ image_grad_staged_kernel(const BwdParams p) {
     static_assert(sizeof(T) == 2, "16-bit gradients only");
     using L = GsLayout<NSUB>;
     constexpr int C = 3, H = 512, W = 512, OH = GS_OW, OW = GS_OW, ROWS = NSUB * GS_ROWS;
-    constexpr int S_CH = (GS_SROWS + 1) * OW;         // bufS channel stride (elements)
-    constexpr int C_CH = GS_CROWS * OW;               // sC channel stride
-    constexpr int T_CH = GS_ROWS * GS_TBW;            // tb channel stride
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
     GsSub* subs = reinterpret_cast<GsSub*>(smem + L::subs);
@@ -63,6 +162,7 @@ image_grad_staged_kernel(const BwdParams p) {
     T* bufS = reinterpret_cast<T*>(smem + L::bufS);   // [2][C][GS_SROWS + 1][OW]
     T* sC = reinterpret_cast<T*>(smem + L::sC);       // [C][GS_CROWS][OW]
     float* tb = reinterpret_cast<float*>(smem + L::tb);   // [C][GS_ROWS][GS_TBW]
+    const uint32_t smem_a = smem_u32(smem);
 
     const int img = blockIdx.y, ybase = blockIdx.x * ROWS, tid = threadIdx.x;
     const bool has_s = p.g_small != nullptr;
@@ -73,6 +173,11 @@ image_grad_staged_kernel(const BwdParams p) {
     const float csx = b.ok ? (float)bw / (float)OW : 1.f, csy = b.ok ? (float)bh / (float)OH : 1.f;
     bool chip_cold = b.ok && (csx < 0.51f || csy < 0.51f);
     const bool chip_tab = b.ok && !chip_cold;
+    int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0; float rs = 1.f;
+    if (p.region) {
+        rx0 = p.region[4 * img]; ry0 = p.region[4 * img + 1]; rx1 = p.region[4 * img + 2]; ry1 = p.region[4 * img + 3];
+        rs = p.scale[img];
+    }
 
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
@@ -81,7 +186,7 @@ image_grad_staged_kernel(const BwdParams p) {
     // zero rows of bufS and the pad columns of tb (read with zero weights, so they must stay finite)
     for (int e = tid; e < 2 * C * OW; e += 256) {
         const int bc = e / OW, x = e - bc * OW;
-        bufS[bc * S_CH + GS_SROWS * OW + x] = from_f32<T>(0.f);
+        bufS[bc * (GS_S_CH / 2) + GS_SROWS * OW + x] = from_f32<T>(0.f);
     }
     for (int e = tid; e < C * GS_ROWS * TPAD; e += 256) {
         const int cr = e / TPAD, q = e - cr * TPAD;
@@ -94,13 +199,14 @@ image_grad_staged_kernel(const BwdParams p) {
         if (g == 0) {
             Tab t; t.lo = 0; t.n = 0; t.w[0] = 0.f;
             if (has_s) t = make_tab(y, ss, H, OH);
-            GsRowS rs_; rs_.off = t.n ? t.lo : -1; rs_.wy = t.n ? t.w[0] : 0.f;       // absolute row for now
-            rowS[r] = rs_;
+            GsRowS a; a.off = t.n ? t.lo : -1;                // absolute row for now
+            a.wy = t.n ? t.w[0] : 0.f; a.wr = (y >= ry0 && y < ry1) ? a.wy : 0.f; a.pad = 0;
+            rowS[r] = a;
         } else {
             Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
             if (chip_tab) t = make_tab(y - b.y0, csy, bh, OH);
             if (t.n > TABW) too_many = 1;
-            GsRowC rc; rc.off = t.lo; rc.n = t.n;
+            GsRowC rc; rc.off = t.lo; rc.n = t.n; rc.pad[0] = rc.pad[1] = 0;
 #pragma unroll
             for (int q = 0; q < TABW; q++) rc.w[q] = t.w[q];
             rowC[r] = rc;
@@ -108,50 +214,51 @@ image_grad_staged_kernel(const BwdParams p) {
     }
     // this thread's two image columns
     const int x_a = 2 * tid;
-    int xs_lo[2]; float xs_w[2]; bool xs_k[2];
-    Tab xc[2];
-    bool in_reg_x[2];
-    int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0; float rs = 1.f;
-    if (p.region) {
-        rx0 = p.region[4 * img]; ry0 = p.region[4 * img + 1]; rx1 = p.region[4 * img + 2]; ry1 = p.region[4 * img + 3];
-        rs = p.scale[img];
-    }
+    GsCols k;
+    int xc_n[2];
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const int x = x_a + v;
         Tab t; t.lo = 0; t.n = 0; t.w[0] = 0.f;
         if (has_s) t = make_tab(x, ss, W, OW);
-        xs_k[v] = t.n != 0; xs_lo[v] = t.n ? t.lo : 0; xs_w[v] = t.n ? t.w[0] : 0.f;
-        xc[v].lo = 0; xc[v].n = 0;
+        const bool keep = t.n != 0;
+        const float ws = keep ? t.w[0] : 0.f;
+        const float wd = (x >= rx0 && x < rx1) ? ws * rs - ws : 0.f;
+        const uint32_t so = keep ? (uint32_t)t.lo * 2u : (uint32_t)(GS_SROWS * OW * 2);
+        Tab u; u.lo = 0; u.n = 0;
 #pragma unroll
-        for (int q = 0; q < TABW; q++) xc[v].w[q] = 0.f;
-        if (chip_tab) xc[v] = make_tab(x - b.x0, csx, bw, OW);
-        if (xc[v].n > TABW) too_many = 1;
-        if (xc[v].n == 0) xc[v].lo = 0;
-        in_reg_x[v] = x >= rx0 && x < rx1;
+        for (int q = 0; q < TABW; q++) u.w[q] = 0.f;
+        if (chip_tab) u = make_tab(x - b.x0, csx, bw, OW);
+        if (u.n > TABW) too_many = 1;
+        if (u.n == 0) u.lo = 0;
+        xc_n[v] = u.n;
+        const uint32_t ta = smem_a + (uint32_t)L::tb + (uint32_t)u.lo * 4u;
+        if (v == 0) { k.s0 = so; k.m0 = keep; k.ws0 = ws; k.wd0 = wd; k.t0 = ta; }
+        else        { k.s1 = so; k.m1 = keep; k.ws1 = ws; k.wd1 = wd; k.t1 = ta; }
+#pragma unroll
+        for (int q = 0; q < TABW; q++) { if (v == 0) k.w0[q] = u.w[q]; else k.w1[q] = u.w[q]; }
     }
     if (__syncthreads_or(too_many)) chip_cold = true;               // also orders the table writes
-    // per sub-tile: which rows to stage; turn absolute rows into offsets inside the staging buffers
+    // per sub-tile: which rows to stage; turn absolute rows into byte offsets inside the staging buffers
     too_many = 0;
     if (tid < NSUB) {
         int s_lo = 1 << 30, s_hi = -1, c_lo = 1 << 30, c_hi = -1;
         for (int r = 0; r < GS_ROWS; r++) {
-            const GsRowS a = rowS[tid * GS_ROWS + r];
-            if (a.off >= 0) { s_lo = min(s_lo, a.off); s_hi = max(s_hi, a.off); }
-            const GsRowC c = rowC[tid * GS_ROWS + r];
-            if (c.n > 0) { c_lo = min(c_lo, c.off); c_hi = max(c_hi, min(c.off + c.n - 1, OH - 1)); }
+            const int so = rowS[tid * GS_ROWS + r].off;
+            if (so >= 0) { s_lo = min(s_lo, so); s_hi = max(s_hi, so); }
+            const int co = rowC[tid * GS_ROWS + r].off, cn = rowC[tid * GS_ROWS + r].n;
+            if (cn > 0) { c_lo = min(c_lo, co); c_hi = max(c_hi, min(co + cn - 1, OH - 1)); }
         }
         GsSub d;
         d.s_first = s_hi >= 0 ? s_lo : 0; d.s_count = s_hi >= 0 ? min(s_hi - s_lo + 1, GS_SROWS) : 0;
         d.c_first = c_hi >= 0 ? c_lo : 0; d.c_count = c_hi >= 0 ? c_hi - c_lo + 1 : 0;
         if (d.c_count > GS_CROWS) too_many = 1;
-        if (chip_cold) d.c_count = 0;
         subs[tid] = d;
         for (int r = 0; r < GS_ROWS; r++) {
             GsRowS& a = rowS[tid * GS_ROWS + r];
-            a.off = a.off >= 0 ? (a.off - d.s_first) * OW : GS_SROWS * OW;
+            a.off = (a.off >= 0 ? min(a.off - d.s_first, GS_SROWS - 1) : GS_SROWS) * OW * 2;
             GsRowC& c = rowC[tid * GS_ROWS + r];
-            c.off = (c.n > 0 ? c.off - d.c_first : 0) * OW;
+            c.off = (c.n > 0 ? c.off - d.c_first : 0) * OW * 2;
         }
     }
     if (__syncthreads_or(too_many)) chip_cold = true;
@@ -167,29 +274,25 @@ image_grad_staged_kernel(const BwdParams p) {
             mbar_arrive_expect_tx(bar, C * bytes);
 #pragma unroll
             for (int c = 0; c < C; c++)
-                bulk_g2s(bufS + ((sub & 1) * C + c) * S_CH, gs_img + c * OH * OW + d.s_first * OW, bytes, bar);
+                bulk_g2s(reinterpret_cast<char*>(bufS) + ((sub & 1) * C + c) * GS_S_CH, gs_img + c * OH * OW + d.s_first * OW, bytes, bar);
         }
         if (chip_fast && d.c_count > 0) {
             const uint32_t bytes = (uint32_t)d.c_count * OW * (uint32_t)sizeof(T);
             mbar_arrive_expect_tx(&bars[2], C * bytes);
 #pragma unroll
             for (int c = 0; c < C; c++)
-                bulk_g2s(sC + c * C_CH, gc_img + c * OH * OW + d.c_first * OW, bytes, &bars[2]);
+                bulk_g2s(reinterpret_cast<char*>(sC) + c * GS_C_CH, gc_img + c * OH * OW + d.c_first * OW, bytes, &bars[2]);
         }
     };
     if (tid == 0) issue(0);
 
-    const float wxs0 = xs_w[0], wxs1 = xs_w[1];
-    const float wxr0 = in_reg_x[0] ? wxs0 * rs : wxs0, wxr1 = in_reg_x[1] ? wxs1 * rs : wxs1;
-    const bool k0 = xs_k[0], k1 = xs_k[1];
-    const bool c_wide = __syncthreads_or((xc[0].n > 2) | (xc[1].n > 2)) != 0;
-    const bool warp_has_chip = __any_sync(0xffffffffu, (xc[0].n | xc[1].n) != 0);
-    const float* tc0 = tb + xc[0].lo;
-    const float* tc1 = tb + xc[1].lo;
+    const bool c_wide = __syncthreads_or((xc_n[0] > 2) | (xc_n[1] > 2)) != 0;
+    const bool warp_has_chip = __any_sync(0xffffffffu, (xc_n[0] | xc_n[1]) != 0);
     char* go_img = reinterpret_cast<char*>(p.g_images) + (size_t)img * C * H * W * sizeof(T) + (size_t)x_a * sizeof(T);
-    constexpr unsigned oplb = (unsigned)(H * W * sizeof(T)), orowb = (unsigned)(W * sizeof(T));
+    constexpr unsigned orowb = (unsigned)(W * sizeof(T));
     uint32_t phS = 0u, phC = 0u;          // mbarrier phase parities (bit k of phS: bufS[k])
 
+#pragma unroll 1
     for (int sub = 0; sub < NSUB; sub++) {
         const int y0 = ybase + sub * GS_ROWS;
         const GsSub d = subs[sub];
@@ -197,25 +300,8 @@ image_grad_staged_kernel(const BwdParams p) {
         // ---- stage 1: vertical pass over the staged chip rows; a thread owns one chip column
         if (chip_rows) {
             mbar_wait(&bars[2], phC); phC ^= 1u;
-            if (tid < OW) {
-                const T* col = sC + tid;
-                float* tcol = tb + tid;
-#pragma unroll 4
-                for (int r = 0; r < GS_ROWS; r++) {
-                    const GsRowC rc = rowC[sub * GS_ROWS + r];               // warp-uniform
-                    float acc[C] = {0.f, 0.f, 0.f};
-                    const T* base = col + rc.off;
-#pragma unroll
-                    for (int q = 0; q < TABW; q++) {
-                        if (q < rc.n) {
-#pragma unroll
-                            for (int c = 0; c < C; c++) acc[c] += rc.w[q] * to_f32(base[c * C_CH + q * OW]);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < C; c++) tcol[c * T_CH + r * GS_TBW] = acc[c];
-                }
-            }
+            if (tid < OW)
+                gs_stage1<T>(smem_a + (uint32_t)L::rowC + sub * GS_ROWS * 32, smem_a + (uint32_t)L::sC + tid * 2, smem_a + (uint32_t)L::tb + tid * 4);
             __syncthreads();
         }
         if (tid == 0 && sub + 1 < NSUB) issue(sub + 1);
@@ -223,61 +309,50 @@ image_grad_staged_kernel(const BwdParams p) {
         // ---- stage 2: horizontal pass for this thread's two columns
         const bool wait_s = has_s && d.s_count > 0;
         if (wait_s) { mbar_wait(&bars[sub & 1], (phS >> (sub & 1)) & 1u); phS ^= 1u << (sub & 1); }
-        const bool do_chip = chip_rows && warp_has_chip;
-        const T* sbuf = bufS + (sub & 1) * C * S_CH;
-        const T* s0 = sbuf + xs_lo[0];
-        const T* s1 = sbuf + xs_lo[1];
-FG_UNROLL(BWD_UNROLL)
-        for (int r = 0; r < GS_ROWS; r++) {
-            const int y = y0 + r;
-            float o0[C], o1[C];
+        const uint32_t rec = smem_a + (uint32_t)L::rowS + sub * GS_ROWS * 16;
+        const uint32_t sbuf = smem_a + (uint32_t)L::bufS + (sub & 1) * C * GS_S_CH;
+        char* out = go_img + (unsigned)y0 * orowb;
+        if (!chip_cold) {
+            const bool do_chip = chip_rows && warp_has_chip;
             if (wait_s) {
-                const GsRowS rr = rowS[sub * GS_ROWS + r];                   // warp-uniform
-                const bool row_reg = y >= ry0 && y < ry1;
-                const float f0 = rr.wy * (row_reg ? wxr0 : wxs0), f1 = rr.wy * (row_reg ? wxr1 : wxs1);
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    o0[c] = k0 ? f0 * to_f32(s0[rr.off + c * S_CH]) : 0.f;
-                    o1[c] = k1 ? f1 * to_f32(s1[rr.off + c * S_CH]) : 0.f;
-                }
+                if (!do_chip) gs_stage2<T, true, false, false>(k, rec, sbuf, out);
+                else if (!c_wide) gs_stage2<T, true, true, false>(k, rec, sbuf, out);
+                else gs_stage2<T, true, true, true>(k, rec, sbuf, out);
             } else {
-#pragma unroll
-                for (int c = 0; c < C; c++) { o0[c] = 0.f; o1[c] = 0.f; }
+                if (!do_chip) gs_stage2<T, false, false, false>(k, rec, sbuf, out);
+                else if (!c_wide) gs_stage2<T, false, true, false>(k, rec, sbuf, out);
+                else gs_stage2<T, false, true, true>(k, rec, sbuf, out);
             }
-            if (do_chip) {
-                const float* t0 = tc0 + r * GS_TBW;
-                const float* t1 = tc1 + r * GS_TBW;
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    o0[c] += xc[0].w[0] * t0[c * T_CH] + xc[0].w[1] * t0[c * T_CH + 1];
-                    o1[c] += xc[1].w[0] * t1[c * T_CH] + xc[1].w[1] * t1[c * T_CH + 1];
-                }
-                if (c_wide) {
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        o0[c] += xc[0].w[2] * t0[c * T_CH + 2] + xc[0].w[3] * t0[c * T_CH + 3];
-                        o1[c] += xc[1].w[2] * t1[c * T_CH + 2] + xc[1].w[3] * t1[c * T_CH + 3];
-                    }
-                }
-            }
-            if (chip_cold) {
-                // rare: tiny box, direct 2-D gather from global memory (the generic kernel's routine)
+        } else {
+            // rare: a box the staging buffers cannot hold; its pixels take the direct 2-D gather from global memory
+#pragma unroll 1
+            for (int r = 0; r < GS_ROWS; r++) {
+                const int y = y0 + r;
+                float o[2][C];
 #pragma unroll
                 for (int v = 0; v < 2; v++) {
                     const int x = x_a + v;
+#pragma unroll
+                    for (int c = 0; c < C; c++) o[v][c] = 0.f;
+                    if (wait_s) {
+                        const uint4 h = lds_v4(rec + r * 16);
+                        const float f = fmaf(__uint_as_float(h.z), v ? k.wd1 : k.wd0, __uint_as_float(h.y) * (v ? k.ws1 : k.ws0));
+                        const uint32_t a = sbuf + (v ? k.s1 : k.s0) + h.x * (v ? k.m1 : k.m0);
+#pragma unroll
+                        for (int c = 0; c < C; c++) o[v][c] = f * bits16_to_f32<T>(lds_u16(a + c * GS_S_CH));
+                    }
                     if (x >= b.x0 && x < b.x1 && y >= b.y0 && y < b.y1) {
                         float acc[FG_MAXC] = {0.f, 0.f, 0.f, 0.f};
                         gather_grid_cold<T>(gc_img, C, OH, OW, x - b.x0, y - b.y0, bw, bh, acc);
 #pragma unroll
-                        for (int c = 0; c < C; c++) { if (v == 0) o0[c] += acc[c]; else o1[c] += acc[c]; }
+                        for (int c = 0; c < C; c++) o[v][c] += acc[c];
                     }
                 }
-            }
-            char* orow = go_img + (unsigned)y * orowb;                       // warp-uniform + lane offset
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                using P2 = Pack2<T>;
-                *reinterpret_cast<typename P2::type*>(orow + c * oplb) = P2::make(o0[c], o1[c]);
+                for (int c = 0; c < C; c++) {
+                    using P2 = Pack2<T>;
+                    *reinterpret_cast<typename P2::type*>(out + r * orowb + (size_t)c * H * W * sizeof(T)) = P2::make(o[0][c], o[1][c]);
+                }
             }
         }
         __syncthreads();

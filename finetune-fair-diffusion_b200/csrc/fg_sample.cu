@@ -325,11 +325,23 @@ static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 gri
         static const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switch for kernel tuning runs
         const bool aligned = ((uintptr_t)p.g_small % 16 == 0) && ((uintptr_t)p.g_chips % 16 == 0);
         if (spec && aligned && !staged_off) {
-            constexpr int NSUB = BSUB;
-            using L = GsLayout<NSUB>;
-            e = cudaFuncSetAttribute(image_grad_staged_kernel<T, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
-            if (e != cudaSuccess) return (int)e;
-            image_grad_staged_kernel<T, NSUB><<<dim3(512 / (NSUB * GS_ROWS), p.n), 256, L::total, st>>>(p);
+            static const int nsub = getenv("FG_BWD_NSUB") ? atoi(getenv("FG_BWD_NSUB")) : 8;                 // tuning runs only
+            if (nsub == 16) {
+                using L = GsLayout<16>;
+                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+                if (e != cudaSuccess) return (int)e;
+                image_grad_staged_kernel<T, 16><<<dim3(512 / (16 * GS_ROWS), p.n), 256, L::total, st>>>(p);
+            } else if (nsub == 8) {
+                using L = GsLayout<8>;
+                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+                if (e != cudaSuccess) return (int)e;
+                image_grad_staged_kernel<T, 8><<<dim3(512 / (8 * GS_ROWS), p.n), 256, L::total, st>>>(p);
+            } else {
+                using L = GsLayout<4>;
+                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
+                if (e != cudaSuccess) return (int)e;
+                image_grad_staged_kernel<T, 4><<<dim3(512 / (4 * GS_ROWS), p.n), 256, L::total, st>>>(p);
+            }
             FG_LAUNCH_CHECK();
             return FG_OK;
         }
