@@ -15,8 +15,9 @@
 //   bufS is double-buffered (stage 2 of sub-tile k reads it while k+1 arrives), sC is single-buffered (free
 //   once stage 1 is done).  The 512 -> 224 resize shrinks by more than 2x, so an image pixel receives at
 //   most ONE resized pixel per axis: the small branch is a scaled gather with no vertical pass.
-//   Rows and columns without a tap read a zero row of the staging buffer: a non-finite gradient never leaks
-//   into pixels it does not touch, and the row loop has no per-lane branch.
+//   Rows and columns without a tap read a zero row of the staging buffer: a non-finite resized-image gradient
+//   never leaks into pixels it does not touch, and the row loop has no per-lane branch.  (Rows are 112 words
+//   apart = 16 banks, so the zero row a tap-less lane reads is picked with the opposite parity of the data row.)
 //   With the latency gone the kernel is bound by instruction issue, so the two row loops are written against
 //   32-bit shared-memory addresses (every offset an immediate once the 8 rows are unrolled) and specialised at
 //   compile time on "has a resized-image gradient / this warp overlaps the box / the box is upscaled".
@@ -25,15 +26,18 @@
 #pragma once
 
 constexpr int GS_ROWS = 8;        // image rows per sub-tile
-constexpr int GS_SROWS = 6;       // resized rows a sub-tile can touch (<= 5 at 512 -> 224) ; row GS_SROWS is the zero row
+constexpr int GS_SROWS = 6;       // resized rows a sub-tile can touch (<= 5 at 512 -> 224)
+constexpr int GS_SZERO = 3;       // zero rows after them (rows 6, 7, 8 of every bufS channel)
 constexpr int GS_CROWS = 16;      // chip rows staged per sub-tile
 constexpr int GS_OW = 224;        // width (and height) of both gradient grids
 constexpr int GS_TBW = GS_OW + TPAD;
-constexpr int GS_S_CH = (GS_SROWS + 1) * GS_OW * 2;     // bufS channel stride, bytes
+constexpr int GS_S_CH = (GS_SROWS + GS_SZERO) * GS_OW * 2;   // bufS channel stride, bytes
 constexpr int GS_C_CH = GS_CROWS * GS_OW * 2;           // sC channel stride, bytes
 constexpr int GS_T_CH = GS_ROWS * GS_TBW * 4;           // tb channel stride, bytes
 
-struct __align__(16) GsRowS { int off; float wy; float wr; int pad; };   // byte offset of the resized row in a bufS channel; y weight; y weight if the row is in the scaled region else 0
+// byte offset of the resized row in a bufS channel; y weight; y weight if the row is in the scaled region else 0;
+// byte offset of the zero row that lanes without a tap read on this row (16 banks away from `off`: no conflict)
+struct __align__(16) GsRowS { int off; float wy; float wr; int offz; };
 struct __align__(16) GsRowC { int off; int n; float w[TABW]; int pad[2]; };   // byte offset of the first chip row in an sC channel, taps
 struct GsSub { int s_first, s_count, c_first, c_count; };
 
@@ -103,15 +107,17 @@ __device__ __forceinline__ void gs_stage1(uint32_t rec, uint32_t col, uint32_t t
 }
 
 struct GsCols {             // per-thread constants of its two image columns
-    uint32_t s0, s1;        // byte offset of the resized-gradient column inside a bufS buffer (the zero row when no tap)
-    uint32_t m0, m1;        // 1: add the row offset (column has a tap), 0: stay on the zero row
+    uint32_t s0, s1;        // byte offset of the resized-gradient column inside a bufS row
+    uint32_t m0, m1;        // 1: the column has a tap (read the data row), 0: read the row's zero row
     float ws0, wd0, ws1, wd1;   // x weight outside the scaled region; (x weight inside) - (x weight outside)
     uint32_t t0, t1;        // shared address of tb[0][0][lo] for the chip taps
+    uint32_t d1;            // (lo of column 1) - (lo of column 0) when that is 0 or 1 (CHIP = 1 reads three shared words)
     float w0[TABW], w1[TABW];
 };
 
 // stage 2 for one sub-tile: 8 image rows x this thread's two columns x 3 channels
-template <typename T, bool DO_S, bool DO_CHIP, bool C_WIDE>
+// CHIP: 0 = this warp's columns miss the box, 1 = three-word fast path, 2 = up to 4 taps per column
+template <typename T, bool DO_S, int CHIP>
 __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_t sbuf, char* out) {
     constexpr unsigned oplb = 512u * 512u * 2u, orowb = 512u * 2u;
 #pragma unroll
@@ -121,23 +127,31 @@ __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_
             const uint4 h = lds_v4(rec + r * 16);             // off, wy, wr      (warp-uniform)
             const float wy = __uint_as_float(h.y), wr = __uint_as_float(h.z);
             const float f0 = fmaf(wr, k.wd0, wy * k.ws0), f1 = fmaf(wr, k.wd1, wy * k.ws1);
-            const uint32_t a0 = sbuf + k.s0 + h.x * k.m0, a1 = sbuf + k.s1 + h.x * k.m1;
+            const uint32_t a0 = sbuf + k.s0 + (k.m0 ? h.x : h.w), a1 = sbuf + k.s1 + (k.m1 ? h.x : h.w);
             uint32_t v0[3], v1[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) { v0[c] = lds_u16(a0 + c * GS_S_CH); v1[c] = lds_u16(a1 + c * GS_S_CH); }
 #pragma unroll
             for (int c = 0; c < 3; c++) { o0[c] = f0 * bits16_to_f32<T>(v0[c]); o1[c] = f1 * bits16_to_f32<T>(v1[c]); }
         }
-        if (DO_CHIP) {
+        if (CHIP == 1) {
+            // downscaled box: <= 2 taps per column and the two columns' taps start 0 or 1 apart -> 3 words cover both
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint32_t a0 = k.t0 + c * GS_T_CH + r * GS_TBW * 4;
+                const float ta = lds_f32(a0), tb_ = lds_f32(a0 + 4), tc = lds_f32(a0 + 8);
+                o0[c] = fmaf(k.w0[0], ta, o0[c]); o0[c] = fmaf(k.w0[1], tb_, o0[c]);
+                o1[c] = fmaf(k.w1[0], k.d1 ? tb_ : ta, o1[c]); o1[c] = fmaf(k.w1[1], k.d1 ? tc : tb_, o1[c]);
+            }
+        }
+        if (CHIP == 2) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const uint32_t a0 = k.t0 + c * GS_T_CH + r * GS_TBW * 4, a1 = k.t1 + c * GS_T_CH + r * GS_TBW * 4;
                 o0[c] = fmaf(k.w0[0], lds_f32(a0), o0[c]); o0[c] = fmaf(k.w0[1], lds_f32(a0 + 4), o0[c]);
                 o1[c] = fmaf(k.w1[0], lds_f32(a1), o1[c]); o1[c] = fmaf(k.w1[1], lds_f32(a1 + 4), o1[c]);
-                if (C_WIDE) {
-                    o0[c] = fmaf(k.w0[2], lds_f32(a0 + 8), o0[c]); o0[c] = fmaf(k.w0[3], lds_f32(a0 + 12), o0[c]);
-                    o1[c] = fmaf(k.w1[2], lds_f32(a1 + 8), o1[c]); o1[c] = fmaf(k.w1[3], lds_f32(a1 + 12), o1[c]);
-                }
+                o0[c] = fmaf(k.w0[2], lds_f32(a0 + 8), o0[c]); o0[c] = fmaf(k.w0[3], lds_f32(a0 + 12), o0[c]);
+                o1[c] = fmaf(k.w1[2], lds_f32(a1 + 8), o1[c]); o1[c] = fmaf(k.w1[3], lds_f32(a1 + 12), o1[c]);
             }
         }
 #pragma unroll
@@ -184,8 +198,8 @@ image_grad_staged_kernel(const BwdParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // zero rows of bufS and the pad columns of tb (read with zero weights, so they must stay finite)
-    for (int e = tid; e < 2 * C * OW; e += 256) {
-        const int bc = e / OW, x = e - bc * OW;
+    for (int e = tid; e < 2 * C * GS_SZERO * OW; e += 256) {
+        const int bc = e / (GS_SZERO * OW), x = e - bc * (GS_SZERO * OW);
         bufS[bc * (GS_S_CH / 2) + GS_SROWS * OW + x] = from_f32<T>(0.f);
     }
     for (int e = tid; e < C * GS_ROWS * TPAD; e += 256) {
@@ -200,7 +214,7 @@ image_grad_staged_kernel(const BwdParams p) {
             Tab t; t.lo = 0; t.n = 0; t.w[0] = 0.f;
             if (has_s) t = make_tab(y, ss, H, OH);
             GsRowS a; a.off = t.n ? t.lo : -1;                // absolute row for now
-            a.wy = t.n ? t.w[0] : 0.f; a.wr = (y >= ry0 && y < ry1) ? a.wy : 0.f; a.pad = 0;
+            a.wy = t.n ? t.w[0] : 0.f; a.wr = (y >= ry0 && y < ry1) ? a.wy : 0.f; a.offz = 0;
             rowS[r] = a;
         } else {
             Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
@@ -215,7 +229,7 @@ image_grad_staged_kernel(const BwdParams p) {
     // this thread's two image columns
     const int x_a = 2 * tid;
     GsCols k;
-    int xc_n[2];
+    int xc_n[2], xc_lo[2];
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const int x = x_a + v;
@@ -224,14 +238,14 @@ image_grad_staged_kernel(const BwdParams p) {
         const bool keep = t.n != 0;
         const float ws = keep ? t.w[0] : 0.f;
         const float wd = (x >= rx0 && x < rx1) ? ws * rs - ws : 0.f;
-        const uint32_t so = keep ? (uint32_t)t.lo * 2u : (uint32_t)(GS_SROWS * OW * 2);
+        const uint32_t so = (uint32_t)(keep ? t.lo : min((int)((float)x / ss), OW - 1)) * 2u;   // tap-less: a column between its neighbours'
         Tab u; u.lo = 0; u.n = 0;
 #pragma unroll
         for (int q = 0; q < TABW; q++) u.w[q] = 0.f;
         if (chip_tab) u = make_tab(x - b.x0, csx, bw, OW);
         if (u.n > TABW) too_many = 1;
         if (u.n == 0) u.lo = 0;
-        xc_n[v] = u.n;
+        xc_n[v] = u.n; xc_lo[v] = u.lo;
         const uint32_t ta = smem_a + (uint32_t)L::tb + (uint32_t)u.lo * 4u;
         if (v == 0) { k.s0 = so; k.m0 = keep; k.ws0 = ws; k.wd0 = wd; k.t0 = ta; }
         else        { k.s1 = so; k.m1 = keep; k.ws1 = ws; k.wd1 = wd; k.t1 = ta; }
@@ -256,7 +270,9 @@ image_grad_staged_kernel(const BwdParams p) {
         subs[tid] = d;
         for (int r = 0; r < GS_ROWS; r++) {
             GsRowS& a = rowS[tid * GS_ROWS + r];
-            a.off = (a.off >= 0 ? min(a.off - d.s_first, GS_SROWS - 1) : GS_SROWS) * OW * 2;
+            const int row = a.off >= 0 ? min(a.off - d.s_first, GS_SROWS - 1) : GS_SROWS;
+            a.off = row * OW * 2;
+            a.offz = (GS_SROWS + 1 + (row & 1)) * OW * 2;
             GsRowC& c = rowC[tid * GS_ROWS + r];
             c.off = (c.n > 0 ? c.off - d.c_first : 0) * OW * 2;
         }
@@ -286,8 +302,13 @@ image_grad_staged_kernel(const BwdParams p) {
     };
     if (tid == 0) issue(0);
 
-    const bool c_wide = __syncthreads_or((xc_n[0] > 2) | (xc_n[1] > 2)) != 0;
+    // column 0 without a tap borrows column 1's start (its weights are zero); the three-word path needs <= 2 taps
+    // per column starting 0 or 1 apart in every lane of the warp
+    if (xc_n[0] == 0) { xc_lo[0] = xc_lo[1]; k.t0 = k.t1; }
+    if (xc_n[1] == 0) xc_lo[1] = xc_lo[0];
+    k.d1 = (uint32_t)(xc_lo[1] - xc_lo[0]);
     const bool warp_has_chip = __any_sync(0xffffffffu, (xc_n[0] | xc_n[1]) != 0);
+    const bool warp_narrow = __all_sync(0xffffffffu, xc_n[0] <= 2 && xc_n[1] <= 2 && k.d1 <= 1u);
     char* go_img = reinterpret_cast<char*>(p.g_images) + (size_t)img * C * H * W * sizeof(T) + (size_t)x_a * sizeof(T);
     constexpr unsigned orowb = (unsigned)(W * sizeof(T));
     uint32_t phS = 0u, phC = 0u;          // mbarrier phase parities (bit k of phS: bufS[k])
@@ -315,13 +336,13 @@ image_grad_staged_kernel(const BwdParams p) {
         if (!chip_cold) {
             const bool do_chip = chip_rows && warp_has_chip;
             if (wait_s) {
-                if (!do_chip) gs_stage2<T, true, false, false>(k, rec, sbuf, out);
-                else if (!c_wide) gs_stage2<T, true, true, false>(k, rec, sbuf, out);
-                else gs_stage2<T, true, true, true>(k, rec, sbuf, out);
+                if (!do_chip) gs_stage2<T, true, 0>(k, rec, sbuf, out);
+                else if (warp_narrow) gs_stage2<T, true, 1>(k, rec, sbuf, out);
+                else gs_stage2<T, true, 2>(k, rec, sbuf, out);
             } else {
-                if (!do_chip) gs_stage2<T, false, false, false>(k, rec, sbuf, out);
-                else if (!c_wide) gs_stage2<T, false, true, false>(k, rec, sbuf, out);
-                else gs_stage2<T, false, true, true>(k, rec, sbuf, out);
+                if (!do_chip) gs_stage2<T, false, 0>(k, rec, sbuf, out);
+                else if (warp_narrow) gs_stage2<T, false, 1>(k, rec, sbuf, out);
+                else gs_stage2<T, false, 2>(k, rec, sbuf, out);
             }
         } else {
             // rare: a box the staging buffers cannot hold; its pixels take the direct 2-D gather from global memory
@@ -337,7 +358,7 @@ image_grad_staged_kernel(const BwdParams p) {
                     if (wait_s) {
                         const uint4 h = lds_v4(rec + r * 16);
                         const float f = fmaf(__uint_as_float(h.z), v ? k.wd1 : k.wd0, __uint_as_float(h.y) * (v ? k.ws1 : k.ws0));
-                        const uint32_t a = sbuf + (v ? k.s1 : k.s0) + h.x * (v ? k.m1 : k.m0);
+                        const uint32_t a = sbuf + (v ? k.s1 : k.s0) + ((v ? k.m1 : k.m0) ? h.x : h.w);
 #pragma unroll
                         for (int c = 0; c < C; c++) o[v][c] = f * bits16_to_f32<T>(lds_u16(a + c * GS_S_CH));
                     }
