@@ -36,6 +36,7 @@ SIGNATURES = {
     "fg_head_attributes": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p]),
     "fg_fair_ce_fwd": (_i, [_p, _p, _p, _i, _i, _f, _p, _i, _p]),
     "fg_fair_ce_bwd": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p]),
+    "fg_fair_loss_fused": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _f, _f, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _p]),
     "fg_rank_binom_workspace_bytes": (_z, [_i]),
     "fg_assign_rank_binom": (_i, [_p, _i, _d, _f, _p, _p, _p, _z, _i, _p]),
     "fg_ot_workspace_bytes": (_z, [_i, _i, _i]),
@@ -82,7 +83,7 @@ CALLS = collections.Counter()      # C-ABI calls made so far, by entry point (be
 KERNELS_PER_CALL = {
     "fg_select_expand_boxes": 1, "fg_crop_resize_fwd": 1, "fg_guidance_factors": 1, "fg_image_grad": 1,
     "fg_region_scale": 1, "fg_head_fwd": 2, "fg_head_bwd": 2, "fg_head_attributes": 1, "fg_fair_ce_fwd": 1,
-    "fg_fair_ce_bwd": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
+    "fg_fair_ce_bwd": 1, "fg_fair_loss_fused": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
     "fg_ot_solve_single": 1, "fg_ot_cost_matrix": 2,
 }
 

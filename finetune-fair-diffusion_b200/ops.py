@@ -215,6 +215,30 @@ def fair_ce_bwd(logits, targets, face, g_loss):
     return g
 
 
+def fair_loss_fused(logits_attr, targets, col_start, k_head, face, g_coef, dyn_w=None, loss_clip=None, loss_dino=None,
+                    loss_face=None, weight_img=0.0, weight_face=0.0, fill=-1.0, want_grad=True):
+    """CE of every attribute + loss assembly + gradient wrt the head logits in one launch (E3:2114-2147).
+    logits_attr / targets: lists of [n,w_a] (dtype) and [n] int64.  Returns (loss_fair list, loss f32 [n], g_logits f32)."""
+    import ctypes
+    A = len(logits_attr)
+    lg = [t.contiguous() for t in logits_attr]
+    tg = [t.to(torch.int64).contiguous() for t in targets]
+    _cuda(*lg, *tg, face)
+    n, dt, dev = lg[0].shape[0], lg[0].dtype, lg[0].device
+    cast = lambda t: None if t is None else t.to(dt).contiguous()
+    lc, ld, lf = cast(loss_clip), cast(loss_dino), cast(loss_face)
+    loss_fair = torch.empty((A, n), dtype=dt, device=dev)
+    loss = torch.empty((n,), dtype=torch.float32, device=dev)
+    g = torch.empty((n, k_head), dtype=torch.float32, device=dev) if want_grad else None
+    ptrs = lambda ts: (ctypes.c_void_p * A)(*[t.data_ptr() for t in ts])
+    ints = lambda xs: (ctypes.c_int32 * A)(*[int(x) for x in xs])
+    check(_lib.lib().fg_fair_loss_fused(ptrs(lg), ptrs(tg), ints([t.shape[1] for t in lg]), ints(col_start), A, _p(_u8(face)), n, int(k_head),
+                                        float(fill), float(g_coef), _p(None if dyn_w is None else dyn_w.float().contiguous()),
+                                        _p(lc), _p(ld), _p(lf), float(weight_img), float(weight_face),
+                                        _p(loss_fair), _p(loss), _p(g), _dt(lg[0]), _stream()), "fg_fair_loss_fused")
+    return list(loss_fair.unbind(0)), loss, g
+
+
 # ------------------------------------------------------------------ assignment
 def assign_rank_binom(probs, target_ratio=0.5, threshold=-1.0, w_uncertainty=True):
     _cuda(probs)

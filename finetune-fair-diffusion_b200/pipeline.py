@@ -128,9 +128,13 @@ def synth_batch_device(n, cfg: GuidanceConfig, dtype, device, seed=5991, H=512, 
         counts = torch.ones(n, dtype=torch.int32, device=device)
     counts = torch.where(r(n) < no_face_frac, torch.zeros_like(counts), counts)
     rn = lambda *shape: torch.randn(*shape, generator=g, device=device)
+    jitter = torch.randint(-12, 13, (n, 4), generator=g, device=device)
+    # face_bboxs_ori (E3:1751): the expanded box found on the ORIGINAL model's image, an input of the path;
+    # here the new box plus a few pixels of jitter
+    ind0, boxes0 = ops.select_expand_boxes(cand, counts, images.shape[-2], cfg.expand_coef, 1.0, -1)
+    bbox_ori = torch.where(ind0.unsqueeze(1), boxes0 + jitter, boxes0)
     return dict(
-        images=images, cand_boxes=cand, counts=counts,
-        bbox_jitter=torch.randint(-12, 13, (n, 4), generator=g, device=device),
+        images=images, cand_boxes=cand, counts=counts, bbox_jitter=jitter, bbox_ori=bbox_ori,
         pooled=rn(n, cfg.d_in).to(dtype),
         g_chips=(rn(n, 3, cfg.size_face, cfg.size_face) * 1e-3).to(dtype),
         g_small=(rn(n, 3, cfg.img_size_small, cfg.img_size_small) * 1e-3).to(dtype),
@@ -206,24 +210,14 @@ class GuidancePath:
             targets_all, _ = ops.ot_targets(counts, probs_all[0], probs_all[1], nv, ws, cfg.uncertainty_threshold, True)
         targets = [t[n * rank:n * (rank + 1)] for t in targets_all]
         P.end("assign")
-        # 7
-        g_logits = torch.zeros((n, k_head), dtype=torch.float32, device=images.device)
-        inv_n = torch.full((n,), 1.0 / n, dtype=images.dtype, device=images.device)
-        loss_fair = []
-        for a, (c, w) in enumerate(zip(col_start, widths)):
-            loss_fair.append(ops.fair_ce_fwd(logits_attr[a], targets[a], ind, -1.0))
-            g_logits[:, c:c + w] = ops.fair_ce_bwd(logits_attr[a], targets[a], ind, inv_n)
-        g_pooled = ops.head_bwd(g_logits, hidden, self.head[0], self.head[2])
-        # 8
-        bbox_ori = torch.where(ind.unsqueeze(1), boxes + batch["bbox_jitter"], boxes)
+        # 7-9: hook factors, then CE of every attribute + loss assembly + gradient wrt the head logits in one launch
+        bbox_ori = batch["bbox_ori"] if "bbox_ori" in batch else torch.where(ind.unsqueeze(1), boxes + batch["bbox_jitter"], boxes)
         region, scale, dyn_w = ops.guidance_factors(ind, boxes, bbox_ori, targets, batch["preds_ori"],
                                                     cfg.factors2[:len(widths)], cfg.factors1[:len(widths)], e1_rule, H, W)
-        # 9
-        loss = loss_fair[0].float()
-        for t in loss_fair[1:]:
-            loss = loss + t.float()
-        loss = loss + cfg.weight_loss_img * dyn_w * (batch["loss_clip"].float() + batch["loss_dino"].float()) \
-            + cfg.weight_loss_face * batch["loss_face"].float()
+        loss_fair, loss, g_logits = ops.fair_loss_fused(
+            logits_attr, targets, col_start, k_head, ind, 1.0 / n, dyn_w, batch["loss_clip"], batch["loss_dino"],
+            batch["loss_face"], cfg.weight_loss_img, cfg.weight_loss_face, -1.0)
+        g_pooled = ops.head_bwd(g_logits, hidden, self.head[0], self.head[2])
         # 10
         P.begin("image_grad")
         g_images = ops.image_grad(batch["g_chips"], batch["g_small"], boxes, ind, region, scale, tuple(images.shape),

@@ -132,6 +132,20 @@ int fg_fair_ce_fwd(const void* logits, const int64_t* targets, const uint8_t* fa
 int fg_fair_ce_bwd(const void* logits, const int64_t* targets, const uint8_t* face_indicators,
                    const void* g_loss, int n, int k, void* g_logits, int dtype, void* stream);
 
+/* The three calls above for every attribute of a head, the per-image loss assembly and d(mean loss)/d(head logits)
+ * in ONE launch (E3:2114-2147, E4:2238-2283):
+ *   loss_fair[a][i] = CE_a or `fill`;   loss[i] = sum_a loss_fair[a][i] + weight_img * dyn_weights[i] *
+ *   (loss_clip[i] + loss_dino[i]) + weight_face * loss_face[i]   (fp32, left to right; the semantic / face terms
+ *   are skipped when their pointers are NULL);   g_logits [n,k_head] f32 = g_coef * (softmax - onehot) in the
+ *   columns [col_start[a], col_start[a]+width[a]) of active rows, 0 elsewhere (rounded through `dtype` like
+ *   fg_fair_ce_bwd).  logits_attr / targets: HOST arrays of n_attr DEVICE pointers ([n,width[a]] dtype and [n]
+ *   int64); width / col_start: HOST arrays; loss_fair [n_attr][n] dtype; loss [n] f32 or NULL; g_logits or NULL. */
+int fg_fair_loss_fused(const void* const* logits_attr, const int64_t* const* targets, const int32_t* width,
+                       const int32_t* col_start, int n_attr, const uint8_t* face_indicators, int n, int k_head,
+                       float fill, float g_coef, const float* dyn_weights, const void* loss_clip,
+                       const void* loss_dino, const void* loss_face, float weight_img, float weight_face,
+                       void* loss_fair, float* loss, float* g_logits, int dtype, void* stream);
+
 /* ------------------------------------------------------------------ assignment ------------
  * generate_dynamic_targets (E1:1403-1447): rank split at N*target_ratio and binomial-CDF
  * uncertainty, N = rows of probs [n_all,2] without a -1.  Ties in probs[:,1] resolve by row index.

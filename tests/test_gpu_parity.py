@@ -273,6 +273,32 @@ def test_fair_ce_vs_oracle(fg, dtype, rtol):
 
 
 # ----------------------------------------------------------------------------- hooks / weights
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("widths,col_start,k_head", [((2,), (40,), 80), ((2, 4), (0, 2), 6), ((2, 4, 2), (0, 2, 6), 8)])
+def test_fused_fair_loss_equals_separate_calls(fg, dtype, widths, col_start, k_head):
+    """fg_fair_loss_fused = fg_fair_ce_fwd + fg_fair_ce_bwd per attribute + the loss expression of E3:2119-2147,
+    bit for bit."""
+    g = torch.Generator().manual_seed(11)
+    n = 333
+    logits = [(torch.randn(n, w, generator=g) * 3).to(dtype).to(DEV) for w in widths]
+    targets = [torch.randint(-1, w, (n,), generator=g).to(DEV) for w in widths]
+    face = (torch.rand(n, generator=g) > 0.1).to(DEV)
+    dyn_w = torch.rand(n, generator=g).to(DEV)
+    lc, ld, lf = [torch.rand(n, generator=g).to(dtype).to(DEV) for _ in range(3)]
+    loss_fair, loss, g_logits = fg.ops.fair_loss_fused(logits, targets, col_start, k_head, face, 1.0 / n, dyn_w, lc, ld, lf, 8.0, 1.0)
+    inv_n = torch.full((n,), 1.0 / n, dtype=dtype, device=DEV)
+    ref_g = torch.zeros(n, k_head, device=DEV)
+    ref_loss = None
+    for a, (c, w) in enumerate(zip(col_start, widths)):
+        l = fg.ops.fair_ce_fwd(logits[a], targets[a], face, -1.0)
+        assert torch.equal(l, loss_fair[a])
+        ref_g[:, c:c + w] = fg.ops.fair_ce_bwd(logits[a], targets[a], face, inv_n)
+        ref_loss = l.float() if ref_loss is None else ref_loss + l.float()
+    ref_loss = ref_loss + 8.0 * dyn_w * (lc.float() + ld.float()) + 1.0 * lf.float()
+    assert torch.equal(g_logits, ref_g)
+    assert torch.equal(loss, ref_loss)
+
+
 @pytest.mark.parametrize("tag", ["e1", "e3", "e4"])
 def test_hooks_and_weights_golden(fg, tag):
     g = load("hooks")
