@@ -89,8 +89,9 @@ KERNELS_PER_CALL = {
 
 
 def ot_levels(n_valid):
-    """Number of base-solve launches fg_ot_plan_counts makes (csrc/fg_assign.cu launch_base)."""
-    return 1 if n_valid > 0 else 0
+    """Extra solver launches of fg_ot_plan_counts besides compact / cost+hist / draws (none: every draw searches
+    from zero prices in its own CTA)."""
+    return 0
 
 
 def check(rc, what):

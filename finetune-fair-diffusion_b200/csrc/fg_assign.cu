@@ -26,11 +26,12 @@
 #include "fg_common.cuh"
 #include <math.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace {
 
 constexpr int KP = 16;                 // classes padded to 16
-constexpr int SOLVER_THREADS = 256;
+constexpr int SOLVER_THREADS = 512;
 constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
 constexpr unsigned long long KEY_INF = 0xFFFFFFFFFFFFFFFFull;
 
@@ -52,6 +53,7 @@ struct OtWs {
     int* idx;           // [n_all] compacted row -> original row
     int* pos;           // [n_all] original row -> compacted row or -1
     double* M;          // [n_valid, K]
+    float* Mf;          // [K, n_valid]  fp32, class-major (the solver's search / screening copy)
     int* hist;          // [S, KP]
     double* prices;     // [KP]
     uint8_t* sigma0;    // [n_valid]
@@ -66,6 +68,7 @@ static OtWs ot_carve(void* base, int n_all, int K, int S) {
     w.idx = (int*)take((size_t)n_all * sizeof(int));
     w.pos = (int*)take((size_t)n_all * sizeof(int));
     w.M = (double*)take((size_t)n_all * K * sizeof(double));
+    w.Mf = (float*)take((size_t)n_all * K * sizeof(float));
     w.hist = (int*)take((size_t)(S > 0 ? S : 1) * KP * sizeof(int));
     w.prices = (double*)take(KP * sizeof(double));
     w.sigma0 = (uint8_t*)take((size_t)n_all);
@@ -148,12 +151,15 @@ __device__ __forceinline__ void cost_row(const T* __restrict__ pg, const T* __re
 template <typename T>
 __global__ void __launch_bounds__(256)
 cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
-                 const int* __restrict__ idx, int N, int K, double* __restrict__ M, int cost_blocks,
+                 const int* __restrict__ idx, int N, int K, double* __restrict__ M, float* __restrict__ Mf, int cost_blocks,
                  const T* __restrict__ rg, const T* __restrict__ rr, const T* __restrict__ ra, int S,
                  int* __restrict__ hist) {
     if ((int)blockIdx.x < cost_blocks) {
         int r = blockIdx.x * 256 + threadIdx.x;
-        if (r < N) cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
+        if (r < N) {
+            cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
+            if (Mf) for (int j = 0; j < K; j++) Mf[(size_t)j * N + r] = (float)M[(size_t)r * K + j];
+        }
         return;
     }
     int s = blockIdx.x - cost_blocks;
@@ -201,6 +207,7 @@ struct SolverSmem {
     unsigned need[KP + 1];
     int path_len;
     int cont[2];               // loop-continue flag, double buffered by iteration parity
+    unsigned whist[2][SOLVER_WARPS][KP / 2];   // price search: per-warp class counts (two 16-bit counts per word), by iteration parity
     int status;
 };
 
@@ -212,23 +219,84 @@ struct SolverViews {
     float* Mf;                 // [K][N]   fp32 copy of the cost matrix for the price search (when it fits)
 };
 
-__host__ __device__ inline size_t solver_off_pos(int N) { return sizeof(SolverSmem) + (((size_t)N + 15) / 16) * 16; }
+constexpr size_t SOLVER_CTRL = (sizeof(SolverSmem) + 15) / 16 * 16;      // control block, padded so that every view is 16-byte aligned
+__host__ __device__ inline size_t solver_off_pos(int N) { return SOLVER_CTRL + (((size_t)N + 15) / 16) * 16; }
 __host__ __device__ inline size_t solver_off_members(int N) { return solver_off_pos(N) + (((size_t)N * 2 + 15) / 16) * 16; }
 __host__ __device__ inline size_t solver_off_M(int N, int K) { return solver_off_members(N) + (((size_t)N * K * 2 + 15) / 16) * 16; }
 
+// order-preserving 32-bit key of a float (for REDUX min)
+__device__ __forceinline__ unsigned fkey(float f) { const unsigned b = __float_as_uint(f); return (b >> 31) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float funkey(unsigned k) { return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k); }
+// |fp32 difference of the fp32 copies - fp64 difference| <= 3 half-ulps of values below 8 (costs are norms of probability
+// differences): 7.2e-7.  Two candidates further apart than twice that in fp32 are ordered the same way in fp64.
+constexpr float SCREEN_EPS = 4e-6f;
+
 // One warp recomputes w[k][l], wi[k][l] for the classes l in `mask` from the member list of class k.
-__device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* __restrict__ M, int N, int K, int k, unsigned mask) {
+// FP64 issues at a small fraction of the FP32 rate on this part and the fp64 matrix lives in global memory, so with the
+// fp32 copy in shared memory (`screen`) a pass over the members finds the fp32 minimum and runner-up of every target:
+// when the runner-up is more than SCREEN_EPS away the fp32 winner is the fp64 winner, and its exact fp64 difference is
+// computed afterwards by lane l for all targets at once (one round trip to global memory per class).  Only targets
+// with a near-tie take the exact scan over all members.
+__device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* __restrict__ M, int N, int K, int k, unsigned mask,
+                            bool screen) {
     const int lane = threadIdx.x & 31;
     const int cnt = sm.cnt[k];
     const uint16_t* mem = v.members + (size_t)k * N;
+    const float* Mk = v.Mf + (size_t)k * N;
     mask &= ~(1u << k);
+    unsigned exact_mask = screen ? 0u : mask;        // targets that need the exact scan
+    if (screen) {
+        unsigned todo = mask;
+        while (todo) {                               // warp-uniform; 4 target classes per pass over the members
+            int ls[4]; int nl = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (todo) { ls[j] = __ffs(todo) - 1; todo &= todo - 1; nl = j + 1; } else ls[j] = ls[0];
+            }
+            float b1[4], b2[4]; int bi[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { b1[j] = INFINITY; b2[j] = INFINITY; bi[j] = 0x7fffffff; }
+            for (int t = lane; t < cnt; t += 32) {
+                const int i = mem[t];
+                const float mk = Mk[i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float x = v.Mf[(size_t)ls[j] * N + i] - mk;
+                    if (x < b1[j]) { b2[j] = b1[j]; b1[j] = x; bi[j] = i; } else if (x < b2[j]) b2[j] = x;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j >= nl) break;                   // warp-uniform
+                const float m1 = funkey(__reduce_min_sync(0xffffffffu, fkey(b1[j])));
+                const float thr = m1 + SCREEN_EPS;
+                const unsigned cand = __ballot_sync(0xffffffffu, b1[j] <= thr);
+                const unsigned close2 = __ballot_sync(0xffffffffu, b2[j] <= thr);
+                if (cand == 0u) {                     // class k is empty
+                    if (lane == 0) { sm.w[k][ls[j]] = INFINITY; sm.wi[k][ls[j]] = -1; }
+                } else if ((cand & (cand - 1)) == 0u && close2 == 0u) {
+                    const int win = __shfl_sync(0xffffffffu, bi[j], __ffs(cand) - 1);
+                    if (lane == 0) sm.wi[k][ls[j]] = win;          // w[k][l] follows below
+                } else {
+                    exact_mask |= 1u << ls[j];
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned direct = mask & ~exact_mask;
+        if (lane < K && ((direct >> lane) & 1u)) {
+            const int i = sm.wi[k][lane];
+            if (i >= 0) sm.w[k][lane] = __dsub_rn(M[(size_t)i * K + lane], M[(size_t)i * K + k]);
+        }
+    }
+    mask = exact_mask;
     while (mask) {                                   // warp-uniform; up to 4 target classes per pass
         int ls[4]; int nl = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (mask) { ls[j] = __ffs(mask) - 1; mask &= mask - 1; nl = j + 1; } else ls[j] = ls[0];
         }
-        // candidates are compared as order-preserving integer keys: FP64 compares issue slowly on this part
+        // candidates are compared as order-preserving integer keys
         unsigned long long bestk[4]; int besti[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { bestk[j] = KEY_INF; besti[j] = 0x7fffffff; }
@@ -318,6 +386,80 @@ __device__ void find_path(SolverSmem& sm, int K) {
     __syncwarp();
 }
 
+// Price search (step 1 of ot_solve_kernel), KK = number of classes (8 or 16).
+// Lane l (< KK) of EVERY warp keeps class l's price, step, last sign and best price in registers, and all warps make
+// the same update from the same counts, so a round costs one block barrier: a row's cheapest class comes from a
+// compare tree over KK independent loads, rows are counted per thread in a packed 4-bit histogram, summed over the
+// warp with REDUX, published per warp and read back by every warp.
+template <int KK>
+__device__ __forceinline__ void price_search(SolverSmem& sm, const float* __restrict__ Mf, const double* __restrict__ M_global,
+                                             int N, int dual_iters, float step0, bool m_in_smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
+    int my_prev = 0, best_resid = 0x7fffffff;
+    const int my_b = lane < KK ? sm.b[lane] : 0;
+    for (int it = 0; it <= dual_iters; it++) {
+        float pr[KK];
+#pragma unroll
+        for (int l = 0; l < KK; l++) pr[l] = __shfl_sync(0xffffffffu, my_price, l);
+        unsigned acc[KP / 2];
+#pragma unroll
+        for (int w = 0; w < KP / 2; w++) acc[w] = 0u;
+        unsigned long long h = 0ull; int pending = 0;
+#pragma unroll 2
+        for (int i = tid; i < N; i += SOLVER_THREADS) {
+            float x[KK]; int idx[KK];
+            if (m_in_smem) {
+#pragma unroll
+                for (int l = 0; l < KK; l++) x[l] = Mf[l * N + i];
+            } else {
+#pragma unroll
+                for (int l = 0; l < KK; l++) x[l] = (float)M_global[(size_t)i * KK + l];
+            }
+#pragma unroll
+            for (int l = 0; l < KK; l++) { x[l] -= pr[l]; idx[l] = l; }
+#pragma unroll
+            for (int st = 1; st < KK; st *= 2)
+#pragma unroll
+                for (int l = 0; l < KK; l += 2 * st)
+                    if (x[l + st] < x[l]) { x[l] = x[l + st]; idx[l] = idx[l + st]; }      // strict: the lower class wins ties
+            h += 1ull << (4 * idx[0]);
+            if (++pending == 15) {                 // 4-bit fields are full: spill into the 16-bit accumulators
+#pragma unroll
+                for (int w = 0; w < KP / 2; w++) acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+                h = 0ull; pending = 0;
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < KK / 2; w++) {
+            acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+            acc[w] = __reduce_add_sync(0xffffffffu, acc[w]);           // N <= 65535: a 16-bit field cannot overflow
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < KK / 2; w++) sm.whist[it & 1][warp][w] = acc[w];
+        }
+        __syncthreads();
+        int cnt = 0;
+        if (lane < KK) {
+#pragma unroll
+            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu);
+        }
+        const int err = lane < KK ? my_b - cnt : 0;
+        const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
+        if (resid < best_resid) { best_resid = resid; my_best = my_price; }
+        if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
+        if (lane < KK) {
+            const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
+            if (sg * my_prev < 0) my_step *= 0.5f; else if (sg * my_prev > 0) my_step *= 1.2f;
+            my_prev = sg;
+            my_price += my_step * (float)sg;                           // too few rows -> cheaper class
+        }
+    }
+    if (warp == 0 && lane < KP) sm.best_pricef[lane] = my_best;
+    __syncthreads();
+}
+
 // One CTA solves one transport problem exactly.
 //
 //  1. price search (all warps):  `dual_iters` rounds of sign-based dual ascent on the K class prices
@@ -334,7 +476,7 @@ __device__ void find_path(SolverSmem& sm, int K) {
 // demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x].  prices_in == nullptr starts
 // from zero prices (the greedy assignment).  prices_out receives feasible optimal prices of the final state.
 __global__ void __launch_bounds__(SOLVER_THREADS)
-ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
+ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ Mf_global, int N, int K,
                 const double* __restrict__ prices_in, double* __restrict__ prices_out, int dual_iters, double step0,
                 Demand demand_by_value, const int* __restrict__ hist,
                 int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
@@ -342,7 +484,7 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
-    v.sigma = dyn_smem + sizeof(SolverSmem);
+    v.sigma = dyn_smem + SOLVER_CTRL;
     v.pos = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_pos(N));
     v.members = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_members(N));
     v.Mf = reinterpret_cast<float*>(dyn_smem + solver_off_M(N, K));
@@ -352,8 +494,23 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
     // prices are admissible) runs in fp32 on a shared-memory copy of the costs; only the final assignment and
     // the exact repair steps touch the fp64 matrix.
     const double* M = M_global;
+#ifdef FG_OT_PROFILE
+    long long tprof[8]; int nprof = 0;
+#define FG_MARK() do { __syncthreads(); tprof[nprof++] = clock64(); } while (0)
+#else
+#define FG_MARK() do {} while (0)
+#endif
+    FG_MARK();
     // class-major copy: lane i reads Mf[l*N + i], conflict-free (a row-major row per lane is a 16-way conflict)
-    if (m_in_smem) for (int e = tid; e < N * K; e += SOLVER_THREADS) { const int i = e / K, l = e - i * K; v.Mf[l * N + i] = (float)M_global[e]; }
+    if (m_in_smem) {
+        if (Mf_global && (N * K) % 4 == 0) {       // precomputed by the cost kernel: straight 16-byte copies
+            const float4* src = reinterpret_cast<const float4*>(Mf_global);
+            float4* dst = reinterpret_cast<float4*>(v.Mf);
+            for (int e = tid; e < N * K / 4; e += SOLVER_THREADS) dst[e] = __ldg(src + e);
+        } else {
+            for (int e = tid; e < N * K; e += SOLVER_THREADS) { const int i = e / K, l = e - i * K; v.Mf[l * N + i] = (float)M_global[e]; }
+        }
+    }
     if (tid < KP) {
         sm.cnt[tid] = 0;
         sm.b[tid] = hist ? hist[blockIdx.x * KP + tid] : demand_by_value.b[tid];
@@ -372,49 +529,14 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
         for (int k = 0; k < K; k++) { if (sm.b[k] < 0) sm.status |= ST_BAD_DEMAND; tot += sm.b[k]; }
         if (tot != N) sm.status |= ST_BAD_DEMAND;
     }
+    FG_MARK();
 
     // ---- 1. price search (fp32)
-    for (int it = 0; it <= dual_iters; it++) {
-        for (int i = tid; i < N; i += SOLVER_THREADS) {
-            float bv = INFINITY; int s = 0;
-            if (m_in_smem) {
-                for (int l = 0; l < K; l++) { const float x = v.Mf[l * N + i] - sm.pricef[l]; if (x < bv) { bv = x; s = l; } }
-            } else {
-                const double* row = M_global + (size_t)i * K;
-                for (int l = 0; l < K; l++) { const float x = (float)row[l] - sm.pricef[l]; if (x < bv) { bv = x; s = l; } }
-            }
-            atomicAdd(&sm.cnt[s], 1);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const int lane = tid;
-            const int err = lane < K ? sm.b[lane] - sm.cnt[lane] : 0;
-            int resid = err < 0 ? -err : err;
-            for (int o = 16; o > 0; o >>= 1) resid += __shfl_xor_sync(0xffffffffu, resid, o);
-            resid >>= 1;
-            const bool better = resid < sm.best_resid;                 // same value in every lane
-            const bool last = resid == 0 || it == dual_iters;
-            __syncwarp();
-            if (better && lane < KP) sm.best_pricef[lane] = sm.pricef[lane];
-            if (lane == 0) {
-                if (better) sm.best_resid = resid;
-                sm.stop = last ? 1 : 0;
-            }
-            if (lane < K && !last) {
-                const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
-                float st = sm.step[lane];
-                const int ps = sm.prev_sign[lane];
-                if (sg * ps < 0) st *= 0.5f; else if (sg * ps > 0) st *= 1.2f;
-                sm.step[lane] = st; sm.prev_sign[lane] = sg;
-                sm.pricef[lane] += st * (float)sg;                     // too few rows -> cheaper class
-            }
-            if (lane < KP) sm.cnt[lane] = 0;
-        }
-        __syncthreads();
-        if (sm.stop) break;
-    }
+    if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
+    else price_search<8>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
     __syncthreads();
+    FG_MARK();
     // final assignment under the best prices + member lists (list order is arbitrary; no result depends on it)
     for (int i = tid; i < N; i += SOLVER_THREADS) {
         int s = 0;
@@ -440,11 +562,13 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
         v.pos[i] = (uint16_t)slot;
     }
     __syncthreads();
+    FG_MARK();
     const unsigned all_mask = (1u << K) - 1u;
     int iters = 0;
     if (!(sm.status & ST_BAD_DEMAND)) {
-        for (int k = warp; k < K; k += SOLVER_WARPS) warp_rescan(sm, v, M, N, K, k, all_mask);
+        for (int k = warp; k < K; k += SOLVER_WARPS) warp_rescan(sm, v, M, N, K, k, all_mask, m_in_smem != 0);
         __syncthreads();
+        FG_MARK();
         const int max_iters = N + KP;
         for (;; iters++) {
             if (warp == 0) {
@@ -475,7 +599,7 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
                         }
                     }
                     __syncwarp();
-                    for (int e = 0; e + 1 < len; e++) warp_rescan(sm, v, M, N, K, sm.path[e], sm.need[e]);
+                    for (int e = 0; e + 1 < len; e++) warp_rescan(sm, v, M, N, K, sm.path[e], sm.need[e], m_in_smem != 0);
                     // rows that arrived in path[e+1]: fold their outgoing differences into the minima
                     if (lane < K) {
                         const int l = lane;
@@ -498,6 +622,7 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
         if (tid == 0 && status) atomicAdd(&status[status_slot], iters);
     }
     __syncthreads();
+    FG_MARK();
 
     // outputs
     if (assign_out) for (int i = tid; i < N; i += SOLVER_THREADS) assign_out[i] = sigma[i];
@@ -522,6 +647,12 @@ ot_solve_kernel(const double* __restrict__ M_global, int N, int K,
         }
     }
     if (tid == 0 && sm.status && status) atomicOr(&status[0], sm.status);
+#ifdef FG_OT_PROFILE
+    FG_MARK();
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 57))
+        printf("otprof blk %d N %d K %d grid %d: copy %lld search %lld assign %lld rescan %lld ssp(%d) %lld out %lld total %lld cycles\n", blockIdx.x, N, K, gridDim.x,
+               tprof[1] - tprof[0], tprof[2] - tprof[1], tprof[3] - tprof[2], tprof[4] - tprof[3], iters, tprof[5] - tprof[4], tprof[6] - tprof[5], tprof[6] - tprof[0]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -721,23 +852,23 @@ static void expected_demand(int n, int K, Demand* d) {
     }
 }
 
-// base assignment: coarse-to-fine over growing prefixes, each level warm-started by the previous prices
-// price-search schedule: the base starts from zero prices (the greedy assignment), the draws from the
-// base's optimal prices and only have to absorb |b_s - b_base|
+// price-search schedule (rounds, first step) of a solve that starts from zero prices, i.e. from the greedy assignment
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
 // defaults; the FG_OT_* environment variables exist for tuning runs only (results do not depend on them)
 #define BASE_DUAL_ITERS env_int("FG_OT_BASE_ITERS", 40)
 #define BASE_STEP0 env_dbl("FG_OT_BASE_STEP", 0.03)
-#define DRAW_DUAL_ITERS env_int("FG_OT_DRAW_ITERS", 24)
-#define DRAW_STEP0 env_dbl("FG_OT_DRAW_STEP", 0.01)
+#define DRAW_DUAL_ITERS env_int("FG_OT_DRAW_ITERS", 40)
+#define DRAW_STEP0 env_dbl("FG_OT_DRAW_STEP", 0.03)
+#define WARM_DUAL_ITERS 24            // fg_ot_solve_single: second solve warm-started from the first one's prices
+#define WARM_STEP0 0.01
 
 // base problem: the expected demand; leaves its optimal prices in w.prices
-static int launch_base(const double* M, int N, int K, OtWs& w, cudaStream_t st) {
+static int launch_base(const double* M, const float* Mf, int N, int K, OtWs& w, cudaStream_t st) {
     int rc = solver_prepare(N, K);
     if (rc) return rc;
     Demand d; expected_demand(N, K, &d);
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(N, K), st>>>(M, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0,
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(N, K), st>>>(M, Mf, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0,
                                                                         d, nullptr, nullptr, nullptr, w.status, 2,
                                                                         solver_m_fits(N, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
@@ -773,13 +904,16 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int cost_blocks = (n_valid + 255) / 256;
     FG_DISPATCH_DTYPE(dtype, T,
         cost_hist_kernel<T><<<cost_blocks + S, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age,
-            w.idx, n_valid, K, w.M, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist));
+            w.idx, n_valid, K, w.M, w.Mf, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist));
     FG_LAUNCH_CHECK();
     if (S == 0) return FG_OK;
-    int rc = launch_base(w.M, n_valid, K, w, st);
+    // Every draw runs the whole price search from zero prices in its own CTA.  (A serial "base" solve of the expected
+    // demand used to warm-start the draws: it saved them ~40% of their search rounds but cost a single-CTA launch
+    // longer than the draws themselves.)
+    int rc = solver_prepare(n_valid, K);
     if (rc) return rc;
     Demand none = {};
-    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, n_valid, K, w.prices, nullptr, DRAW_DUAL_ITERS,
+    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, w.Mf, n_valid, K, nullptr, nullptr, DRAW_DUAL_ITERS,
                                                                              DRAW_STEP0, none, w.hist, nullptr, counts, w.status, 3,
                                                                              solver_m_fits(n_valid, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
@@ -815,9 +949,9 @@ extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* 
     cudaStream_t st = fg_stream(stream);
     cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    int rc = launch_base(M, n, K, w, st);      // exercises the coarse-to-fine path as well
+    int rc = launch_base(M, nullptr, n, K, w, st);
     if (rc) return rc;
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, n, K, w.prices, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0,
+    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, nullptr, n, K, w.prices, nullptr, WARM_DUAL_ITERS, WARM_STEP0,
                                                                          d, nullptr, assign, nullptr, w.status, 3,
                                                                          solver_m_fits(n, K) ? 1 : 0);
     FG_LAUNCH_CHECK();
@@ -836,7 +970,7 @@ extern "C" int fg_ot_cost_matrix(const void* probs_gender, const void* probs_rac
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status);
         if (n_valid > 0) cost_hist_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
-            (const T*)probs_age, w.idx, n_valid, K, M, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr));
+            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

@@ -8,11 +8,14 @@
 //
 // One CTA computes a 128 x 64 output tile: M = 128 rows live on the 128 TMEM lanes, the fp32 accumulator takes 64
 // TMEM columns, K advances 64 elements per shared-memory stage (4 tcgen05.mma of K = 16 each).  Operands are staged
-// by all 128 threads with 16-byte global loads into the canonical K-major, no-swizzle UMMA layout (8 x 16-byte core
-// matrices; LBO = stride between core matrices along K, SBO = stride between 8-row groups), two stages deep so the
-// loads of stage s+1 overlap the MMAs of stage s; completion is tracked with tcgen05.commit on mbarriers.  The
-// backward reads W1 with N contiguous and transposes it while staging.  The problem is tiny (2.5 GFLOP at m = 1024),
-// so the kernel is built for low latency and few launches, not for peak tensor throughput.
+// by all 128 threads with 16-byte cp.async copies straight into the canonical no-swizzle UMMA layouts (8 x 16-byte
+// core matrices; LBO = stride between core matrices along K, SBO = stride between 8-row groups along M/N): K-major
+// for A and for the forward's W1 [N,K]; MN-major for the backward's W1 read as [K,N] (a core matrix is then 8 k-rows
+// of 8 consecutive n, i.e. the 16-byte chunks of the row-major matrix as they are -- no transpose while staging).
+// The ring is STAGES deep with DIST stages in flight, so the DRAM latency of the operands (the step's streaming
+// kernels leave nothing of them in L2) is paid once, not per K step; completion of the MMAs that read a slot is
+// tracked with tcgen05.commit on mbarriers.  The problem is tiny (2.5 GFLOP at m = 1024), so the kernel is built
+// for low latency and few launches, not for peak tensor throughput.
 #pragma once
 
 namespace tc {
@@ -24,6 +27,7 @@ constexpr int B_STAGE = BN * BK * 2;
 constexpr int A_LBO = BM * 16, B_LBO = BN * 16; // K-direction stride between core matrices
 constexpr int SBO = 128;                        // M/N-direction stride between 8-row groups
 constexpr int TMEM_COLS = 64;
+constexpr int STAGES = 4, DIST = 3;            // shared-memory ring depth, stages in flight (2 CTAs of 96 KB fit an SM)
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -32,11 +36,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ uint32_t instr_desc(int a_fmt, int b_fmt) {
-    // cute::UMMA::InstrDescriptor: c_format F32 = 1 [4,6) | a_format [7,10) | b_format [10,13) | K-major A,B |
-    // n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
-    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t instr_desc(int a_fmt, int b_fmt, int b_mn_major) {
+    // cute::UMMA::InstrDescriptor: c_format F32 = 1 [4,6) | a_format [7,10) | b_format [10,13) | a_major [15] = K |
+    // b_major [16]: 0 = K-major, 1 = MN-major | n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {   // src_bytes = 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -81,29 +91,52 @@ struct Params {
     float* part;                      // MODE 0: [N/BN, M, k_head]
 };
 
-// dynamic smem: 2 x (A stage | B stage) | W2 tile fp32 [k_head][BN] | b1 tile [BN] | mbarriers | tmem slot
+// dynamic smem: STAGES x (A stage | B stage) | W2 tile fp32 [k_head][BN] | b1 tile [BN] | mbarriers | tmem slot
 template <typename T, int MODE>
 __global__ void __launch_bounds__(THREADS)
 head_gemm_tc_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* stageA[2] = {smem, smem + A_STAGE + B_STAGE};
-    uint8_t* stageB[2] = {smem + A_STAGE, smem + 2 * A_STAGE + B_STAGE};
-    float* w2s = reinterpret_cast<float*>(smem + 2 * (A_STAGE + B_STAGE));
+    float* w2s = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE));
     float* b1s = w2s + (MODE == 0 ? p.k_head * BN : 0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + BN);          // [0,1]: stage free, [2]: accumulator ready
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b1s + BN);          // [0, STAGES): slot free, [STAGES]: accumulator ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES + 1);
+    const uint32_t ring = s32(smem);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const T* A = reinterpret_cast<const T*>(p.A);
     const T* B = reinterpret_cast<const T*>(p.B);
 
     if (tid == 0) {
-        bar_init(&bars[0], 1); bar_init(&bars[1], 1); bar_init(&bars[2], 1);
+        for (int s = 0; s <= STAGES; s++) bar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // one K step of operands -> ring slot: 12 x 16-byte chunks per thread
+    auto load_stage = [&](int ks) {
+        const uint32_t a_dst = ring + (ks % STAGES) * (A_STAGE + B_STAGE), b_dst = a_dst + A_STAGE;
+        const int k0 = ks * BK;
+#pragma unroll
+        for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
+            const bool in = m0 + r < p.M;
+            cp_async16(a_dst + kc * A_LBO + r * 16, A + (size_t)(in ? m0 + r : 0) * p.lda + k0 + kc * 8, in ? 16u : 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
+            const int c = tid + THREADS * j, r = c >> 3, q = c & 7;
+            if (MODE == 0)    // B [N,K]: row n, 8 consecutive k -> K-major core-matrix row n
+                cp_async16(b_dst + q * B_LBO + r * 16, B + (size_t)(n0 + r) * p.ldb + k0 + q * 8, 16u);
+            else              // B [K,N]: row k, 8 consecutive n -> MN-major core matrix (k group r>>3, n group q), row k&7
+                cp_async16(b_dst + (r >> 3) * B_LBO + q * SBO + (r & 7) * 16, B + (size_t)(k0 + r) * p.ldb + n0 + q * 8, 16u);
+        }
+    };
+    const int ksteps = p.K / BK;
+    for (int s = 0; s < DIST; s++) {
+        if (s < ksteps) load_stage(s);
+        cp_async_commit();
     }
     if (MODE == 0) {
         const T* w2 = reinterpret_cast<const T*>(p.w2);
@@ -115,56 +148,16 @@ head_gemm_tc_kernel(const Params p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code);
+    const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code, MODE == 1 ? 1 : 0);
 
-    const int ksteps = p.K / BK;
     for (int ks = 0; ks < ksteps; ks++) {
-        const int st = ks & 1;
-        const int k0 = ks * BK;
-        // all global loads of this stage are issued before anything is stored (the stores go through generic
-        // pointers, so the compiler would otherwise keep each load behind the previous store), and before the wait
-        // for the stage to be free, so their latency overlaps the MMAs still reading it
-        int4 va[(BM * BK / 8) / THREADS], vb[(BN * BK / 8) / THREADS];
-#pragma unroll
-        for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
-            const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
-            va[j] = make_int4(0, 0, 0, 0);
-            if (m0 + r < p.M) va[j] = __ldg(reinterpret_cast<const int4*>(A + (size_t)(m0 + r) * p.lda + k0 + kc * 8));
-        }
-#pragma unroll
-        for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
-            const int c = tid + THREADS * j, r = c >> 3, q = c & 7;
-            if (MODE == 0) vb[j] = __ldg(reinterpret_cast<const int4*>(B + (size_t)(n0 + r) * p.ldb + k0 + q * 8));
-            else           vb[j] = __ldg(reinterpret_cast<const int4*>(B + (size_t)(k0 + r) * p.ldb + n0 + q * 8));
-        }
-        if (ks >= 2) bar_wait(&bars[st], (uint32_t)(((ks >> 1) - 1) & 1));   // MMAs that read this stage are done
-        // ---- stage A: 128 rows x 8 chunks of 8 elements
-#pragma unroll
-        for (int j = 0; j < (BM * BK / 8) / THREADS; j++) {
-            const int c = tid + THREADS * j, r = c >> 3, kc = c & 7;
-            *reinterpret_cast<int4*>(stageA[st] + kc * A_LBO + r * 16) = va[j];
-        }
-        // ---- stage B
-#pragma unroll
-        for (int j = 0; j < (BN * BK / 8) / THREADS; j++) {
-            const int c = tid + THREADS * j;
-            if (MODE == 0) {
-                const int r = c >> 3, kc = c & 7;
-                *reinterpret_cast<int4*>(stageB[st] + kc * B_LBO + r * 16) = vb[j];
-            } else {
-                // B is [K, N] with N contiguous: 8 consecutive n of one k go to 8 core-matrix rows
-                const int k = c >> 3, nc = c & 7;
-                const uint16_t* e = reinterpret_cast<const uint16_t*>(&vb[j]);
-                uint8_t* base = stageB[st] + (k >> 3) * B_LBO + nc * 128 + (k & 7) * 2;
-#pragma unroll
-                for (int q = 0; q < 8; q++) *reinterpret_cast<uint16_t*>(base + q * 16) = e[q];
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+        const int st = ks % STAGES;
+        cp_async_wait<DIST - 1>();                                       // this thread's chunks of K step ks have landed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // ... and are visible to the tensor core
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = s32(stageA[st]), b0 = s32(stageB[st]);
+            const uint32_t a0 = ring + st * (A_STAGE + B_STAGE), b0 = a0 + A_STAGE;
 #pragma unroll
             for (int kk = 0; kk < BK / 16; kk++) {
                 const uint64_t ad = smem_desc(a0 + kk * 2 * A_LBO, A_LBO, SBO);
@@ -172,10 +165,17 @@ head_gemm_tc_kernel(const Params p) {
                 mma_f16(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
             }
             mma_commit(&bars[st]);                                        // implies fence::before_thread_sync
-            if (ks == ksteps - 1) mma_commit(&bars[2]);
+            if (ks == ksteps - 1) mma_commit(&bars[STAGES]);
         }
+        const int nxt = ks + DIST;
+        if (nxt < ksteps) {
+            // the slot of K step nxt was last read by the MMAs of K step nxt - STAGES
+            if (nxt >= STAGES) bar_wait(&bars[nxt % STAGES], (uint32_t)((nxt / STAGES - 1) & 1));
+            load_stage(nxt);
+        }
+        cp_async_commit();
     }
-    bar_wait(&bars[2], 0);
+    bar_wait(&bars[STAGES], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: thread = output row (TMEM lane), 2 chunks of 32 columns
@@ -250,7 +250,7 @@ __global__ void head_reduce_partials_kernel(const float* __restrict__ part, cons
 }
 
 inline size_t smem_bytes(int mode, int k_head) {
-    return 2 * (A_STAGE + B_STAGE) + (mode == 0 ? (size_t)k_head * BN * 4 : 0) + BN * 4 + 3 * 8 + 16;
+    return STAGES * (A_STAGE + B_STAGE) + (mode == 0 ? (size_t)k_head * BN * 4 : 0) + BN * 4 + (STAGES + 1) * 8 + 16;
 }
 
 }  // namespace tc
