@@ -649,7 +649,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     if (tid == 0 && sm.status && status) atomicOr(&status[0], sm.status);
 #ifdef FG_OT_PROFILE
     FG_MARK();
-    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 57))
+    if (tid == 0)
         printf("otprof blk %d N %d K %d grid %d: copy %lld search %lld assign %lld rescan %lld ssp(%d) %lld out %lld total %lld cycles\n", blockIdx.x, N, K, gridDim.x,
                tprof[1] - tprof[0], tprof[2] - tprof[1], tprof[3] - tprof[2], tprof[4] - tprof[3], iters, tprof[5] - tprof[4], tprof[6] - tprof[5], tprof[6] - tprof[0]);
 #endif

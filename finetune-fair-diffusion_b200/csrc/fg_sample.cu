@@ -322,12 +322,12 @@ static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 gri
     cudaError_t e;
     if constexpr (sizeof(T) == 2) {
         // 16-bit gradients at the BASELINE shape: rows staged through shared memory by bulk async copies
-        static const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switch for kernel tuning runs
+        const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switch for kernel tuning runs
         const bool aligned = ((uintptr_t)p.g_small % 16 == 0) && ((uintptr_t)p.g_chips % 16 == 0);
         if (spec && aligned && !staged_off) {
             // rows per CTA: per-CTA set-up (tap tables) is amortised over NSUB * 8 rows, but the grid should still be
             // >= ~8 waves of 148 SMs x 3 resident CTAs; FG_BWD_NSUB overrides for tuning runs only
-            static const int nsub_env = getenv("FG_BWD_NSUB") ? atoi(getenv("FG_BWD_NSUB")) : 0;
+            const int nsub_env = getenv("FG_BWD_NSUB") ? atoi(getenv("FG_BWD_NSUB")) : 0;
             const int nsub = nsub_env ? nsub_env : (p.n >= 896 ? 16 : p.n >= 448 ? 8 : 4);
             if (nsub == 16) {
                 using L = GsLayout<16>;

@@ -153,6 +153,59 @@ def test_tiled_and_generic_kernels_agree(fg, dtype, H, W, o, monkeypatch):
         assert torch.allclose(a, b, rtol=tol, atol=tol * max(1.0, float(b.abs().max()))), (a - b).abs().max()
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("branches", ["both", "chips_only", "small_only"])
+@pytest.mark.parametrize("nsub", ["4", "8", "16"])
+def test_staged_image_grad_matches_generic_kernel(fg, dtype, branches, nsub, monkeypatch):
+    """The bulk-copy staged backward (16-bit gradients, 512x512 / 224x224) against the generic gather kernel, for every
+    rows-per-CTA variant, with each gradient branch alone, boxes that are upscaled (< 224 px), huge, tiny (cold path),
+    partly or fully outside the image, missing faces and a scaled region."""
+    H = W = 512; o = 224; n = 12
+    rng = np.random.default_rng(int(nsub) + len(branches))
+    boxes = torch.tensor(_random_boxes(rng, n, H, W), device=DEV)
+    boxes[0] = torch.tensor([-120, -90, 530, 560])        # larger than the image
+    boxes[1] = torch.tensor([200, 210, 205, 214])         # 5x4 px: direct-gather path
+    boxes[2] = torch.tensor([100, 120, 250, 270])         # 150 px: upscaled, up to 3 taps per pixel
+    boxes[3] = torch.tensor([300, 40, 700, 440])          # crosses the right border
+    boxes[4] = torch.tensor([600, 600, 800, 800])         # outside
+    boxes[5] = torch.tensor([10, 300, 130, 420])          # 120 px: more than 16 chip rows per 8 image rows at the edge
+    boxes[6] = torch.tensor([0, 0, 512, 512])
+    ind = torch.ones(n, dtype=torch.bool, device=DEV); ind[7] = False
+    region = torch.tensor([[50, 60, 400, 380]] * n, dtype=torch.int32, device=DEV)
+    region[8] = torch.tensor([0, 0, 0, 0], dtype=torch.int32)
+    scale = torch.linspace(0.2, 1.0, n, device=DEV)
+    gc = torch.randn(n, 3, o, o, device=DEV).to(dtype) if branches != "small_only" else None
+    gs = torch.randn(n, 3, o, o, device=DEV).to(dtype) if branches != "chips_only" else None
+    outs = []
+    for generic in (False, True):
+        monkeypatch.setenv("FG_BWD_NSUB", nsub)
+        if generic:
+            monkeypatch.setenv("FG_FORCE_GENERIC", "1")
+        else:
+            monkeypatch.delenv("FG_FORCE_GENERIC", raising=False)
+        outs.append(fg.ops.image_grad(gc, gs, boxes, ind, region, scale, (n, 3, H, W), dtype, torch.device(DEV)).float())
+    a, b = outs
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.allclose(a, b, rtol=tol, atol=tol * float(b.abs().max())), (a - b).abs().max()
+    # pixels no gradient reaches are exactly zero
+    if branches == "chips_only":
+        assert float(a[7].abs().max()) == 0.0 and float(a[4].abs().max()) == 0.0
+
+
+def test_staged_image_grad_keeps_nonfinite_local(fg):
+    """A non-finite resized-image gradient must not leak into pixels it does not touch (rows / columns without a tap
+    read a zero row, not a zero weight)."""
+    H = W = 512; o = 224
+    gs = torch.zeros(1, 3, o, o, device=DEV, dtype=torch.bfloat16)
+    gs[0, :, 100, 50] = float("inf")
+    g = fg.ops.image_grad(None, gs, torch.zeros(1, 4, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.bool, device=DEV),
+                          None, None, (1, 3, H, W), torch.bfloat16, torch.device(DEV)).float()
+    bad = ~torch.isfinite(g)
+    ys, xs = torch.where(bad[0, 0])
+    assert 1 <= ys.numel() <= 4 and int(ys.min()) >= 227 and int(ys.max()) <= 230 and int(xs.min()) >= 113 and int(xs.max()) <= 116
+    assert float(g[torch.isfinite(g)].abs().max()) == 0.0
+
+
 def test_crop_adjoint_property_full_size(fg):
     """<crop(x), g> == <x, crop_bwd(g)> at the BASELINE shapes (size-independent check of the
     backward against the forward), plus linearity of the sampler in the image."""
