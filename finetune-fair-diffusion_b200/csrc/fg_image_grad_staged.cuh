@@ -56,17 +56,6 @@ template <int NSUB> struct GsLayout {
     static constexpr size_t total = tb + 3 * GS_T_CH;
 };
 
-// shared-memory accesses by 32-bit address (volatile: never merged or hoisted across the barriers)
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-template <typename T> __device__ __forceinline__ float bits16_to_f32(uint32_t v);
-template <> __device__ __forceinline__ float bits16_to_f32<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
-template <> __device__ __forceinline__ float bits16_to_f32<__half>(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)v)); }
-
 // stage 1 for one sub-tile: tb[c][r][ox] = sum_q w[r][q] * sC[c][off_r + q][ox]   (this thread: column ox)
 template <typename T>
 __device__ __forceinline__ void gs_stage1(uint32_t rec, uint32_t col, uint32_t tcol) {

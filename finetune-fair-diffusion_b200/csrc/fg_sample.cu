@@ -307,6 +307,7 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
     p.boxes = (const long long*)boxes; p.ind = indicators;
     p.chips = chips; p.ch = chip_h; p.cw = chip_w; p.small = small; p.sh = small_h; p.sw = small_w;
     p.fill = fill_value; p.total_tiles = (int)total;
+    p.pair_mode = getenv("FG_FWD_PAIR") ? 1 : 2;      // 1: tuning A/B, two columns per thread everywhere
     const unsigned grid = (unsigned)(total < 2LL * FG_NUM_SMS ? total : 2LL * FG_NUM_SMS);   // persistent, 2 CTAs per SM
     switch (dtype) {
         case FG_F32: return launch_fwd_tiled_t<float, 2>(p, smem, grid, st);

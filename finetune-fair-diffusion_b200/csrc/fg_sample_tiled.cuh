@@ -53,6 +53,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared-memory accesses by 32-bit address (volatile: never merged or hoisted across barriers)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+template <typename T> __device__ __forceinline__ float bits16_to_f32(uint32_t v);
+template <> __device__ __forceinline__ float bits16_to_f32<__nv_bfloat16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <> __device__ __forceinline__ float bits16_to_f32<__half>(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)v)); }
+template <> __device__ __forceinline__ float bits16_to_f32<float>(uint32_t v) { return 0.f; }     // never called (16-bit paths only)
+
 template <typename T> struct Pack2;
 template <> struct Pack2<float> { using type = float2; static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); } };
 template <> struct Pack2<__nv_bfloat16> { using type = __nv_bfloat162; static __device__ __forceinline__ __nv_bfloat162 make(float a, float b) { return __floats2bfloat162_rn(a, b); } };
@@ -66,6 +78,7 @@ struct FwdParams {
     float fill;
     int tiles_small, tiles_chip;      // row tiles per job
     int total_tiles;
+    int pair_mode;                    // tuning: 1 = 16-bit interior tiles use the two-columns-per-thread path
 };
 
 // one per ring stage: written by the producer (lane 0) before it arrives on `full`
@@ -82,6 +95,7 @@ struct __align__(16) FwdMeta {
     int ya[TOH], yb[TOH];   // absolute image rows of the two taps
     int sa[TOH], sb[TOH];   // ring row slots (per channel) holding those rows
     float l0[TOH], l1[TOH];
+    uint4 rowrec[TOH];      // {byte offset of tap row a inside a ring channel, same for b, l0 bits, l1 bits}: one 16-byte read per row
 };
 
 template <typename T, int C, int STAGES, int WFIX>
@@ -170,6 +184,8 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                 m.ya[lane] = b.y0 + ay.i0; m.yb[lane] = b.y0 + ay.i1; m.l0[lane] = ay.l0; m.l1[lane] = ay.l1;
                 m.sa[lane] = dense ? b.y0 + ay.i0 - yf : 2 * lane;
                 m.sb[lane] = dense ? b.y0 + ay.i1 - yf : 2 * lane + 1;
+                m.rowrec[lane] = make_uint4((uint32_t)(m.sa[lane] * W) * (uint32_t)sizeof(T), (uint32_t)(m.sb[lane] * W) * (uint32_t)sizeof(T),
+                                            __float_as_uint(ay.l0), __float_as_uint(ay.l1));
             }
             if (lane == 0) {
                 m.ok = b.ok ? 1 : 0;
@@ -190,6 +206,9 @@ sample_fwd_tiled_kernel(const FwdParams p) {
         // ------------------------------------------------------------------ consumer warps
         const int ctid = threadIdx.x;                  // 0..223
         const float fill = p.fill;
+        const uint32_t ring_a = smem_u32(ring), meta_a = smem_u32(meta);
+        int cache_x0 = 0x7fffffff, cache_bw = -1;      // single-column path: the box this thread's column taps were built for
+        uint32_t col_a = 0, col_d = 0; float lx0 = 0.f, lx1 = 0.f;
         int k = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
             const int s = k % STAGES;
@@ -209,7 +228,41 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                 const T* st = reinterpret_cast<const T*>(ring) + (size_t)s * stage_elems;
                 const int x0 = m.x0, bw = m.bw;
                 const float sx = m.sx;
-                if (sizeof(T) == 2 && m.inside && (ow & 1) == 0) {
+                if (sizeof(T) == 2 && WFIX && p.pair_mode != 1 && m.inside && ow == FWD_CONSUMERS) {
+                    // interior tile of a 16-bit job whose rows are as wide as the consumer group (224): a thread owns ONE
+                    // output column, so the 32 lanes of a load touch a compact run of shared-memory words (a pair of
+                    // columns per thread spreads them over 2.3x more words: 2.45 wavefronts per load on the whole-image
+                    // resize).  Addresses are 32-bit shared addresses; every channel / row offset is an immediate.
+                    constexpr uint32_t CHB = (uint32_t)RMAX * (WFIX ? WFIX : 1) * (uint32_t)sizeof(T);
+                    if (x0 != cache_x0 || bw != cache_bw) {            // column taps change only with the box
+                        const Axis a = axis_index(ctid, sx, bw);
+                        col_a = (uint32_t)(x0 + a.i0) * (uint32_t)sizeof(T); col_d = (uint32_t)(a.i1 - a.i0) * (uint32_t)sizeof(T);
+                        lx0 = a.l0; lx1 = a.l1; cache_x0 = x0; cache_bw = bw;
+                    }
+                    const uint32_t sbase = ring_a + (uint32_t)s * (uint32_t)(stage_elems * sizeof(T)) + col_a;
+                    const uint32_t rec = meta_a + (uint32_t)s * (uint32_t)sizeof(FwdMeta) + (uint32_t)offsetof(FwdMeta, rowrec);
+                    T* outp = out + ctid;
+#pragma unroll
+                    for (int r = 0; r < TOH; r++) {
+                        if (r < rows) {
+                            const uint4 h = lds_v4(rec + r * 16);
+                            const float l0 = __uint_as_float(h.z), l1 = __uint_as_float(h.w);
+                            const uint32_t aA = sbase + h.x, aB = sbase + h.y;
+                            uint32_t v[C][4];
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                v[c][0] = lds_u16(aA + c * CHB); v[c][1] = lds_u16(aA + col_d + c * CHB);
+                                v[c][2] = lds_u16(aB + c * CHB); v[c][3] = lds_u16(aB + col_d + c * CHB);
+                            }
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                const float top = lx0 * bits16_to_f32<T>(v[c][0]) + lx1 * bits16_to_f32<T>(v[c][1]);
+                                const float bot = lx0 * bits16_to_f32<T>(v[c][2]) + lx1 * bits16_to_f32<T>(v[c][3]);
+                                outp[c * oplane + r * FWD_CONSUMERS] = from_f32<T>(l0 * top + l1 * bot);
+                            }
+                        }
+                    }
+                } else if (sizeof(T) == 2 && p.pair_mode && m.inside && (ow & 1) == 0) {
                     // interior tile: a thread owns two adjacent output columns (packed store) and two of the
                     // four rows; with WFIX the row offsets into the ring are compile-time constants
                     constexpr int HALF = FWD_CONSUMERS / 2;
