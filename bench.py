@@ -107,6 +107,23 @@ class EventProbe:
         return sum(a.elapsed_time(b) for a, b in p) / len(p) if p else None
 
 
+def ncu_traffic(kernel, n_local, dtype_name):
+    """dram read + write bytes of one launch of `kernel` from the committed `ncu --set full` capture (profiles/*_traffic.json,
+    taken on workload C5 at 1 GPU); None for any other workload."""
+    if n_local != 1024 or dtype_name != "bfloat16":
+        return None
+    here = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(f for f in os.listdir(os.path.join(here, "profiles")) if f.endswith("_traffic.json"))
+    if not files:
+        return None
+    d = json.load(open(os.path.join(here, "profiles", files[-1])))
+    for name, launches in d["kernels"].items():
+        if kernel in name:
+            l = launches[-1]
+            return l["dram_read_bytes"] + l["dram_write_bytes"]
+    return None
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
@@ -304,8 +321,9 @@ def main():
     dom = "image_grad" if (stage_ms["image_grad"] or 0) >= (stage_ms["sample_fwd"] or 0) else "sample_fwd"
     alg = (bwd_b if dom == "image_grad" else fwd_b) * n_local
     ach = alg / (stage_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+    kname = {"image_grad": "image_grad_staged_kernel" if esize == 2 else "image_grad_tiled_kernel", "sample_fwd": "sample_fwd_tiled_kernel"}[dom]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(kname, n_local, dtype_name), "peak_source": pk_src,
                 "algorithmic_bytes_per_launch": alg,
                 "kernels": {k: {"ms": stage_ms[k], "GBps": ((fwd_b if k == "sample_fwd" else bwd_b) * n_local / (stage_ms[k] * 1e-3) / 1e9)}
                             for k in ("sample_fwd", "image_grad") if stage_ms[k]},

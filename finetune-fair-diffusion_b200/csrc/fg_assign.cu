@@ -15,14 +15,18 @@
 //   * from such a state, moving one unit from an over-full class to an under-full class along a
 //     SHORTEST path of the K-node class graph (edge k->l costs  min_{i in k} M[i,l]-M[i,k])
 //     keeps optimality for the new class sizes (successive shortest paths);
-//   * so one "base" assignment for the expected demand is computed once (coarse-to-fine over
-//     growing prefixes of the rows, each level warm-started by the previous level's prices), and
-//     every draw only repairs  |b_s - b_base|_1 / 2  units starting from the base.
+//   * so every draw runs, in its own CTA, a cheap parallel PRICE SEARCH (sign-based dual ascent on the K prices in
+//     fp32: any prices are admissible, it only has to bring the class sizes close to the demand) and then repairs
+//     the remaining  |sizes - b_s|_1 / 2  units exactly, one shortest path each.
 //
-// One CTA per problem; the class graph lives in shared memory; edge minima are found with
-// warp-level REDUX reductions on order-preserving 64-bit keys; the shortest-path search
-// (Bellman-Ford over <= 16 nodes) runs in one warp with shuffles.  All cost arithmetic is fp64
-// like POT's; ties resolve to the lowest row index / lowest class index, deterministically.
+// One CTA (512 threads) per problem.  FP64 issues at a small fraction of the FP32 rate on this part and the fp64
+// cost matrix stays in global memory, so shared memory holds a class-major FP32 copy (written once by the cost
+// kernel) that serves the price search and SCREENS every exact decision: the final argmin of a row and the edge
+// minima of the class graph are taken in fp32 first, and fp64 is evaluated only for the winner or, when the runner-up
+// is within SCREEN_EPS, for the near-ties.  The class graph lives in shared memory; edge minima use warp-level REDUX
+// on order-preserving keys; the shortest-path search (Bellman-Ford over <= 16 nodes) runs in one warp.  Every result
+// that leaves the kernel is decided by fp64 arithmetic like POT's; ties resolve to the lowest row index / lowest
+// class index, deterministically.  fg_ot_solve_single additionally exercises a warm-started second solve.
 #include "fg_common.cuh"
 #include <math.h>
 #include <cstdlib>

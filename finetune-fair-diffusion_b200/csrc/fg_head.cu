@@ -4,10 +4,10 @@
 // per-attribute slice / softmax / argmax / scatter of get_face_gender* (E1:1355-1401,
 // E3:1387-1457, E4:1378-1475).
 //
-// Round-1 implementation: the two projections run as shared-memory tiled fp32-accumulate GEMMs on
-// the CUDA cores (exact fp32 for the fp32 configs).  The 960->1280 projection is the only
-// GEMM-shaped work on the path (2.46 MFLOP per face); the tcgen05 version is in fg_head_tc.cu and
-// is selected for bf16/fp16 inputs when FG_HEAD_TC is enabled.
+// The 960->1280 projection is the only GEMM-shaped work on the path (2.46 MFLOP per face).  bf16 / fp16 inputs run it
+// on the tensor cores (fg_head_tc.cuh: tcgen05.mma with the accumulator in TMEM, bias + Hardswish + the partial
+// second projection fused into the epilogue; FG_HEAD_SIMT=1 forces the CUDA-core path for A/B runs); fp32 inputs keep
+// exact fp32 arithmetic with the shared-memory tiled fp32-accumulate GEMM below.
 #include "fg_common.cuh"
 #include <cstdlib>
 

@@ -10,9 +10,12 @@
 //   producer also decodes the tile (image, box, scales, row taps) once and hands that to the consumers
 //   through shared memory.  Rows keep their absolute x position in shared memory; pixels outside the
 //   image are detected from coordinates and read `fill`.  Tiles are numbered image-major with small_i
-//   and chip_i adjacent, so the second pass over an image's pixels hits L2.
+//   and chip_i adjacent, so the second pass over an image's pixels hits L2.  Interior 16-bit tiles at the BASELINE
+//   width take a lean path: one output column per thread (the 32 lanes of a load then touch a compact run of
+//   shared-memory words), 32-bit shared addresses with every row / channel offset an immediate.
 //
-// BACKWARD  image_grad_tiled_kernel
+// BACKWARD  image_grad_tiled_kernel   (fp32 gradients and shapes other than 512/224; 16-bit gradients at the BASELINE
+//                                      shape use image_grad_staged_kernel, fg_image_grad_staged.cuh)
 //   One CTA per (image, 32 source rows), processed as 4 sub-tiles of 8 rows.  Bilinear resampling is
 //   separable, so the gather runs in two stages through shared memory:
 //     stage 1 (vertical)   t[g][c][r][ox] = sum_oy wy(oy, y_r) * G_g[c][oy][ox]      coalesced G reads
