@@ -10,6 +10,9 @@
 // exact fp32 arithmetic with the shared-memory tiled fp32-accumulate GEMM below.
 #include "fg_common.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <cuda.h>             // CUtensorMap types only; the encoder is looked up through the runtime, libcuda is not linked
 
 namespace {
 
@@ -178,17 +181,67 @@ static bool tc_ok(int dtype, int m, int d_in, int d_hid, int k_head, const void*
            ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && getenv("FG_HEAD_SIMT") == nullptr;
 }
 
+// ---- 2-D tensor maps for the TMA kernel (row-major 16-bit matrix, 64-element x box_rows boxes, 128-byte swizzle)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return getenv("FG_HEAD_CPASYNC") ? nullptr : fn;       // FG_HEAD_CPASYNC=1: A/B runs against the cp.async kernel
+}
+template <typename T>
+static bool make_map(tc::TmaMap* out, const void* base, int inner, int rows, int ld, int box_rows) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) return false;
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (enc(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(tc::TmaMap), "tensor map size");
+    memcpy(out, &m, sizeof(m));
+    return true;
+}
+
+template <typename T, int MODE>
+static int launch_head_gemm(const tc::Params& p, dim3 grid, cudaStream_t st) {
+    tc::TmaMap mapA, mapB;
+    // A [M,K]: boxes of 128 rows; B: forward [N,K] boxes of 64 rows (n), backward [K,N] boxes of 64 rows (k) x 64 n
+    const bool tma = make_map<T>(&mapA, p.A, p.K, p.M, p.lda, tc::BM) &&
+                     (MODE == 0 ? make_map<T>(&mapB, p.B, p.K, p.N, p.ldb, tc::BN) : make_map<T>(&mapB, p.B, p.N, p.K, p.ldb, tc::BK));
+    cudaError_t e;
+    if (tma) {
+        const size_t smem = tc::smem_bytes_tma(MODE, p.k_head);
+        e = cudaFuncSetAttribute(tc::head_gemm_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        tc::head_gemm_tma_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p, mapA, mapB);
+    } else {
+        const size_t smem = tc::smem_bytes(MODE, p.k_head);
+        e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        tc::head_gemm_tc_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p);
+    }
+    return FG_OK;
+}
+
 template <typename T>
 static int head_fwd_tc(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2, int m, int d_in,
                        int d_hid, int k_head, void* hidden_pre, float* logits, float* part, cudaStream_t st) {
     tc::Params p;
     p.A = pooled; p.lda = d_in; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_hid; p.K = d_in;
     p.bias = b1; p.out = hidden_pre; p.ldo = d_hid; p.w2 = w2; p.k_head = k_head; p.part = part;
-    const size_t smem = tc::smem_bytes(0, k_head);
-    cudaError_t e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    dim3 grid(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM);
-    tc::head_gemm_tc_kernel<T, 0><<<grid, tc::THREADS, smem, st>>>(p);
+    int rc = launch_head_gemm<T, 0>(p, dim3(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    if (rc) return rc;
     const int tot = m * k_head;
     tc::head_reduce_partials_kernel<T><<<(tot + 255) / 256, 256, 0, st>>>(part, (const T*)b2, d_hid / tc::BN, m, k_head, logits);
     FG_LAUNCH_CHECK();
@@ -203,11 +256,8 @@ static int head_bwd_tc(const float* g_logits, const void* hidden_pre, const void
     tc::Params p;
     p.A = g_pre16; p.lda = d_hid; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_in; p.K = d_hid;
     p.bias = nullptr; p.out = g_pooled; p.ldo = d_in; p.w2 = nullptr; p.k_head = 0; p.part = nullptr;
-    const size_t smem = tc::smem_bytes(1, 0);
-    cudaError_t e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    dim3 grid(d_in / tc::BN, (m + tc::BM - 1) / tc::BM);
-    tc::head_gemm_tc_kernel<T, 1><<<grid, tc::THREADS, smem, st>>>(p);
+    int rc = launch_head_gemm<T, 1>(p, dim3(d_in / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    if (rc) return rc;
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

@@ -91,6 +91,65 @@ struct Params {
     float* part;                      // MODE 0: [N/BN, M, k_head]
 };
 
+// epilogue: thread = output row (TMEM lane), 2 chunks of 32 columns
+template <typename T, int MODE>
+__device__ __forceinline__ void epilogue(const Params& p, uint32_t tmem, const float* w2s, const float* b1s, int m0, int n0) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = m0 + tid;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    T* out = reinterpret_cast<T*>(p.out);
+    if (MODE == 0) {
+        float part[8];
+        for (int kb = 0; kb < p.k_head; kb += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) part[q] = 0.f;
+            for (int ch = 0; ch < BN / 32; ch++) {
+                float v[32];
+                __align__(16) T prs[32];
+                tmem_ld32(lane_base + ch * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float pre = round_to<T>(v[i] + b1s[ch * 32 + i]);
+                    const float r6 = fminf(fmaxf(pre + 3.f, 0.f), 6.f);
+                    v[i] = round_to<T>(pre * r6 * (1.f / 6.f));
+                    prs[i] = from_f32<T>(pre);
+                }
+                if (kb == 0 && row < p.M) {
+                    int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(prs)[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (kb + q < p.k_head) {
+                        const float* wr = w2s + (kb + q) * BN + ch * 32;
+                        float a = part[q];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) a = fmaf(v[i], wr[i], a);
+                        part[q] = a;
+                    }
+                }
+            }
+            if (row < p.M)
+                for (int q = 0; q < 8 && kb + q < p.k_head; q++)
+                    p.part[((size_t)blockIdx.x * p.M + row) * p.k_head + kb + q] = part[q];
+        }
+    } else {
+        for (int ch = 0; ch < BN / 32; ch++) {
+            float v[32];
+            tmem_ld32(lane_base + ch * 32, v);
+            if (row < p.M) {
+                __align__(16) T o16[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) o16[i] = from_f32<T>(v[i]);
+                int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(o16)[q];
+            }
+        }
+    }
+}
+
 // dynamic smem: STAGES x (A stage | B stage) | W2 tile fp32 [k_head][BN] | b1 tile [BN] | mbarriers | tmem slot
 template <typename T, int MODE>
 __global__ void __launch_bounds__(THREADS)
@@ -178,63 +237,119 @@ head_gemm_tc_kernel(const Params p) {
     bar_wait(&bars[STAGES], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: thread = output row (TMEM lane), 2 chunks of 32 columns
-    const int row = m0 + tid;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    T* out = reinterpret_cast<T*>(p.out);
-    if (MODE == 0) {
-        float part[8];
-        for (int kb = 0; kb < p.k_head; kb += 8) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) part[q] = 0.f;
-            for (int ch = 0; ch < BN / 32; ch++) {
-                float v[32];
-                __align__(16) T prs[32];
-                tmem_ld32(lane_base + ch * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float pre = round_to<T>(v[i] + b1s[ch * 32 + i]);
-                    const float r6 = fminf(fmaxf(pre + 3.f, 0.f), 6.f);
-                    v[i] = round_to<T>(pre * r6 * (1.f / 6.f));
-                    prs[i] = from_f32<T>(pre);
-                }
-                if (kb == 0 && row < p.M) {
-                    int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(prs)[q];
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    if (kb + q < p.k_head) {
-                        const float* wr = w2s + (kb + q) * BN + ch * 32;
-                        float a = part[q];
-#pragma unroll
-                        for (int i = 0; i < 32; i++) a = fmaf(v[i], wr[i], a);
-                        part[q] = a;
-                    }
-                }
-            }
-            if (row < p.M)
-                for (int q = 0; q < 8 && kb + q < p.k_head; q++)
-                    p.part[((size_t)blockIdx.x * p.M + row) * p.k_head + kb + q] = part[q];
-        }
-    } else {
-        for (int ch = 0; ch < BN / 32; ch++) {
-            float v[32];
-            tmem_ld32(lane_base + ch * 32, v);
-            if (row < p.M) {
-                __align__(16) T o16[32];
-#pragma unroll
-                for (int i = 0; i < 32; i++) o16[i] = from_f32<T>(v[i]);
-                int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
-#pragma unroll
-                for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(o16)[q];
-            }
-        }
-    }
+    epilogue<T, MODE>(p, tmem, w2s, b1s, m0, n0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA version of the same tile: one elected thread streams the operands with cp.async.bulk.tensor (2-D tensor maps,
+// 128-byte swizzle) into a STAGES-slot ring and issues the MMAs; the copies are written through the async proxy, so no
+// proxy fence and no block barrier sits between a slot landing and the MMAs that read it (the cp.async version above
+// serialises on exactly that).  A tile row is 64 elements = 128 bytes = one swizzle span:
+//   A, forward W1 [N,K]:  K-major SWIZZLE_128B, 8-row groups 1024 bytes apart (SBO), K advances 32 bytes per MMA
+//   backward W1 as [K,N]: MN-major SWIZZLE_128B, a K row is one 128-byte line of 64 n, 8-row K groups 1024 bytes apart
+struct alignas(64) TmaMap { unsigned char bytes[128]; };     // CUtensorMap, opaque to device code
+
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    // start[0,14) | LBO[16,30) = 1 (unused for one swizzle span) | SBO[32,46) = 1024 >> 4 | version 1 [46,48) | SWIZZLE_128B = 2 [61,64)
+    return (uint64_t)((addr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const TmaMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s32(bar)), "r"(bytes) : "memory");
+}
+
+// dynamic smem (1024-byte aligned inside the kernel): STAGES x (A | B) | W2 tile | b1 tile | full[STAGES] empty[STAGES] done | tmem slot
+template <typename T, int MODE>
+__global__ void __launch_bounds__(THREADS)
+head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const __grid_constant__ TmaMap mapB) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
+    float* w2s = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE));
+    float* b1s = w2s + (MODE == 0 ? p.k_head * BN : 0);
+    uint64_t* full = reinterpret_cast<uint64_t*>(b1s + BN);
+    uint64_t* empty = full + STAGES;
+    uint64_t* done = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const uint32_t ring = s32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int ksteps = p.K / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+        bar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the whole ring is free: start streaming before anything else happens
+        for (int s = 0; s < STAGES && s < ksteps; s++) {
+            const uint32_t a_dst = ring + s * (A_STAGE + B_STAGE);
+            bar_expect_tx(&full[s], A_STAGE + B_STAGE);
+            tma_load_2d(a_dst, &mapA, s * BK, m0, &full[s]);
+            if (MODE == 0) tma_load_2d(a_dst + A_STAGE, &mapB, s * BK, n0, &full[s]);
+            else           tma_load_2d(a_dst + A_STAGE, &mapB, n0, s * BK, &full[s]);
+        }
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (MODE == 0) {
+        const T* w2 = reinterpret_cast<const T*>(p.w2);
+        const T* b1 = reinterpret_cast<const T*>(p.bias);
+        for (int e = tid; e < p.k_head * BN; e += THREADS) { int k = e / BN, n = e - k * BN; w2s[e] = to_f32(w2[(size_t)k * p.N + n0 + n]); }
+        for (int e = tid; e < BN; e += THREADS) b1s[e] = to_f32(b1[n0 + e]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code, MODE == 1 ? 1 : 0);
+        for (int ks = 0; ks < ksteps; ks++) {
+            const int st = ks % STAGES;
+            bar_wait(&full[st], (uint32_t)((ks / STAGES) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = ring + st * (A_STAGE + B_STAGE), b0 = a0 + A_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; kk++) {
+                const uint64_t ad = smem_desc_sw128(a0 + kk * 32);
+                const uint64_t bd = smem_desc_sw128(MODE == 0 ? b0 + kk * 32 : b0 + kk * 2048);
+                mma_f16(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
+            }
+            mma_commit(&empty[st]);
+            if (ks == ksteps - 1) mma_commit(done);
+            // refill the slot the PREVIOUS K step used (its MMAs have had one step to finish)
+            const int prev = ks - 1, nxt = prev + STAGES;
+            if (prev >= 0 && nxt < ksteps) {
+                const int ps = prev % STAGES;
+                bar_wait(&empty[ps], (uint32_t)((prev / STAGES) & 1));
+                const uint32_t a_dst = ring + ps * (A_STAGE + B_STAGE);
+                bar_expect_tx(&full[ps], A_STAGE + B_STAGE);
+                tma_load_2d(a_dst, &mapA, nxt * BK, m0, &full[ps]);
+                if (MODE == 0) tma_load_2d(a_dst + A_STAGE, &mapB, nxt * BK, n0, &full[ps]);
+                else           tma_load_2d(a_dst + A_STAGE, &mapB, n0, nxt * BK, &full[ps]);
+            }
+        }
+    }
+    __syncwarp();
+    bar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue<T, MODE>(p, tmem, w2s, b1s, m0, n0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+inline size_t smem_bytes_tma(int mode, int k_head) {
+    return 1024 + STAGES * (A_STAGE + B_STAGE) + (mode == 0 ? (size_t)k_head * BN * 4 : 0) + BN * 4 + (2 * STAGES + 1) * 8 + 16;
 }
 
 // logits[m,k] = b2[k] + sum_t part[t,m,k]   (fixed order: deterministic)
