@@ -291,6 +291,26 @@ def customized_all_gather(tensor, accelerator=None, return_tensor_other_processe
     return fdist.customized_all_gather(tensor, accelerator, return_tensor_other_processes)
 
 
+# ----------------------------------------------------------------------------- next rows
+def stage_detector_input(images, to_host=True):
+    """The detector's input array of ``get_face_app`` (E1:1317 + the BGR swap of E1:1326): uint8 ``[n,H,W,3]`` BGR.
+    The conversion runs on the device; with ``to_host`` the result is copied into pinned host memory (3 bytes per
+    pixel instead of the reference's float tensor) and returned as a numpy array, one row per ``face_app.get`` call."""
+    staged = ops.stage_detector_input(images.detach())
+    if not to_host:
+        return staged
+    host = torch.empty(staged.shape, dtype=torch.uint8, pin_memory=True)
+    host.copy_(staged, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def get_evaluate_metrics(probs_gender_all, probs_race_all, probs_age_all=None):
+    """E3:1716-1749 (5 numbers) / E4:1780-1821 (9 numbers with ``probs_age_all``) as python floats; one launch and one
+    device-to-host read instead of one blocking ``.item()`` per number."""
+    return tuple(ops.bias_metrics(probs_gender_all, probs_race_all, probs_age_all).tolist())
+
+
 def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_classifier=None, accelerator=None):
     """Closures with the reference's exact signatures (the reference captures these objects from
     ``main``): ``fg = bind(gender_race_classifier=clf, accelerator=acc); fg.get_face_gender_race(chips, sel)``."""
@@ -310,4 +330,6 @@ def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_cl
         face_chips, selector, fill_value, gender_race_age_classifier=gender_race_age_classifier)
     ns.customized_all_gather = lambda tensor, acc=accelerator, return_tensor_other_processes=False: customized_all_gather(
         tensor, acc, return_tensor_other_processes)
+    ns.stage_detector_input = stage_detector_input
+    ns.get_evaluate_metrics = get_evaluate_metrics
     return ns

@@ -317,3 +317,24 @@ def ot_cost_matrix(probs_gender, probs_race, probs_age, n_valid):
     check(_lib.lib().fg_ot_cost_matrix(_p(probs_gender.contiguous()), _p(probs_race.contiguous()), _p(pa), n_all, n_valid, _p(M),
                                        _p(ws.buf), ws.nbytes, _dt(probs_gender), _stream()), "fg_ot_cost_matrix")
     return M
+
+
+# ------------------------------------------------------------------ next rows (SURVEY 8f)
+def stage_detector_input(images):
+    """[n,3,H,W] in [-1,1] -> uint8 [n,H,W,3] BGR on the device (E1:1317 + 1326): what face_app.get() is fed."""
+    _cuda(images)
+    images = images.contiguous()
+    n, C, H, W = images.shape
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=images.device)
+    check(_lib.lib().fg_stage_detector_input(_p(images), n, C, H, W, _p(out), _dt(images), _stream()), "fg_stage_detector_input")
+    return out
+
+
+def bias_metrics(probs_gender, probs_race, probs_age=None):
+    """get_evaluate_metrics (E3:1716 / E4:1780) as one launch; returns a DEVICE fp64 tensor of 5 (or 9) numbers."""
+    _cuda(probs_gender, probs_race, probs_age)
+    pg, pr = probs_gender.contiguous(), probs_race.to(probs_gender.dtype).contiguous()
+    pa = None if probs_age is None else probs_age.to(probs_gender.dtype).contiguous()
+    out = torch.empty((9 if pa is not None else 5,), dtype=torch.float64, device=pg.device)
+    check(_lib.lib().fg_bias_metrics(_p(pg), _p(pr), _p(pa), pg.shape[0], _p(out), _dt(pg), _stream()), "fg_bias_metrics")
+    return out

@@ -187,6 +187,20 @@ int fg_ot_solve_single(const double* M, int n, int K, const int64_t* b_host, int
 int fg_ot_cost_matrix(const void* probs_gender, const void* probs_race, const void* probs_age, int n_all,
                       int n_valid, double* M, void* workspace, size_t workspace_bytes, int dtype, void* stream);
 
+/* ------------------------------------------------------------------ next rows -
+ * f2: detector staging (E1:1317 + 1326, same in E3 / E4).  out_bgr_hwc [n,H,W,3] uint8 =
+ *   ((images*0.5 + 0.5)*255) with every operation rounded through `dtype` like the eager expression, truncated to
+ *   uint8 like numpy's astype (out-of-range values wrap modulo 256, non-finite -> 0), permuted to HWC and swapped
+ *   to BGR -- the array face_app.get() receives.  images [n,3,H,W] dtype. */
+int fg_stage_detector_input(const void* images, int n, int C, int H, int W, uint8_t* out_bgr_hwc, int dtype, void* stream);
+
+/* f3: get_evaluate_metrics (E3:1716-1749; E4:1780-1821 when probs_age != NULL).  probs_* [n,2] / [n,4] / [n,2] dtype,
+ * rows of -1 are skipped.  out (DEVICE, fp64): [0] gender_gap [1] gender_pred_below_08 [2] race_gap
+ * [3] race_pred_below_08 [4] gender_race_gap, and with age [5] age0_freq [6] age1_freq [7] age_pred_below_08 [8] age_gap.
+ * One launch, no host synchronisation (the reference makes one blocking .item() per number). */
+int fg_bias_metrics(const void* probs_gender, const void* probs_race, const void* probs_age, int n, double* out,
+                    int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

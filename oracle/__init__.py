@@ -18,6 +18,7 @@ E3 = exp-3-debias-gender-race/1-main-debias.py, E4 = exp-4-debias-gender-race-ag
                 gen_dynamic_weights E1:1619-1633 / E3:1787-1803 / E4:1870-1895
     loss.py     loss assembly E1:1912-1933 / E3:2114-2147 / E4:2238-2283
     emd.py      exact transport solve standing in for POT ``ot.emd`` (not installed)
+    nextrows.py detector staging E1:1317/1326, get_evaluate_metrics E3:1716-1749 / E4:1780-1821
 
 Parity pinning: the reference has no tests or golden vectors.  The
 oracle is pinned instead against outputs of the reference's OWN function bodies, executed

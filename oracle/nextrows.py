@@ -1,0 +1,50 @@
+"""Oracle for the two "next" rows: detector staging and the bias-gap metrics.  Test infrastructure only.
+
+    stage_detector_input   E1:1317 (the uint8 conversion) + E1:1326 (the BGR swap), same lines in E3 / E4
+    evaluate_metrics       get_evaluate_metrics, E3:1716-1749 and E4:1780-1821
+
+torch-CPU restatements; pinned by tests/golden/nextrows.npz, which holds the outputs of the reference's own statements
+executed by tests/golden/make_golden_next.py.
+"""
+import numpy as np
+import torch
+
+
+def stage_detector_input(images):
+    """images [n,3,H,W] (any float dtype) -> uint8 [n,H,W,3], channels B,G,R.
+    The three arithmetic steps run in the tensor's dtype (one rounding each), as in the eager expression."""
+    scaled = images.detach() * 0.5
+    scaled = scaled + 0.5
+    scaled = scaled * 255
+    hwc = scaled.cpu().permute(0, 2, 3, 1).float().numpy().astype(np.uint8)
+    return np.ascontiguousarray(hwc[..., ::-1])
+
+
+def _valid(p):
+    return p[(p != -1).all(dim=-1)]
+
+
+def _freqs(hit_masks):
+    return torch.stack([m.float().mean() for m in hit_masks])
+
+
+def _mean_offdiag_l1(freq):
+    k = freq.shape[0]
+    d = (freq[:, None] - freq[None, :]).abs()
+    return (d.sum() / (k * (k - 1))).item()          # the diagonal is zero
+
+
+def evaluate_metrics(probs_gender_all, probs_race_all, probs_age_all=None):
+    g = _valid(probs_gender_all); r = _valid(probs_race_all)
+    pg, pr = g.argmax(dim=-1), r.argmax(dim=-1)
+    fg = _freqs([pg == q for q in range(2)])
+    fr = _freqs([pr == q for q in range(4)])
+    fgr = _freqs([(pg == a) * (pr == b) for a in range(2) for b in range(4)])
+    out = [abs(fg[1] - fg[0]).item(), (g.max(dim=-1).values < 0.8).float().mean().item(), _mean_offdiag_l1(fr),
+           (r.max(dim=-1).values < 0.8).float().mean().item(), _mean_offdiag_l1(fgr)]
+    if probs_age_all is not None:
+        a = _valid(probs_age_all)
+        pa = a.argmax(dim=-1)
+        a0, a1 = (pa == 0).float().mean().item(), (pa == 1).float().mean().item()
+        out += [a0, a1, (a.max(dim=-1).values < 0.8).float().mean().item(), (abs(a0 - 0.75) + abs(a1 - 0.25)) / 2]
+    return tuple(out)

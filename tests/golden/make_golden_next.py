@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Golden vectors for the "next" rows, produced by EXECUTING THE REFERENCE'S OWN STATEMENTS.
+
+    python tests/golden/make_golden_next.py [--ref /root/reference]        (build container only)
+
+* get_evaluate_metrics (E3:1716, E4:1780): the FunctionDef nodes are lifted unmodified with ``ast`` (as in
+  make_golden.py) and run on seeded probability tensors (fp32, bf16, fp16; some rows -1).
+* detector staging: the assignment ``images_np = ...`` inside get_face_app (E1:1317) and the subscript passed to
+  ``face_app.get`` (E1:1326) are located in the syntax tree and their VALUE expressions evaluated with ``images`` /
+  ``image_np`` bound to seeded tensors.  Nothing from the reference is written into this repo.
+"""
+import argparse
+import ast
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+E1 = "exp-1-debias-gender/1-main-debias.py"
+E3 = "exp-3-debias-gender-race/1-main-debias.py"
+E4 = "exp-4-debias-gender-race-age/1-main-debias.py"
+
+
+def find_function(tree, name):
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return node
+    raise KeyError(name)
+
+
+def compile_function(node, ns):
+    mod = ast.Module(body=[node], type_ignores=[])
+    exec(compile(mod, "<reference>", "exec"), ns)
+    return ns[node.name]
+
+
+def staging_expressions(tree):
+    fn = find_function(tree, "get_face_app")
+    assign = next(n for n in ast.walk(fn) if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "images_np")
+    call = next(n for n in ast.walk(fn) if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr == "get"
+                and isinstance(n.func.value, ast.Name) and n.func.value.id == "face_app")
+    to_code = lambda e: compile(ast.Expression(body=e), "<reference>", "eval")
+    return to_code(assign.value), to_code(call.args[0])
+
+
+def probs(gen, n, w, dtype, sharp):
+    p = torch.softmax(torch.randn(n, w, generator=gen) * sharp, -1).to(dtype)
+    return p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    a = ap.parse_args()
+    out = {}
+    # ---- metrics
+    for tag, rel, with_age in (("e3", E3, False), ("e4", E4, True)):
+        tree = ast.parse(open(os.path.join(a.ref, rel)).read())
+        fn = compile_function(find_function(tree, "get_evaluate_metrics"), {"torch": torch, "abs": abs})
+        for di, dtype in enumerate((torch.float32, torch.bfloat16, torch.float16)):
+            gen = torch.Generator().manual_seed(100 + di)
+            n = 257
+            pg, pr, pa = probs(gen, n, 2, dtype, 1.5), probs(gen, n, 4, dtype, 1.5), probs(gen, n, 2, dtype, 1.5)
+            pg[5:9, 0] = 0.796875; pg[5:9, 1] = 1 - 0.796875          # straddle the 0.8 confidence threshold in every dtype
+            pg[9, 0] = 0.7998046875; pg[9, 1] = 0.2001953125
+            pg[10] = 0.5                                               # argmax tie
+            miss = torch.rand(n, generator=gen) < 0.1
+            for t in (pg, pr, pa):
+                t[miss] = -1
+            res = fn(pg, pr, pa) if with_age else fn(pg, pr)
+            key = f"metrics_{tag}_{str(dtype).split('.')[-1]}"
+            out[key + "_pg"], out[key + "_pr"], out[key + "_pa"] = pg.float().numpy(), pr.float().numpy(), pa.float().numpy()
+            out[key + "_out"] = np.array(res, dtype=np.float64)
+    # ---- staging
+    tree = ast.parse(open(os.path.join(a.ref, E1)).read())
+    expr_u8, expr_bgr = staging_expressions(tree)
+    for di, dtype in enumerate((torch.float32, torch.bfloat16, torch.float16)):
+        gen = torch.Generator().manual_seed(200 + di)
+        images = (torch.rand(3, 3, 10, 12, generator=gen) * 2.1 - 1.05).to(dtype)      # a few values outside [-1,1]
+        images[0, :, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.999])
+        images_np = eval(expr_u8, {"np": np, "torch": torch, "images": images})
+        bgr = np.stack([eval(expr_bgr, {"image_np": im}) for im in images_np])
+        key = f"stage_{str(dtype).split('.')[-1]}"
+        out[key + "_in"] = images.float().numpy()
+        out[key + "_out"] = np.ascontiguousarray(bgr)
+    np.savez_compressed(os.path.join(HERE, "nextrows.npz"), **out)
+    print("wrote nextrows.npz:", sorted(out))
+
+
+if __name__ == "__main__":
+    main()
