@@ -88,7 +88,7 @@ compact_kernel(const T* __restrict__ pg, const T* __restrict__ pr, int n_all, in
                int* __restrict__ idx, int* __restrict__ pos, int* __restrict__ status) {
     __shared__ int warp_sums[32];
     __shared__ int base;
-    if (threadIdx.x == 0) base = 0;
+    if (threadIdx.x == 0) { base = 0; status[0] = 0; status[2] = 0; status[3] = 0; }      // first kernel of the call: clears the status words
     __syncthreads();
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int start = 0; start < n_all; start += 1024) {
@@ -157,12 +157,13 @@ __global__ void __launch_bounds__(256)
 cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
                  const int* __restrict__ idx, int N, int K, double* __restrict__ M, float* __restrict__ Mf, int cost_blocks,
                  const T* __restrict__ rg, const T* __restrict__ rr, const T* __restrict__ ra, int S,
-                 int* __restrict__ hist) {
+                 int* __restrict__ hist, int32_t* __restrict__ counts_to_zero) {
     if ((int)blockIdx.x < cost_blocks) {
         int r = blockIdx.x * 256 + threadIdx.x;
         if (r < N) {
             cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
             if (Mf) for (int j = 0; j < K; j++) Mf[(size_t)j * N + r] = (float)M[(size_t)r * K + j];
+            if (counts_to_zero) for (int j = 0; j < K; j++) counts_to_zero[(size_t)r * K + j] = 0;
         }
         return;
     }
@@ -211,7 +212,8 @@ struct SolverSmem {
     unsigned need[KP + 1];
     int path_len;
     int cont[2];               // loop-continue flag, double buffered by iteration parity
-    unsigned whist[2][SOLVER_WARPS][KP / 2];   // price search: per-warp class counts (two 16-bit counts per word), by iteration parity
+    unsigned whist[2][SOLVER_WARPS][KP / 2];   // price search: per-warp class counts (packed), by iteration parity
+    __align__(16) float wprice[SOLVER_WARPS][KP];   // price search: the warp's copy of the K prices of this round
     int status;
 };
 
@@ -464,6 +466,79 @@ __device__ __forceinline__ void price_search(SolverSmem& sm, const float* __rest
     __syncthreads();
 }
 
+// Register-resident variant of the price search for problems with at most RPT rows per thread (N <= RPT * 512, RPT <= 4):
+// the thread's rows of the fp32 cost copy are loaded once and stay in registers for all rounds, the per-thread class
+// histogram uses 8-bit fields (32 lanes x RPT rows <= 128 per class and warp), so four REDUX sums give the warp counts
+// with no unpacking, and the K prices reach the lanes through a per-warp shared-memory row instead of K shuffles.
+template <int KK, int RPT>
+__device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __restrict__ Mf, int N, int dual_iters, float step0) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
+    int my_prev = 0, best_resid = 0x7fffffff;
+    const int my_b = lane < KK ? sm.b[lane] : 0;
+    float x[RPT][KK];
+    bool have[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+        const int i = tid + r * SOLVER_THREADS;
+        have[r] = i < N;
+#pragma unroll
+        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? Mf[l * N + i] : 0.f;
+    }
+    float* wp = sm.wprice[warp];
+    for (int it = 0; it <= dual_iters; it++) {
+        if (lane < KK) wp[lane] = my_price;
+        __syncwarp();
+        float pr[KK];
+#pragma unroll
+        for (int l = 0; l < KK; l += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(wp + l);
+            pr[l] = q.x; pr[l + 1] = q.y; pr[l + 2] = q.z; pr[l + 3] = q.w;
+        }
+        __syncwarp();
+        unsigned long long hlo = 0ull, hhi = 0ull;          // 8-bit count per class: classes 0-7 / 8-15
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            float y[KK]; int idx[KK];
+#pragma unroll
+            for (int l = 0; l < KK; l++) { y[l] = x[r][l] - pr[l]; idx[l] = l; }
+#pragma unroll
+            for (int st = 1; st < KK; st *= 2)
+#pragma unroll
+                for (int l = 0; l < KK; l += 2 * st)
+                    if (y[l + st] < y[l]) { y[l] = y[l + st]; idx[l] = idx[l + st]; }      // strict: the lower class wins ties
+            const unsigned long long one = have[r] ? 1ull : 0ull;
+            if (KK <= 8) hlo += one << (8 * idx[0]);
+            else { hlo += (idx[0] < 8 ? one : 0ull) << (8 * (idx[0] & 7)); hhi += (idx[0] < 8 ? 0ull : one) << (8 * (idx[0] & 7)); }
+        }
+        unsigned acc[4];
+        acc[0] = __reduce_add_sync(0xffffffffu, (unsigned)hlo); acc[1] = __reduce_add_sync(0xffffffffu, (unsigned)(hlo >> 32));
+        if (KK > 8) { acc[2] = __reduce_add_sync(0xffffffffu, (unsigned)hhi); acc[3] = __reduce_add_sync(0xffffffffu, (unsigned)(hhi >> 32)); }
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < KK / 4; w++) sm.whist[it & 1][warp][w] = acc[w];
+        }
+        __syncthreads();
+        int cnt = 0;
+        if (lane < KK) {
+#pragma unroll
+            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][lane >> 2] >> ((lane & 3) * 8)) & 0xFFu);
+        }
+        const int err = lane < KK ? my_b - cnt : 0;
+        const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
+        if (resid < best_resid) { best_resid = resid; my_best = my_price; }
+        if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
+        if (lane < KK) {
+            const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
+            if (sg * my_prev < 0) my_step *= 0.5f; else if (sg * my_prev > 0) my_step *= 1.2f;
+            my_prev = sg;
+            my_price += my_step * (float)sg;                           // too few rows -> cheaper class
+        }
+    }
+    if (warp == 0 && lane < KP) sm.best_pricef[lane] = my_best;
+    __syncthreads();
+}
+
 // One CTA solves one transport problem exactly.
 //
 //  1. price search (all warps):  `dual_iters` rounds of sign-based dual ascent on the K class prices
@@ -536,7 +611,13 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     FG_MARK();
 
     // ---- 1. price search (fp32)
-    if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
+    if (m_in_smem && N <= 2 * SOLVER_THREADS) {
+        if (K == 16) price_search_reg<16, 2>(sm, v.Mf, N, dual_iters, (float)step0);
+        else price_search_reg<8, 2>(sm, v.Mf, N, dual_iters, (float)step0);
+    } else if (m_in_smem && N <= 4 * SOLVER_THREADS) {
+        if (K == 16) price_search_reg<16, 4>(sm, v.Mf, N, dual_iters, (float)step0);
+        else price_search_reg<8, 4>(sm, v.Mf, N, dual_iters, (float)step0);
+    } else if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     else price_search<8>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
     __syncthreads();
@@ -895,20 +976,17 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     if (!workspace || workspace_bytes < fg_ot_workspace_bytes(n_all, K, S)) return FG_ERR_WORKSPACE;
     OtWs w = ot_carve(workspace, n_all > 0 ? n_all : 1, K, S);
     cudaStream_t st = fg_stream(stream);
-    cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
-    if (n_all == 0) return FG_OK;
+    if (n_all == 0) return cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st) == cudaSuccess ? FG_OK : FG_ERR_INVALID_ARG;
+    // the status words are cleared by compact_kernel and the plan counts by cost_hist_kernel (no memset launches)
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status));
     FG_LAUNCH_CHECK();
     if (n_valid == 0) return FG_OK;
     if (!counts || (S > 0 && (!rand_gender || !rand_race || (K == 16 && !rand_age)))) return FG_ERR_INVALID_ARG;
-    e = cudaMemsetAsync(counts, 0, (size_t)n_valid * K * sizeof(int32_t), st);
-    if (e != cudaSuccess) return (int)e;
     int cost_blocks = (n_valid + 255) / 256;
     FG_DISPATCH_DTYPE(dtype, T,
         cost_hist_kernel<T><<<cost_blocks + S, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age,
-            w.idx, n_valid, K, w.M, w.Mf, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist));
+            w.idx, n_valid, K, w.M, w.Mf, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist, counts));
     FG_LAUNCH_CHECK();
     if (S == 0) return FG_OK;
     // Every draw runs the whole price search from zero prices in its own CTA.  (A serial "base" solve of the expected
@@ -974,7 +1052,7 @@ extern "C" int fg_ot_cost_matrix(const void* probs_gender, const void* probs_rac
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status);
         if (n_valid > 0) cost_hist_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
-            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr));
+            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

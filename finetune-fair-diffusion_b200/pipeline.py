@@ -201,8 +201,10 @@ class GuidancePath:
             nv = num_valid if num_valid is not None else int(ind_all.sum().item())
             ws = ops.OtWorkspace(n_all, K, cfg.num_samples_per_device, images.device)
             if rand_tensors is None and nv > 0:
-                rand_tensors = tuple(torch.rand([cfg.num_samples_per_device, nv], dtype=images.dtype, device=images.device)
-                                     for _ in widths)
+                # one generator launch for all attributes (api.generate_dynamic_targets_* keeps the reference's
+                # one-torch.rand-per-attribute order for seeded parity)
+                rand_tensors = tuple(torch.rand([len(widths), cfg.num_samples_per_device, nv], dtype=images.dtype,
+                                                device=images.device).unbind(0))
             pa = probs_all[2] if len(widths) == 3 else None
             counts = ops.ot_plan_counts(probs_all[0], probs_all[1], pa, rand_tensors or (), nv, ws)
             if nv > 0:
