@@ -61,8 +61,11 @@ struct OtWs {
     int* hist;          // [S, KP]
     double* prices;     // [KP]
     uint8_t* sigma0;    // [n_valid]
+    uint16_t* members;  // [S][K][n_valid] member lists of the solver's mode 2 (empty otherwise)
     size_t total;
 };
+
+static size_t solver_members_bytes(int N, int K, int S);
 
 static OtWs ot_carve(void* base, int n_all, int K, int S) {
     OtWs w;
@@ -76,6 +79,7 @@ static OtWs ot_carve(void* base, int n_all, int K, int S) {
     w.hist = (int*)take((size_t)(S > 0 ? S : 1) * KP * sizeof(int));
     w.prices = (double*)take(KP * sizeof(double));
     w.sigma0 = (uint8_t*)take((size_t)n_all);
+    w.members = (uint16_t*)take(solver_members_bytes(n_all, K, S));
     w.total = off;
     return w;
 }
@@ -554,19 +558,27 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
 //
 // demand: from `demand_by_value` when hist == nullptr, else hist[blockIdx.x].  prices_in == nullptr starts
 // from zero prices (the greedy assignment).  prices_out receives feasible optimal prices of the final state.
+//
+// MODE selects where the two large views live (solver_mode): 0 = member lists and the fp32 cost copy in shared memory
+// (N*K up to ~36k), 1 = member lists in shared memory, the fp32 copy read from global memory (it is written once by
+// the cost kernel and stays in L2), 2 = both in global memory (`members_global` holds [gridDim.x][K][N] entries) --
+// the shape of the 8-GPU weak-scaling batch (8192 rows x 16 classes).
+template <int MODE>
 __global__ void __launch_bounds__(SOLVER_THREADS)
 ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ Mf_global, int N, int K,
                 const double* __restrict__ prices_in, double* __restrict__ prices_out, int dual_iters, double step0,
                 Demand demand_by_value, const int* __restrict__ hist,
                 int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
-                int* __restrict__ status, int status_slot, int m_in_smem) {
+                int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
     v.sigma = dyn_smem + SOLVER_CTRL;
     v.pos = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_pos(N));
-    v.members = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_members(N));
-    v.Mf = reinterpret_cast<float*>(dyn_smem + solver_off_M(N, K));
+    if (MODE == 2) v.members = members_global + (size_t)blockIdx.x * K * N;
+    else v.members = reinterpret_cast<uint16_t*>(dyn_smem + solver_off_members(N));
+    if (MODE == 0) v.Mf = reinterpret_cast<float*>(dyn_smem + solver_off_M(N, K));
+    else v.Mf = const_cast<float*>(Mf_global);
     uint8_t* sigma = v.sigma;
     const int tid = threadIdx.x, warp = tid >> 5;
     // FP64 issues at a small fraction of the FP32 rate on this part, so the price search (a heuristic: any
@@ -581,7 +593,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
 #endif
     FG_MARK();
     // class-major copy: lane i reads Mf[l*N + i], conflict-free (a row-major row per lane is a 16-way conflict)
-    if (m_in_smem) {
+    if (MODE == 0 && m_in_smem) {
         if (Mf_global && (N * K) % 4 == 0) {       // precomputed by the cost kernel: straight 16-byte copies
             const float4* src = reinterpret_cast<const float4*>(Mf_global);
             float4* dst = reinterpret_cast<float4*>(v.Mf);
@@ -611,10 +623,10 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     FG_MARK();
 
     // ---- 1. price search (fp32)
-    if (m_in_smem && N <= 2 * SOLVER_THREADS) {
+    if (MODE == 0 && m_in_smem && N <= 2 * SOLVER_THREADS) {
         if (K == 16) price_search_reg<16, 2>(sm, v.Mf, N, dual_iters, (float)step0);
         else price_search_reg<8, 2>(sm, v.Mf, N, dual_iters, (float)step0);
-    } else if (m_in_smem && N <= 4 * SOLVER_THREADS) {
+    } else if (MODE == 0 && m_in_smem && N <= 4 * SOLVER_THREADS) {
         if (K == 16) price_search_reg<16, 4>(sm, v.Mf, N, dual_iters, (float)step0);
         else price_search_reg<8, 4>(sm, v.Mf, N, dual_iters, (float)step0);
     } else if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
@@ -904,24 +916,47 @@ rank_split_kernel(const T* __restrict__ probs, int n_all, double ratio, float th
     if (unc) unc[i] = from_f32<T>(uf);
 }
 
-// shared memory of one solver CTA: control block, assignment bytes, list positions, member lists
-// (+ the cost matrix when it fits)
-static bool solver_m_fits(int N, int K) {
-    return solver_off_M(N, K) + (size_t)N * K * sizeof(float) <= 220 * 1024;
+// shared memory of one solver CTA: control block, assignment bytes, list positions (+ member lists, + the fp32 cost
+// matrix, while they fit); see ot_solve_kernel for the three modes
+static int solver_mode(int N, int K) {
+    if (solver_off_M(N, K) + (size_t)N * K * sizeof(float) <= 220 * 1024) return 0;
+    if (solver_off_M(N, K) <= 220 * 1024) return 1;
+    return 2;
 }
 static int solver_smem_bytes(int N, int K) {
-    size_t b = solver_off_M(N, K);
-    if (solver_m_fits(N, K)) b += (size_t)N * K * sizeof(float);
-    return (int)b;
+    const int mode = solver_mode(N, K);
+    if (mode == 0) return (int)(solver_off_M(N, K) + (size_t)N * K * sizeof(float));
+    if (mode == 1) return (int)solver_off_M(N, K);
+    return (int)solver_off_members(N);
+}
+static size_t solver_members_bytes(int N, int K, int S) {      // global member lists of mode 2
+    return solver_mode(N, K) == 2 ? (size_t)(S > 0 ? S : 1) * K * N * sizeof(uint16_t) : 0;
 }
 
 static int solver_prepare(int N, int K) {
     if (N > 65535) return FG_ERR_LIMIT;           // member lists index rows with 16 bits
     if (solver_smem_bytes(N, K) > 227 * 1024) return FG_ERR_LIMIT;
-    // the coarse levels may need more than the final one (their cost matrix fits): opt in to the maximum
-    cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ot_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ot_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ot_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e == cudaSuccess ? FG_OK : (int)e;
 }
+
+// fp32 class-major copy of a row-major fp64 cost matrix (fg_ot_solve_single in modes 1 / 2; the plan path gets it from
+// cost_hist_kernel)
+__global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict__ Mf, int N, int K) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < N * K) { const int i = e / K, l = e - i * K; Mf[(size_t)l * N + i] = (float)M[e]; }
+}
+
+#define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, ...)                                                                      \
+    do {                                                                                                              \
+        const int mode_ = solver_mode(N_, K_);                                                                        \
+        const int smem_ = solver_smem_bytes(N_, K_);                                                                  \
+        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                        \
+        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                   \
+        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                                   \
+    } while (0)
 
 // expected demand for n rows: largest-remainder rounding of n*q
 static void expected_demand(int n, int K, Demand* d) {
@@ -953,9 +988,8 @@ static int launch_base(const double* M, const float* Mf, int N, int K, OtWs& w, 
     int rc = solver_prepare(N, K);
     if (rc) return rc;
     Demand d; expected_demand(N, K, &d);
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(N, K), st>>>(M, Mf, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0,
-                                                                        d, nullptr, nullptr, nullptr, w.status, 2,
-                                                                        solver_m_fits(N, K) ? 1 : 0);
+    FG_SOLVE_LAUNCH(N, K, 1, st, M, Mf, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0, d, nullptr, nullptr, nullptr, w.status, 2,
+                    1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -995,9 +1029,8 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int rc = solver_prepare(n_valid, K);
     if (rc) return rc;
     Demand none = {};
-    ot_solve_kernel<<<S, SOLVER_THREADS, solver_smem_bytes(n_valid, K), st>>>(w.M, w.Mf, n_valid, K, nullptr, nullptr, DRAW_DUAL_ITERS,
-                                                                             DRAW_STEP0, none, w.hist, nullptr, counts, w.status, 3,
-                                                                             solver_m_fits(n_valid, K) ? 1 : 0);
+    FG_SOLVE_LAUNCH(n_valid, K, S, st, w.M, w.Mf, n_valid, K, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, w.hist, nullptr, counts,
+                    w.status, 3, 1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -1031,11 +1064,15 @@ extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* 
     cudaStream_t st = fg_stream(stream);
     cudaError_t e = cudaMemsetAsync(w.status, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    int rc = launch_base(M, nullptr, n, K, w, st);
+    const float* Mf = nullptr;                     // mode 0 builds its shared-memory copy from M
+    if (solver_mode(n, K) != 0) {
+        mf_from_m_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(M, w.Mf, n, K);
+        Mf = w.Mf;
+    }
+    int rc = launch_base(M, Mf, n, K, w, st);
     if (rc) return rc;
-    ot_solve_kernel<<<1, SOLVER_THREADS, solver_smem_bytes(n, K), st>>>(M, nullptr, n, K, w.prices, nullptr, WARM_DUAL_ITERS, WARM_STEP0,
-                                                                         d, nullptr, assign, nullptr, w.status, 3,
-                                                                         solver_m_fits(n, K) ? 1 : 0);
+    FG_SOLVE_LAUNCH(n, K, 1, st, M, Mf, n, K, w.prices, nullptr, WARM_DUAL_ITERS, WARM_STEP0, d, nullptr, assign, nullptr, w.status, 3,
+                    1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

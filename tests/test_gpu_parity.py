@@ -407,7 +407,8 @@ def _problem(seed, N, K):
     return pg, pr, pa, oemd.cost_matrix_c(pg, pr, pa), rng
 
 
-@pytest.mark.parametrize("N,K", [(1, 8), (5, 8), (64, 16), (300, 8), (1024, 16), (4096, 8)])
+# (3000, 16) and (8192, 16) leave the all-shared-memory mode of the solver (cost copy / member lists in global memory)
+@pytest.mark.parametrize("N,K", [(1, 8), (5, 8), (64, 16), (300, 8), (1024, 16), (4096, 8), (3000, 16), (8192, 16), (13000, 8)])
 def test_ot_cost_and_single_solve_vs_oracle(fg, N, K):
     from oracle import emd as oemd
     pg, pr, pa, M, rng = _problem(N * 7 + K, N, K)
@@ -453,7 +454,7 @@ def test_assign_mc_golden(fg, tag):
             assert np.array_equal(ts2[a].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("N,kind,S", [(512, "e3", 100), (1024, "e4", 100), (4096, "e3", 16)])
+@pytest.mark.parametrize("N,kind,S", [(512, "e3", 100), (1024, "e4", 100), (4096, "e3", 16), (4096, "e4", 12), (8192, "e4", 10)])
 def test_assign_mc_large_vs_oracle(fg, N, kind, S):
     from oracle import assign as oassign
     n_attr = 2 if kind == "e3" else 3
