@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C5|C2|C3|C4|C1]
 
 Workload (default C5 = BASELINE.json configs[4], the one the 1/2/4/8-GPU sweep is quoted on):
-1024 synthetic 512x512 bf16 images in total (sharded over the ranks: strong scaling), 1 face box
-each (5 % without a face), gender+race+age heads (K = 16 assignment classes, 75/25 age target),
+1024 synthetic 512x512 bf16 images PER GPU (weak scaling, the reference's own data parallelism: every
+rank generates its own `train_images_per_prompt_GPU` images and the balanced assignment runs over the
+gathered N = 1024 * gpus rows, E3:1978-2016; `--scaling strong` shards 1024 images in total instead), 1 face
+box each (5 % without a face), gender+race+age heads (K = 16 assignment classes, 75/25 age target),
 100 Monte-Carlo draws per rank, threshold 0.2, full backward into the image gradient.  A "step" is one
 pass of pipeline.GuidancePath.step over that batch.  The classifier backbone (torchvision MobileNetV3
 `features`, cuDNN) and CLIP/DINO are not part of the path: their outputs /
@@ -170,11 +172,16 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96, help="images per step of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's image count per GPU (default); strong: that count in total, sharded")
     a = ap.parse_args()
-    kind, n_global, dtype_name, max_faces, desc = WORKLOADS[a.workload]
+    kind, n_workload, dtype_name, max_faces, desc = WORKLOADS[a.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_ranks = world
+    n_local = n_workload if a.scaling == "weak" else n_workload // n_ranks
+    n_global = n_local * n_ranks
 
     if a.impl == "reference":
         if rank != 0:
@@ -183,8 +190,8 @@ def main():
         r = cpu_reference_run(kind, a.cpu_sample, steps, warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": a.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{a.workload}: {desc}", "kind": kind, "global_batch": n_global,
+                "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{a.workload}: {desc}", "kind": kind, "global_batch": n_global, "images_per_gpu": n_local,
                            "sample_images_per_step": a.cpu_sample},
                 "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -204,7 +211,6 @@ def main():
     assert world == a.gpus or world == 1, (world, a.gpus)
     dtype = getattr(torch, dtype_name)
     esize = torch.empty((), dtype=dtype).element_size()
-    n_local = n_global // world
     cfg = pipeline.GuidanceConfig(kind=kind)
     head = pipeline.make_head_weights(cfg, dtype, dev)
     batch = pipeline.synth_batch_device(n_local, cfg, dtype, dev, seed=5991 + rank, max_faces=max_faces)
@@ -332,7 +338,7 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         cpu = cpu_reference_run(kind, a.cpu_sample, 2, 1)
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": {"bfloat16": "bf16", "float32": "f32", "float16": "f16"}[dtype_name], "data": "synthetic",
             "config": {"workload": f"{a.workload}: {desc}", "kind": kind, "global_batch": n_global, "images_per_gpu": n_local,
                        "image": "3x512x512", "chip": "3x224x224", "mc_draws_per_rank": cfg.num_samples_per_device,
