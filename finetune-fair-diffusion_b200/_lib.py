@@ -46,6 +46,9 @@ SIGNATURES = {
     "fg_ot_cost_matrix": (_i, [_p, _p, _p, _i, _i, _p, _p, _z, _i, _p]),
     "fg_stage_detector_input": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
     "fg_bias_metrics": (_i, [_p, _p, _p, _i, _p, _i, _p]),
+    "fg_race_workspace_bytes": (_z, [_i, _i]),
+    "fg_assign_race_enumerated": (_i, [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p, _z, _i, _p]),
+    "fg_race_cost_matrix": (_i, [_p, _i, _i, _p, _p, _z, _i, _p]),
 }
 
 _lib = None
@@ -87,6 +90,7 @@ KERNELS_PER_CALL = {
     "fg_region_scale": 1, "fg_head_fwd": 2, "fg_head_bwd": 2, "fg_head_attributes": 1, "fg_fair_ce_fwd": 1,
     "fg_fair_ce_bwd": 1, "fg_fair_loss_fused": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
     "fg_ot_solve_single": 2, "fg_ot_cost_matrix": 2, "fg_stage_detector_input": 1, "fg_bias_metrics": 1,
+    "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2,
 }
 
 

@@ -9,7 +9,11 @@ kernels through the C ABI (include/fairguide.h); there is no CPU or eager-PyTorc
 E1 = exp-1-debias-gender/1-main-debias.py, E3 = exp-3-debias-gender-race/1-main-debias.py,
 E4 = exp-4-debias-gender-race-age/1-main-debias.py.
 """
+import functools
+import math
 import types
+
+import numpy as np
 
 import torch
 
@@ -222,6 +226,51 @@ def generate_dynamic_targets_gender_race_age(probs_gender, probs_race, probs_age
     """E4:1477-1615 -> (t_g, u_g, t_r, u_r, t_a, u_a) or targets only."""
     return _mc_targets((probs_gender, probs_race, probs_age), w_uncertainty, num_samples_per_device, rand_tensors,
                        num_valid, uncertainty_threshold, group)
+
+
+@functools.lru_cache(maxsize=64)
+def race_compositions(N, mass=0.95):
+    """Host side of E6:1438-1459 (host code in the reference as well; depends only on N): every composition
+    (n1,n2,n3,n4) of N with its multinomial coefficient, normalised to sum 1, sorted by decreasing weight with the same
+    numpy calls as the reference (so equal weights order the same way under the same numpy), cut after the cumulative
+    weight first exceeds ``mass``.  -> (combs int64 [S,4], weights float64 [S])."""
+    combs, coefs = [], []
+    for n1 in range(N + 1):
+        c1 = math.comb(N, n1)
+        for n2 in range(N - n1 + 1):
+            c12 = c1 * math.comb(N - n1, n2)
+            for n3 in range(N - n1 - n2 + 1):
+                combs.append([n1, n2, n3, N - n1 - n2 - n3])
+                coefs.append(c12 * math.comb(N - n1 - n2, n3))
+    combs, w = np.array(combs), np.array(coefs)
+    w = w / np.linalg.norm(w, ord=1)
+    order = np.flip(w.argsort())
+    acc, keep = 0, len(order)
+    for k, j in enumerate(order):
+        acc += w[j]
+        if acc > mass:
+            keep = k + 1
+            break
+    order = order[:keep]
+    return combs[order].astype(np.int64), w[order].astype(np.float64)
+
+
+def generate_dynamic_targets_race(probs, w_uncertainty=False, *, num_valid=None, uncertainty_threshold=None):
+    """exp-6-debias-race/1-main-debias.py:1413-1482 -> targets_all or (targets_all, uncertainty_all).
+    ``num_valid`` = number of rows with a face if the caller knows it (the reference reads it from the device as well,
+    E6:1424); ``uncertainty_threshold`` fuses the caller's ``targets[uncertainty > thr] = -1``."""
+    if num_valid is None:
+        num_valid = int((probs != -1).all(dim=-1).sum().item())
+    demands = weights = None
+    if num_valid > 0:
+        combs, w = race_compositions(num_valid)
+        d16 = np.zeros((combs.shape[0], 16), dtype=np.int32)
+        d16[:, :4] = combs
+        demands = torch.from_numpy(d16).to(probs.device)
+        weights = torch.from_numpy(w).to(probs.device)
+    thr = -1.0 if uncertainty_threshold is None else float(uncertainty_threshold)
+    targets, unc, _ = ops.assign_race_enumerated(probs, num_valid, demands, weights, thr, w_uncertainty)
+    return (targets, unc) if w_uncertainty else targets
 
 
 def threshold_and_slice(targets_all, uncertainty_all, uncertainty_threshold, n_local, local_process_index):

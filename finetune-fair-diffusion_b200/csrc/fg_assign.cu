@@ -99,7 +99,7 @@ compact_kernel(const T* __restrict__ pg, const T* __restrict__ pr, int n_all, in
         int i = start + threadIdx.x;
         bool v = false;
         if (i < n_all) {
-            v = to_f32(pg[2 * i]) != -1.f && to_f32(pg[2 * i + 1]) != -1.f;
+            v = !pg || (to_f32(pg[2 * i]) != -1.f && to_f32(pg[2 * i + 1]) != -1.f);      // race-only variant (E6): pg == nullptr
             for (int q = 0; q < 4; q++) v = v && to_f32(pr[4 * i + q]) != -1.f;
         }
         unsigned m = __ballot_sync(0xffffffffu, v);
@@ -722,7 +722,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     FG_MARK();
 
     // outputs
-    if (assign_out) for (int i = tid; i < N; i += SOLVER_THREADS) assign_out[i] = sigma[i];
+    if (assign_out) for (int i = tid; i < N; i += SOLVER_THREADS) assign_out[(size_t)blockIdx.x * N + i] = sigma[i];
     if (counts) for (int i = tid; i < N; i += SOLVER_THREADS) atomicAdd(&counts[(size_t)i * K + sigma[i]], 1);
     if (prices_out) {
         // feasible prices for the final state: v_l = min(0, min_k v_k + w[k][l]) (difference constraints)
@@ -994,6 +994,73 @@ static int launch_base(const double* M, const float* Mf, int N, int K, OtWs& w, 
     return FG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// E6 (race only): generate_dynamic_targets_race, exp-6-debias-race/1-main-debias.py:1413-1482.
+// The demands are the enumerated compositions (n1..n4) of N that cover 95 % of the multinomial mass (host side,
+// api.py); each is an exact transport problem on the SAME solver (the 4 classes are padded to 8 with unreachable
+// ones: cost RACE_PAD, demand 0), and the plans are accumulated with their weights in the reference's order.
+constexpr double RACE_PAD = 1.0e3;
+
+// cost E6:1461 = ot.dist(probs, eye(4), metric="euclidean") as POT 0.9.3 evaluates it on the numpy backend
+// (ot/utils.py euclidean_distances): c = -2 * X.Y^T ; c += |x|^2 ; c += |y|^2 ; sqrt(max(c, 0)), where |x|^2 is the
+// fp32 einsum of the fp32 probabilities (numpy reduces the 4 products pairwise) and X.Y^T is exact in fp64.
+template <typename T>
+__global__ void __launch_bounds__(256)
+race_cost_kernel(const T* __restrict__ pr, const int* __restrict__ idx, int N, double* __restrict__ M, float* __restrict__ Mf) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= N) return;
+    const int i = idx[r];
+    float x[4];
+    for (int q = 0; q < 4; q++) x[q] = to_f32(pr[4 * i + q]);
+    const float a2 = __fadd_rn(__fadd_rn(__fmul_rn(x[0], x[0]), __fmul_rn(x[1], x[1])), __fadd_rn(__fmul_rn(x[2], x[2]), __fmul_rn(x[3], x[3])));
+    for (int j = 0; j < 8; j++) {
+        double c = RACE_PAD;
+        if (j < 4) {
+            c = __dadd_rn(__dmul_rn(-2.0, (double)x[j]), (double)a2);
+            c = __dadd_rn(c, 1.0);
+            c = __dsqrt_rn(c > 0.0 ? c : 0.0);
+        }
+        M[(size_t)r * 8 + j] = c;
+        Mf[(size_t)j * N + r] = (float)c;
+    }
+}
+
+// target_probs += T * prob over the compositions in order (E6:1463-1466), row L1 normalisation (E6:1467), argmax and
+// 1 - max (E6:1469-1472), scatter to all rows (E6:1474-1479), optional thresholding in the probs dtype (E6 call site)
+template <typename T>
+__global__ void race_accumulate_kernel(const int32_t* __restrict__ sigma, const double* __restrict__ weights, int S, int N,
+                                       const int* __restrict__ pos, int n_all, float threshold,
+                                       long long* __restrict__ targets, T* __restrict__ unc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    const int p = pos[i];
+    if (p < 0) { targets[i] = -1; if (unc) unc[i] = from_f32<T>(-1.f); return; }
+    double tp[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int s = 0; s < S; s++) {
+        const int c = sigma[(size_t)s * N + p];
+        const double w = weights[s];
+#pragma unroll
+        for (int q = 0; q < 4; q++) tp[q] = __dadd_rn(tp[q], c == q ? w : 0.0);      // T is 0/1: the other entries add +0.0
+    }
+    const double nrm = __dadd_rn(__dadd_rn(__dadd_rn(fabs(tp[0]), fabs(tp[1])), fabs(tp[2])), fabs(tp[3]));
+    int best = 0; double bv = __ddiv_rn(tp[0], nrm);
+    for (int q = 1; q < 4; q++) { const double v = __ddiv_rn(tp[q], nrm); if (v > bv) { bv = v; best = q; } }
+    const float uf = round_to<T>((float)__dsub_rn(1.0, bv));
+    long long t = best;
+    if (threshold >= 0.f && uf > round_to<T>(threshold)) t = -1;
+    targets[i] = t;
+    if (unc) unc[i] = from_f32<T>(uf);
+}
+
+struct RaceWs { OtWs ot; int32_t* sigma; size_t total; };
+static RaceWs race_carve(void* base, int n_all, int S) {
+    RaceWs w;
+    w.ot = ot_carve(base, n_all, 8, S);
+    w.sigma = (int32_t*)((char*)base + w.ot.total);
+    w.total = w.ot.total + fg_align_up((size_t)(S > 0 ? S : 1) * n_all * sizeof(int32_t), 256);
+    return w;
+}
+
 }  // namespace
 
 extern "C" size_t fg_ot_workspace_bytes(int n_all, int K, int S) {
@@ -1112,5 +1179,59 @@ extern "C" int fg_assign_rank_binom(const void* probs, int n_all, double target_
         rank_split_kernel<T><<<(n_all + 255) / 256, 256, 0, st>>>((const T*)probs, n_all, target_ratio, threshold, w.nvalid,
                                                                   w.cdf0, w.cdf1, (long long*)targets, (T*)uncertainty));
     FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" size_t fg_race_workspace_bytes(int n_all, int S) {
+    if (n_all < 0 || S < 0) return 0;
+    return race_carve(nullptr, n_all > 0 ? n_all : 1, S).total;
+}
+
+extern "C" int fg_assign_race_enumerated(const void* probs_race, int n_all, int n_valid, const int32_t* demands,
+                                         const double* weights, int S, float threshold, int64_t* targets, void* uncertainty,
+                                         void* workspace, size_t workspace_bytes, int dtype, void* stream) {
+    if (n_all < 0 || n_valid < 0 || n_valid > n_all || S < 0) return FG_ERR_INVALID_ARG;
+    if (n_all == 0) return FG_OK;
+    if (!probs_race || !targets || (n_valid > 0 && (S == 0 || !demands || !weights))) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_race_workspace_bytes(n_all, S)) return FG_ERR_WORKSPACE;
+    RaceWs w = race_carve(workspace, n_all, S);
+    cudaStream_t st = fg_stream(stream);
+    FG_DISPATCH_DTYPE(dtype, T,
+        compact_kernel<T><<<1, 1024, 0, st>>>((const T*)nullptr, (const T*)probs_race, n_all, n_valid, w.ot.idx, w.ot.pos, w.ot.status));
+    FG_LAUNCH_CHECK();
+    if (n_valid > 0) {
+        FG_DISPATCH_DTYPE(dtype, T,
+            race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf));
+        FG_LAUNCH_CHECK();
+        int rc = solver_prepare(n_valid, 8);
+        if (rc) return rc;
+        Demand none = {};
+        FG_SOLVE_LAUNCH(n_valid, 8, S, st, w.ot.M, w.ot.Mf, n_valid, 8, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, demands, w.sigma,
+                        nullptr, w.ot.status, 3, 1, w.ot.members);
+        FG_LAUNCH_CHECK();
+    }
+    FG_DISPATCH_DTYPE(dtype, T,
+        race_accumulate_kernel<T><<<(n_all + 127) / 128, 128, 0, st>>>(w.sigma, weights, S, n_valid, w.ot.pos, n_all, threshold,
+                                                                     (long long*)targets, (T*)uncertainty));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+/* Test hook: the E6 cost matrix, M [n_valid, 4] float64 in compacted row order. */
+extern "C" int fg_race_cost_matrix(const void* probs_race, int n_all, int n_valid, double* M4, void* workspace,
+                                   size_t workspace_bytes, int dtype, void* stream) {
+    if (n_all <= 0 || n_valid < 0 || n_valid > n_all || !probs_race || !M4) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_race_workspace_bytes(n_all, 0)) return FG_ERR_WORKSPACE;
+    RaceWs w = race_carve(workspace, n_all, 0);
+    cudaStream_t st = fg_stream(stream);
+    FG_DISPATCH_DTYPE(dtype, T,
+        compact_kernel<T><<<1, 1024, 0, st>>>((const T*)nullptr, (const T*)probs_race, n_all, n_valid, w.ot.idx, w.ot.pos, w.ot.status);
+        if (n_valid > 0) race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf));
+    FG_LAUNCH_CHECK();
+    if (n_valid > 0) {
+        cudaError_t e = cudaMemcpy2DAsync(M4, 4 * sizeof(double), w.ot.M, 8 * sizeof(double), 4 * sizeof(double), n_valid,
+                                          cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     return FG_OK;
 }

@@ -295,6 +295,36 @@ def ot_targets(counts, probs_gender, probs_race, n_valid, ws, threshold=-1.0, w_
     return ts[:A], us[:A]
 
 
+def assign_race_enumerated(probs_race, n_valid, demands, weights, threshold=-1.0, w_uncertainty=True):
+    """E6:1413-1482 on the device: exact plan per enumerated composition, weighted accumulation in the given order.
+    demands int32 [S,16] (classes 4..15 zero), weights float64 [S] -> (targets int64 [n_all], uncertainty or None);
+    also returns the workspace (status words)."""
+    _cuda(probs_race, demands, weights)
+    pr = probs_race.contiguous()
+    n_all, dev = pr.shape[0], pr.device
+    S = int(demands.shape[0]) if n_valid > 0 else 0
+    assert n_valid == 0 or (demands.dtype == torch.int32 and tuple(demands.shape) == (S, 16) and weights.dtype == torch.float64)
+    nbytes = _lib.lib().fg_race_workspace_bytes(n_all, S)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    targets = torch.empty((n_all,), dtype=torch.int64, device=dev)
+    unc = torch.empty((n_all,), dtype=pr.dtype, device=dev) if w_uncertainty else None
+    check(_lib.lib().fg_assign_race_enumerated(_p(pr), n_all, n_valid, _p(demands.contiguous()) if S else None,
+                                               _p(weights.contiguous()) if S else None, S, float(threshold), _p(targets), _p(unc),
+                                               _p(ws), nbytes, _dt(pr), _stream()), "fg_assign_race_enumerated")
+    return targets, unc, ws
+
+
+def race_cost_matrix(probs_race, n_valid):
+    """Test hook: the E6 cost matrix [n_valid,4] float64."""
+    _cuda(probs_race)
+    pr = probs_race.contiguous()
+    nbytes = _lib.lib().fg_race_workspace_bytes(pr.shape[0], 0)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=pr.device)
+    M = torch.empty((n_valid, 4), dtype=torch.float64, device=pr.device)
+    check(_lib.lib().fg_race_cost_matrix(_p(pr), pr.shape[0], n_valid, _p(M), _p(ws), nbytes, _dt(pr), _stream()), "fg_race_cost_matrix")
+    return M
+
+
 def ot_solve_single(M, b):
     """Test hook: exact assignment int32 [n] of the rows of M [n,K] float64 to classes with sizes b."""
     _cuda(M)

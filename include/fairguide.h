@@ -201,6 +201,23 @@ int fg_stage_detector_input(const void* images, int n, int C, int H, int W, uint
 int fg_bias_metrics(const void* probs_gender, const void* probs_race, const void* probs_age, int n, double* out,
                     int dtype, void* stream);
 
+/* f3: generate_dynamic_targets_race (exp-6-debias-race/1-main-debias.py:1413-1482), the enumerated-composition
+ * assignment of the race-only experiment.  The caller enumerates the compositions (n1..n4) of N = n_valid, weights them
+ * with the normalised multinomial coefficients, sorts by weight and keeps the 95 % head (E6:1438-1459; host code in
+ * the reference as well): demands [S,16] int32 (classes 4..15 zero), weights [S] float64, both on the DEVICE.
+ * Per composition the exact transport problem ot.emd(ones, b, M) with M = ot.dist(probs, eye(4), "euclidean")
+ * (E6:1461-1464) is solved by the solver of fg_ot_plan_counts; the plans are accumulated with their weights in
+ * the given order in fp64, rows L1-normalised, argmax / 1 - max taken (E6:1465-1472) and scattered to
+ * targets [n_all] int64 / uncertainty [n_all] dtype (NULL to skip), -1 for rows without a face.  threshold >= 0
+ * applies targets[uncertainty > threshold] = -1. */
+size_t fg_race_workspace_bytes(int n_all, int S);
+int fg_assign_race_enumerated(const void* probs_race, int n_all, int n_valid, const int32_t* demands,
+                              const double* weights, int S, float threshold, int64_t* targets, void* uncertainty,
+                              void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* Test hook: the E6 cost matrix, M4 [n_valid,4] float64, rows in compacted order. */
+int fg_race_cost_matrix(const void* probs_race, int n_all, int n_valid, double* M4, void* workspace,
+                        size_t workspace_bytes, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,3 +228,65 @@ def threshold_and_slice(targets_all, uncertainty_all, threshold, n_local, rank):
     t = targets_all.clone()
     t[uncertainty_all > threshold] = -1
     return t[n_local * rank:n_local * (rank + 1)], t
+
+
+# ----------------------------------------------------------------------------- E6 (race only)
+def pot_dist_euclidean(x1, x2):
+    """``ot.dist(x1, x2, metric="euclidean")`` as POT 0.9.3 (environment.yml:172; not installed here) evaluates it on
+    the numpy backend -- ot/utils.py ``euclidean_distances(X, Y, squared=False)``: squared norms by einsum in the
+    inputs' own dtypes, the cross term ``-2 * X.Y^T``, both norms added in place, clamp at 0, square root.
+    Call site: exp-6-debias-race/1-main-debias.py:1461."""
+    a2 = np.einsum("ij,ij->i", x1, x1)
+    b2 = np.einsum("ij,ij->i", x2, x2)
+    c = -2 * np.dot(x1, x2.T)
+    c += a2[:, None]
+    c += b2[None, :]
+    c = np.maximum(c, 0)
+    return np.sqrt(c)
+
+
+def race_compositions(N):
+    """E6:1438-1459: all compositions of N into 4 parts, multinomial weights, 95 % head (statement by statement)."""
+    all_combs, all_probs = [], []
+    for n1 in range(N + 1):
+        for n2 in range(N - n1 + 1):
+            for n3 in range(N - n1 - n2 + 1):
+                n4 = N - n1 - n2 - n3
+                all_combs.append([n1, n2, n3, n4])
+                all_probs.append(math.comb(N, n1) * math.comb(N - n1, n2) * math.comb(N - n1 - n2, n3))
+    all_combs = np.array(all_combs)
+    all_probs = np.array(all_probs)
+    all_probs = all_probs / np.linalg.norm(all_probs, ord=1)
+    idxs_sorted = np.flip(all_probs.argsort())
+    prob_accumulate = 0
+    for i_idx, idx in enumerate(idxs_sorted):
+        prob_accumulate += all_probs[idx]
+        if prob_accumulate > 0.95:
+            break
+    return all_combs[idxs_sorted[:i_idx + 1]], all_probs[idxs_sorted[:i_idx + 1]]
+
+
+@torch.no_grad()
+def generate_dynamic_targets_race(probs, w_uncertainty=False, emd=None):
+    """exp-6-debias-race/1-main-debias.py:1413-1482 with ``ot.dist`` / ``ot.emd`` restated (pot_dist_euclidean, oracle/emd.py)."""
+    solver = emd or _emd.emd_c
+    idxs_2_rank = (probs != -1).all(dim=-1)
+    probs_2_rank = probs[idxs_2_rank]
+    N = probs_2_rank.shape[0]
+    targets_all = torch.ones([probs.shape[0]], dtype=torch.long, device=probs.device) * (-1)
+    uncertainty_all = torch.ones([probs.shape[0]], dtype=probs.dtype, device=probs.device) * (-1)
+    if N > 0:        # (the reference divides 0/0 for N = 0 and scatters nothing)
+        a = np.ones([N])
+        target_points = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        all_combs, all_probs = race_compositions(N)
+        M = pot_dist_euclidean(np.array(probs_2_rank.cpu()), target_points)
+        target_probs = np.zeros([N, 4])
+        for b, prob in itertools.zip_longest(all_combs, all_probs):
+            T = solver(a, b, M)
+            target_probs += T * prob
+        target_probs = target_probs / np.expand_dims(np.linalg.norm(target_probs, axis=-1, ord=1), axis=-1)
+        targets_all[idxs_2_rank] = torch.tensor(target_probs.argmax(axis=-1)).to(torch.long)
+        uncertainty_all[idxs_2_rank] = torch.tensor(1 - target_probs.max(axis=-1)).to(probs.dtype)
+    if w_uncertainty:
+        return targets_all, uncertainty_all
+    return targets_all

@@ -8,6 +8,10 @@
 * detector staging: the assignment ``images_np = ...`` inside get_face_app (E1:1317) and the subscript passed to
   ``face_app.get`` (E1:1326) are located in the syntax tree and their VALUE expressions evaluated with ``images`` /
   ``image_np`` bound to seeded tensors.  Nothing from the reference is written into this repo.
+* generate_dynamic_targets_race (E6:1413-1482): FunctionDef lifted unmodified and run on seeded fp32 probabilities
+  (N = 3..26 faces, some rows -1).  ``ot`` (POT 0.9.3) is not installed: ``ot.emd`` -> exact assignment by
+  scipy.optimize.linear_sum_assignment (as in make_golden.py), ``ot.dist`` -> the arithmetic of POT's
+  ``euclidean_distances`` on the numpy backend (einsum norms + ``-2 X.Y^T``, clamp, sqrt).
 """
 import argparse
 import ast
@@ -20,6 +24,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 E1 = "exp-1-debias-gender/1-main-debias.py"
 E3 = "exp-3-debias-gender-race/1-main-debias.py"
 E4 = "exp-4-debias-gender-race-age/1-main-debias.py"
+E6 = "exp-6-debias-race/1-main-debias.py"
+
+
+def pot_dist(x1, x2, metric="euclidean", p=1):
+    assert metric == "euclidean"
+    a2 = np.einsum("ij,ij->i", x1, x1)
+    b2 = np.einsum("ij,ij->i", x2, x2)
+    c = -2 * np.dot(x1, x2.T)
+    c += a2[:, None]
+    c += b2[None, :]
+    return np.sqrt(np.maximum(c, 0))
+
+
+def lsa_emd(a, b, M):
+    from scipy.optimize import linear_sum_assignment
+    b = np.asarray(b, dtype=np.int64)
+    cols = np.repeat(np.arange(M.shape[1]), b)
+    r, c = linear_sum_assignment(np.asarray(M, dtype=np.float64)[:, cols])
+    T = np.zeros(M.shape, dtype=np.float64)
+    T[r, cols[c]] = 1.0
+    return T
 
 
 def find_function(tree, name):
@@ -84,6 +109,23 @@ def main():
         key = f"stage_{str(dtype).split('.')[-1]}"
         out[key + "_in"] = images.float().numpy()
         out[key + "_out"] = np.ascontiguousarray(bgr)
+    # ---- E6 enumerated-composition assignment
+    import itertools
+    import math
+    import types
+    tree = ast.parse(open(os.path.join(a.ref, E6)).read())
+    fn = compile_function(find_function(tree, "generate_dynamic_targets_race"),
+                          {"torch": torch, "np": np, "math": math, "itertools": itertools,
+                           "ot": types.SimpleNamespace(dist=pot_dist, emd=lsa_emd)})
+    cases = [(3, 0, 2.0), (8, 2, 1.0), (17, 3, 2.0), (26, 4, 0.7), (24, 0, 3.0)]
+    out["race_n_cases"] = np.array(len(cases))
+    for c, (nv, nmiss, sharp) in enumerate(cases):
+        gen = torch.Generator().manual_seed(300 + c)
+        p = probs(gen, nv + nmiss, 4, torch.float32, sharp)
+        if nmiss:
+            p[torch.randperm(nv + nmiss, generator=gen)[:nmiss]] = -1
+        t, u = fn(p, True)
+        out[f"race_probs_{c}"], out[f"race_targets_{c}"], out[f"race_unc_{c}"] = p.numpy(), t.numpy(), u.numpy()
     np.savez_compressed(os.path.join(HERE, "nextrows.npz"), **out)
     print("wrote nextrows.npz:", sorted(out))
 

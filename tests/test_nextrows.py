@@ -1,4 +1,5 @@
-"""The two "next" rows of SURVEY.md 8f: detector staging (E1:1317/1326) and get_evaluate_metrics (E3:1716, E4:1780).
+"""The "next" rows of SURVEY.md 8f: detector staging (E1:1317/1326), get_evaluate_metrics (E3:1716, E4:1780) and the
+E6 enumerated-composition assignment (E6:1413-1482).
 Golden vectors come from the reference's own statements (tests/golden/make_golden_next.py)."""
 import os
 
@@ -81,3 +82,73 @@ def test_gpu_staging_vs_oracle(dname, shape):
     want = nextrows.stage_detector_input(x)
     got = fg.ops.stage_detector_input(x.cuda()).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+# ----------------------------------------------------------------------------- E6 enumerated-composition assignment
+def test_oracle_race_assignment_golden():
+    """The oracle's restatement of generate_dynamic_targets_race (E6:1413-1482) against the outputs of the reference's own
+    function body (lifted with ast, `ot` stubbed: see make_golden_next.py)."""
+    from oracle import assign as oassign
+    for c in range(int(GOLD["race_n_cases"])):
+        p = torch.tensor(GOLD[f"race_probs_{c}"])
+        t, u = oassign.generate_dynamic_targets_race(p, True)
+        assert np.array_equal(t.numpy(), GOLD[f"race_targets_{c}"]), c
+        assert np.array_equal(u.numpy(), GOLD[f"race_unc_{c}"]), c
+        assert torch.equal(oassign.generate_dynamic_targets_race(p), t)
+
+
+def test_race_compositions_host_logic():
+    """Product host code (api.race_compositions) == the oracle's statement-by-statement version, incl. the object-dtype
+    regime (N >= 36: multinomial coefficients beyond int64) and the tie order at the 95 % cut."""
+    import fairguide as fg
+    from oracle import assign as oassign
+    for N in (1, 2, 7, 24, 37):
+        c1, w1 = oassign.race_compositions(N)
+        c2, w2 = fg.api.race_compositions(N)
+        assert np.array_equal(np.asarray(c1, dtype=np.int64), c2) and np.array_equal(np.asarray(w1, dtype=np.float64), w2)
+        assert (c2.sum(1) == N).all() and w2.sum() > 0.95 and (np.diff(w2) <= 0).all()
+
+
+@pytest.mark.gpu
+def test_gpu_race_assignment_golden():
+    import fairguide as fg
+    for c in range(int(GOLD["race_n_cases"])):
+        p = torch.tensor(GOLD[f"race_probs_{c}"]).cuda()
+        t, u = fg.generate_dynamic_targets_race(p, True)
+        assert np.array_equal(t.cpu().numpy(), GOLD[f"race_targets_{c}"]), c          # bit-exact targets
+        assert np.array_equal(u.cpu().numpy(), GOLD[f"race_unc_{c}"]), c              # fp64 accumulation in the reference's order
+        assert torch.equal(fg.generate_dynamic_targets_race(p), t)
+        # fused thresholding == the caller's two lines
+        t2, _ = fg.generate_dynamic_targets_race(p, True, uncertainty_threshold=0.2)
+        ref = GOLD[f"race_targets_{c}"].copy(); ref[GOLD[f"race_unc_{c}"] > np.float32(0.2)] = -1
+        assert np.array_equal(t2.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,nmiss,sharp", [(1, 1, 2.0), (33, 5, 1.5), (48, 0, 2.5)])
+def test_gpu_race_assignment_vs_oracle(N, nmiss, sharp):
+    import fairguide as fg
+    from oracle import assign as oassign
+    g = torch.Generator().manual_seed(N)
+    p = torch.softmax(torch.randn(N + nmiss, 4, generator=g) * sharp, -1)
+    if nmiss:
+        p[torch.randperm(N + nmiss, generator=g)[:nmiss]] = -1
+    valid = (p != -1).all(-1)
+    M = fg.ops.race_cost_matrix(p.cuda(), N).cpu().numpy()
+    assert np.array_equal(M, oassign.pot_dist_euclidean(p[valid].numpy(), np.eye(4, dtype=np.int64)))   # fp64, bit-exact
+    t, u = fg.generate_dynamic_targets_race(p.cuda(), True, num_valid=N)
+    rt, ru = oassign.generate_dynamic_targets_race(p, True)
+    assert torch.equal(t.cpu(), rt) and torch.equal(u.cpu(), ru)
+    # every composition solved exactly: status word clean
+    combs, w = fg.api.race_compositions(N)
+    d16 = np.zeros((len(w), 16), np.int32); d16[:, :4] = combs
+    _, _, ws = fg.ops.assign_race_enumerated(p.cuda(), N, torch.from_numpy(d16).cuda(), torch.from_numpy(w).cuda())
+    assert ws[:4].view(torch.int32).item() == 0
+
+
+@pytest.mark.gpu
+def test_gpu_race_assignment_no_faces():
+    import fairguide as fg
+    p = torch.full((5, 4), -1.0).cuda()
+    t, u = fg.generate_dynamic_targets_race(p, True)
+    assert (t == -1).all() and (u == -1).all()
