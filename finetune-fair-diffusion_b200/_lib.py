@@ -49,6 +49,18 @@ SIGNATURES = {
     "fg_race_workspace_bytes": (_z, [_i, _i]),
     "fg_assign_race_enumerated": (_i, [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p, _z, _i, _p]),
     "fg_race_cost_matrix": (_i, [_p, _i, _i, _p, _p, _z, _i, _p]),
+    "fg_align_params_bytes": (_z, [_i]),
+    "fg_align_matrices": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fg_aligned_warp_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _f, _i, _p]),
+    "fg_aligned_warp_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "fg_feats_normalize_fwd": (_i, [_p, _i, _i, _p, _p, _i, _p]),
+    "fg_feats_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
+    "fg_face_search_workspace_bytes": (_z, [_i]),
+    "fg_face_search_top1": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _z, _p]),
+    "fg_face_loss_workspace_bytes": (_z, [_i, _i]),
+    "fg_face_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _i, _f, _p, _p, _z, _i, _p]),
+    "fg_face_loss_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _z, _i, _p]),
+    "fg_face_loss_target_rows": (_i, [_p, _i, _i, _p, _p]),
 }
 
 _lib = None
@@ -90,7 +102,9 @@ KERNELS_PER_CALL = {
     "fg_region_scale": 1, "fg_head_fwd": 2, "fg_head_bwd": 2, "fg_head_attributes": 1, "fg_fair_ce_fwd": 1,
     "fg_fair_ce_bwd": 1, "fg_fair_loss_fused": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
     "fg_ot_solve_single": 2, "fg_ot_cost_matrix": 2, "fg_stage_detector_input": 1, "fg_bias_metrics": 1,
-    "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2,
+    "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2, "fg_align_matrices": 1, "fg_aligned_warp_fwd": 1,
+    "fg_aligned_warp_bwd": 1, "fg_feats_normalize_fwd": 1, "fg_feats_normalize_bwd": 1, "fg_face_search_top1": 2,
+    "fg_face_loss_fwd": 4, "fg_face_loss_bwd": 1, "fg_face_loss_target_rows": 0,
 }
 
 

@@ -279,6 +279,79 @@ def threshold_and_slice(targets_all, uncertainty_all, uncertainty_threshold, n_l
     return targets_all[n_local * local_process_index:n_local * (local_process_index + 1)]
 
 
+# ----------------------------------------------------------------------------- f1: aligned chip
+def similarity_matrices(face_landmarks, face_indicators=None, image_hw=(512, 512)):
+    """``tform.params[0:2]`` of E1:304-307 for a batch of five-point landmarks [n,5,2] -> float64 [n,2,3]."""
+    lm = torch.as_tensor(face_landmarks)
+    return ops.align_matrices(lm, face_indicators, image_hw, want_matrix=True)[1]
+
+
+def aligned_face_chips(images, face_landmarks, face_indicators=None, size_aligned_face=112, fill_value=-1):
+    """The aligned-chip column of get_face_app (E1:1324-1351) in one call: image_pipeline (E1:292-312) for every image
+    with a face, ``fill_value`` elsewhere.  images [n,3,H,W] (gradient flows to them), face_landmarks [n,5,2]."""
+    lm = torch.as_tensor(face_landmarks, device=images.device)
+    params = ops.align_matrices(lm, face_indicators, images.shape[-2:], (size_aligned_face,) * 2)
+    return ag.AlignedWarp.apply(images, params, face_indicators, (size_aligned_face,) * 2, float(fill_value))
+
+
+def image_pipeline(img, tgz_landmark):
+    """E1:292-312: one image [3,H,W] in [-1,1] and its landmarks (numpy or tensor [5,2]) -> aligned chip [3,112,112]."""
+    lm = torch.as_tensor(np.asarray(tgz_landmark) if not torch.is_tensor(tgz_landmark) else tgz_landmark)
+    return aligned_face_chips(img.unsqueeze(0), lm.to(img.device).unsqueeze(0)).squeeze(0)
+
+
+def get_face_feats(net, data, flip=True, normalize=True, to_high_precision=True):
+    """E1:1179-1190.  ``net`` (SFNet in the reference) is an external callable; the float cast + L2 normalisation run in
+    one kernel (with its backward)."""
+    feats = net(data)
+    if flip:
+        feats = feats + net(torch.flip(data, [3]))
+    if normalize:
+        return ag.FeatsNormalize.apply(feats)          # computes in and returns float32, like to_high_precision=True
+    return feats.to(torch.float) if to_high_precision else feats
+
+
+class FaceFeatsModel(torch.nn.Module):
+    """E1:82-117: the face database as a frozen, L2-normalised parameter and its top-1 dot-product search.  Built from
+    the feature matrix [D,d] (the reference unpickles it from ``face_feats_path``)."""
+
+    def __init__(self, face_feats):
+        super().__init__()
+        self.face_feats = torch.nn.Parameter(ops.feats_normalize_fwd(face_feats)[0] if face_feats.is_cuda
+                                             else torch.nn.functional.normalize(face_feats.float(), dim=-1), requires_grad=False)
+
+    def forward(self, x):
+        return None
+
+    @torch.no_grad()
+    def semantic_search(self, query_embeddings, selector=None, return_similarity=False):
+        q = query_embeddings
+        best, sim = ops.face_search_top1(q, selector, self.face_feats.data)
+        hit = best >= 0
+        target = torch.ones_like(q) * (-1)
+        target[hit] = self.face_feats.data[best[hit]].to(q.dtype)
+        if return_similarity:
+            return target, sim.to(q.dtype)
+        return target
+
+
+def face_realism_loss(raw_feats, face_feats_ori, face_feats_model, face_indicators, *attr_args, confidence_level,
+                      search_needs_target=None, fill_value=-1):
+    """loss_face_ij of E1:1917-1929 (one attribute: ``targets, preds_ori, probs_ori``), E3:2124-2143 (two) and
+    E4:2253-2272 (three) for the whole micro-batch, as one differentiable op on the RAW summed features
+    ``net(x) + net(flip x)`` [b,d].  ``search_needs_target``: E1 searches only rows that have a target (default for one
+    attribute), E3 / E4 search every row with a face."""
+    n_attr = len(attr_args) // 3
+    targets = [attr_args[3 * a] for a in range(n_attr)]
+    preds = [attr_args[3 * a + 1] for a in range(n_attr)]
+    probs = [attr_args[3 * a + 2] for a in range(n_attr)]
+    if search_needs_target is None:
+        search_needs_target = n_attr == 1
+    db = face_feats_model.face_feats.data if isinstance(face_feats_model, torch.nn.Module) else face_feats_model
+    return ag.FaceLoss.apply(raw_feats, face_feats_ori.to(torch.float32), db, face_indicators, float(confidence_level),
+                             bool(search_needs_target), float(fill_value), n_attr, *targets, *preds, *probs)
+
+
 # ----------------------------------------------------------------------------- hooks / weights
 def _as_lists(args, n_attr):
     """(t0, pred0, prob0, t1, pred1, prob1, ...) -> ([t...], [pred...])"""

@@ -90,3 +90,54 @@ class ScatterRows(torch.autograd.Function):
     def backward(ctx, g):
         (index,) = ctx.saved_tensors
         return g[index], None, None, None
+
+
+class AlignedWarp(torch.autograd.Function):
+    """image_pipeline (E1:292-312) for a batch: similarity warp of every image onto the 112x112 template."""
+
+    @staticmethod
+    def forward(ctx, images, params, indicators, dst_hw, fill_value):
+        ctx.save_for_backward(params, indicators)
+        ctx.image_shape = tuple(images.shape)
+        return ops.aligned_warp_fwd(images, params, indicators, dst_hw, fill_value)
+
+    @staticmethod
+    def backward(ctx, g):
+        params, indicators = ctx.saved_tensors
+        return ops.aligned_warp_bwd(g, params, indicators, ctx.image_shape), None, None, None, None
+
+
+class FeatsNormalize(torch.autograd.Function):
+    """feats.to(float) -> F.normalize(dim=-1) (E1:1186-1189)."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        f, inv = ops.feats_normalize_fwd(raw)
+        ctx.save_for_backward(f, inv)
+        ctx.raw_dtype = raw.dtype
+        return f
+
+    @staticmethod
+    def backward(ctx, g):
+        f, inv = ctx.saved_tensors
+        return ops.feats_normalize_bwd(g, f, inv, ctx.raw_dtype)
+
+
+class FaceLoss(torch.autograd.Function):
+    """loss_face (E1:1917-1929 and its E3 / E4 forms) from the raw summed features of the micro-batch."""
+
+    @staticmethod
+    def forward(ctx, raw_feats, feats_ori, db, face_indicators, confidence_level, search_needs_target, fill, n_attr, *attr):
+        targets, preds, probs = attr[:n_attr], attr[n_attr:2 * n_attr], attr[2 * n_attr:]
+        loss, ws = ops.face_loss_fwd(raw_feats, feats_ori, db, face_indicators, targets, preds, probs, confidence_level,
+                                     search_needs_target, fill)
+        ctx.save_for_backward(feats_ori, db, ws)
+        ctx.meta = (raw_feats.shape[0], raw_feats.shape[1], raw_feats.dtype)
+        ctx.n_inputs = 8 + 3 * n_attr
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        feats_ori, db, ws = ctx.saved_tensors
+        n, d, dtype = ctx.meta
+        return (ops.face_loss_bwd(g_loss, feats_ori, db, ws, n, d, dtype),) + (None,) * (ctx.n_inputs - 1)

@@ -368,3 +368,115 @@ def bias_metrics(probs_gender, probs_race, probs_age=None):
     out = torch.empty((9 if pa is not None else 5,), dtype=torch.float64, device=pg.device)
     check(_lib.lib().fg_bias_metrics(_p(pg), _p(pr), _p(pa), pg.shape[0], _p(out), _dt(pg), _stream()), "fg_bias_metrics")
     return out
+
+
+# ------------------------------------------------------------------ f1: aligned 112x112 chip
+def align_matrices(landmarks, indicators, src_hw, dst_hw=(112, 112), want_matrix=False):
+    """landmarks [n,5,2] float32 -> params [n,16] float32 (for the two warp kernels) and, optionally, the similarity
+    matrices [n,2,3] float64 of E1:304-307."""
+    _cuda(landmarks, indicators)
+    lm = landmarks.to(torch.float32).contiguous()
+    n = lm.shape[0]
+    params = torch.empty((max(n, 1), 16), dtype=torch.float32, device=lm.device)
+    M = torch.empty((n, 2, 3), dtype=torch.float64, device=lm.device) if want_matrix else None
+    check(_lib.lib().fg_align_matrices(_p(lm), _p(_u8(indicators)), n, src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
+                                       _p(M), _p(params), _stream()), "fg_align_matrices")
+    return (params, M) if want_matrix else params
+
+
+def aligned_warp_fwd(images, params, indicators, dst_hw=(112, 112), fill=-1.0):
+    _cuda(images, params, indicators)
+    images = images.contiguous()
+    n, C, H, W = images.shape
+    out = torch.empty((n, C, dst_hw[0], dst_hw[1]), dtype=images.dtype, device=images.device)
+    check(_lib.lib().fg_aligned_warp_fwd(_p(images), n, C, H, W, _p(params), _p(_u8(indicators)), _p(out), dst_hw[0], dst_hw[1],
+                                         float(fill), _dt(images), _stream()), "fg_aligned_warp_fwd")
+    return out
+
+
+def aligned_warp_bwd(g_out, params, indicators, image_shape, g_images=None):
+    """Gradient of aligned_warp_fwd wrt the images; with ``g_images`` given it is accumulated in place."""
+    _cuda(g_out, params, indicators, g_images)
+    g_out = g_out.contiguous()
+    n, C, Hd, Wd = g_out.shape
+    acc = g_images is not None
+    if acc:
+        assert g_images.is_contiguous() and tuple(g_images.shape) == tuple(image_shape) and g_images.dtype == g_out.dtype
+    else:
+        g_images = torch.empty(tuple(image_shape), dtype=g_out.dtype, device=g_out.device)
+    check(_lib.lib().fg_aligned_warp_bwd(_p(g_out), n, C, Hd, Wd, _p(params), _p(_u8(indicators)), _p(g_images), image_shape[2],
+                                         image_shape[3], 1 if acc else 0, _dt(g_out), _stream()), "fg_aligned_warp_bwd")
+    return g_images
+
+
+# ------------------------------------------------------------------ f1: face-realism loss
+def feats_normalize_fwd(raw):
+    _cuda(raw)
+    raw = raw.contiguous()
+    n, d = raw.shape
+    f = torch.empty((n, d), dtype=torch.float32, device=raw.device)
+    inv = torch.empty((n,), dtype=torch.float32, device=raw.device)
+    check(_lib.lib().fg_feats_normalize_fwd(_p(raw), n, d, _p(f), _p(inv), _dt(raw), _stream()), "fg_feats_normalize_fwd")
+    return f, inv
+
+
+def feats_normalize_bwd(g_f, f, inv, dtype):
+    n, d = f.shape
+    g_raw = torch.empty((n, d), dtype=dtype, device=f.device)
+    check(_lib.lib().fg_feats_normalize_bwd(_p(g_f.to(torch.float32).contiguous()), _p(f), _p(inv), n, d, _p(g_raw), _DT[dtype], _stream()),
+          "fg_feats_normalize_bwd")
+    return g_raw
+
+
+def face_search_top1(queries, selector, db):
+    """-> (best_row int64 [m] (-1 where not selected), similarity float32 [m])."""
+    _cuda(queries, selector, db)
+    q = queries.to(torch.float32).contiguous()
+    m, d = q.shape
+    assert db.dtype == torch.float32 and db.is_contiguous() and db.shape[1] == d
+    best = torch.empty((m,), dtype=torch.int64, device=q.device)
+    sim = torch.empty((m,), dtype=torch.float32, device=q.device)
+    nbytes = _lib.lib().fg_face_search_workspace_bytes(m)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
+    check(_lib.lib().fg_face_search_top1(_p(q), _p(_u8(selector)), m, _p(db), db.shape[0], d, _p(best), _p(sim), _p(ws), nbytes,
+                                         _stream()), "fg_face_search_top1")
+    return best, sim
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def face_loss_fwd(raw_feats, feats_ori, db, face_indicators, targets, preds_ori, probs_ori, confidence_level,
+                  search_needs_target, fill=-1.0):
+    """-> (loss [n] in raw_feats.dtype, workspace) ; the workspace carries the state face_loss_bwd needs."""
+    _cuda(raw_feats, feats_ori, db, face_indicators, *targets, *preds_ori, *probs_ori)
+    raw = raw_feats.contiguous()
+    n, d = raw.shape
+    assert feats_ori.dtype == torch.float32 and db.dtype == torch.float32 and db.is_contiguous()
+    fo = feats_ori.contiguous()
+    ts = [t.to(torch.int64).contiguous() for t in targets]
+    ps = [t.to(torch.int64).contiguous() for t in preds_ori]
+    qs = [t.to(raw.dtype).contiguous() for t in probs_ori]
+    widths = _iarr([q.shape[1] for q in qs])
+    nbytes = _lib.lib().fg_face_loss_workspace_bytes(n, d)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=raw.device)
+    loss = torch.empty((n,), dtype=raw.dtype, device=raw.device)
+    ind = _u8(face_indicators)
+    check(_lib.lib().fg_face_loss_fwd(_p(raw), _p(fo), _p(db), n, d, db.shape[0], _p(ind), _ptr_array(ts), _ptr_array(ps),
+                                      _ptr_array(qs), widths, len(ts), float(confidence_level), 1 if search_needs_target else 0,
+                                      float(fill), _p(loss), _p(ws), nbytes, _dt(raw), _stream()), "fg_face_loss_fwd")
+    return loss, ws
+
+
+def face_loss_bwd(g_loss, feats_ori, db, ws, n, d, dtype):
+    g_raw = torch.empty((n, d), dtype=dtype, device=db.device)
+    check(_lib.lib().fg_face_loss_bwd(_p(g_loss.to(dtype).contiguous()), _p(feats_ori.contiguous()), _p(db), n, d, _p(g_raw), _p(ws),
+                                      ws.numel(), _DT[dtype], _stream()), "fg_face_loss_bwd")
+    return g_raw
+
+
+def face_loss_target_rows(ws, n, d):
+    out = torch.empty((n,), dtype=torch.int64, device=ws.device)
+    check(_lib.lib().fg_face_loss_target_rows(_p(ws), n, d, _p(out), _stream()), "fg_face_loss_target_rows")
+    return out

@@ -218,6 +218,58 @@ int fg_assign_race_enumerated(const void* probs_race, int n_all, int n_valid, co
 int fg_race_cost_matrix(const void* probs_race, int n_all, int n_valid, double* M4, void* workspace,
                         size_t workspace_bytes, int dtype, void* stream);
 
+/* f1: aligned 112x112 face chip, image_pipeline (E1:292-312) for a batch.
+ *
+ * fg_align_matrices: landmarks [n,5,2] float32 (the detector's `kps`, image pixels); indicators [n] uint8 or NULL.
+ *   Least-squares similarity of the landmarks onto the 112x112 five-point template (skimage SimilarityTransform.estimate,
+ *   E1:304-305; closed form in 2-D), rounded to float32 like `.to(img.dtype)` (E1:307).  M_out [n,2,3] float64 or NULL
+ *   receives that matrix (-1 rows without a face); params [n,16] float32 (fg_align_params_bytes) receives what the two
+ *   warp kernels need: the composed `output pixel -> source pixel` affine map of kornia.warp_affine(align_corners=False)
+ *   (pixel<->[-1,1] with 2/(size-1), grid_sample un-normalisation with align_corners=False), its inverse and the bounding
+ *   box of the taps.
+ * fg_aligned_warp_fwd: images [n,C,Hs,Ws] -> out [n,C,Hd,Wd]; bilinear, taps outside the image read -1 (zero padding in
+ *   the 0..255 domain of E1:293); rows without a face are filled with `fill` (E1:1332).
+ * fg_aligned_warp_bwd: g_out [n,C,Hd,Wd] -> g_images [n,C,Hs,Ws], C <= 4; gather form (no atomics).  accumulate = 0
+ *   overwrites the whole gradient (zeros away from the face), accumulate = 1 adds to what fg_image_grad wrote. */
+size_t fg_align_params_bytes(int n);
+int fg_align_matrices(const float* landmarks, const uint8_t* indicators, int n, int Hs, int Ws, int Hd, int Wd,
+                      double* M_out, float* params, void* stream);
+int fg_aligned_warp_fwd(const void* images, int n, int C, int Hs, int Ws, const float* params, const uint8_t* indicators,
+                        void* out, int Hd, int Wd, float fill, int dtype, void* stream);
+int fg_aligned_warp_bwd(const void* g_out, int n, int C, int Hd, int Wd, const float* params, const uint8_t* indicators,
+                        void* g_images, int Hs, int Ws, int accumulate, int dtype, void* stream);
+
+/* f1: face-realism loss.  Feature rows are [n,d] (d = 512 for the reference's SFNet), d % 4 == 0.
+ *
+ * fg_feats_normalize_fwd / _bwd: the tail of get_face_feats (E1:1186-1189): raw [n,d] dtype (net(x) + net(flip x)) ->
+ *   f [n,d] float32 = raw / max(|raw|, 1e-12), inv_norm [n] float32 (or NULL); the backward maps g_f to g_raw (dtype).
+ * fg_face_search_top1: FaceFeatsModel.semantic_search (E1:96-117), top-1 dot product.  queries [m,d] float32, selector [m]
+ *   uint8 or NULL, db [D,d] float32 (L2-normalised rows, E1:88) -> best_row [m] int64 (-1 where not selected; the lowest
+ *   row wins ties), similarity [m] float32 or NULL (-1 where not selected).
+ * fg_face_loss_fwd: loss_face of E1:1917-1929 / E3:2124-2143 / E4:2253-2272 for the whole micro-batch in one call:
+ *   normalise raw_feats; a row with a face whose targets all equal the original predictions with confidence
+ *   max(probs_ori) >= confidence_level takes the original image's features feats_ori [n,d] float32 as target; the other
+ *   rows with a face (search_needs_target = 1, E1: and with a target) take the nearest database row; loss = 1 - <f, target>
+ *   in `dtype`, `fill` elsewhere.  targets / preds_ori: HOST arrays of n_attr device pointers ([n] int64 each);
+ *   probs_ori: host array of device pointers [n,widths[a]] dtype.
+ * fg_face_loss_bwd: g_loss [n] dtype -> g_raw_feats [n,d] dtype, reading the forward's state from the same workspace. */
+int fg_feats_normalize_fwd(const void* raw, int n, int d, float* f, float* inv_norm, int dtype, void* stream);
+int fg_feats_normalize_bwd(const float* g_f, const float* f, const float* inv_norm, int n, int d, void* g_raw, int dtype,
+                           void* stream);
+size_t fg_face_search_workspace_bytes(int m);
+int fg_face_search_top1(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
+                        int64_t* best_row, float* similarity, void* workspace, size_t workspace_bytes, void* stream);
+size_t fg_face_loss_workspace_bytes(int n, int d);
+int fg_face_loss_fwd(const void* raw_feats, const float* feats_ori, const float* db, int n, int d, int D,
+                     const uint8_t* face_indicators, const int64_t* const* targets, const int64_t* const* preds_ori,
+                     const void* const* probs_ori, const int32_t* widths, int n_attr, float confidence_level,
+                     int search_needs_target, float fill, void* loss, void* workspace, size_t workspace_bytes,
+                     int dtype, void* stream);
+int fg_face_loss_bwd(const void* g_loss, const float* feats_ori, const float* db, int n, int d, void* g_raw_feats,
+                     void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* Test hook: which target every row of the last fg_face_loss_fwd used (>= 0 database row, -2 feats_ori, -1 none). */
+int fg_face_loss_target_rows(const void* workspace, int n, int d, int64_t* target_row, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

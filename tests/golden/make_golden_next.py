@@ -126,6 +126,34 @@ def main():
             p[torch.randperm(nv + nmiss, generator=gen)[:nmiss]] = -1
         t, u = fn(p, True)
         out[f"race_probs_{c}"], out[f"race_targets_{c}"], out[f"race_unc_{c}"] = p.numpy(), t.numpy(), u.numpy()
+    # ---- image_pipeline (E1:292-312): the reference's glue around skimage / kornia (both absent -> oracle restatements)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import align as oalign
+
+    class _Similarity:
+        def estimate(self, src, dst):
+            self.params = oalign.umeyama(src, dst, True)
+            return True
+
+    tree = ast.parse(open(os.path.join(a.ref, E1)).read())
+    fn = compile_function(find_function(tree, "image_pipeline"),
+                          {"torch": torch, "np": np, "transform": types.SimpleNamespace(SimilarityTransform=_Similarity),
+                           "kornia": types.SimpleNamespace(geometry=types.SimpleNamespace(transform=types.SimpleNamespace(
+                               warp_affine=lambda src, M, dsize, mode, padding_mode, align_corners:
+                               oalign.warp_affine(src, M, dsize, align_corners=align_corners))))})
+    rng = np.random.default_rng(7)
+    out["align_n_cases"] = np.array(3)
+    for c in range(3):
+        gen = torch.Generator().manual_seed(400 + c)
+        yy = torch.arange(160, dtype=torch.float32).view(1, 160, 1)
+        xx = torch.arange(192, dtype=torch.float32).view(1, 1, 192)
+        img = (0.6 * torch.sin(0.05 * xx + c) * torch.cos(0.04 * yy) + (torch.rand(3, 160, 192, generator=gen) - 0.5) * 0.2).clamp(-1, 1)
+        s, th = [(1.2, 0.3), (0.9, -0.4), (0.5, 0.1)][c]
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        lm = ((oalign.TEMPLATE_112 - 56.0) @ (R.T * s) + [[90, 70], [30, 120], [150, 80]][c] + rng.normal(size=(5, 2))).astype(np.float32)
+        res = fn(img, lm)
+        out[f"align_img_{c}"], out[f"align_lm_{c}"], out[f"align_out_{c}"] = img.numpy(), lm, res.numpy()
     np.savez_compressed(os.path.join(HERE, "nextrows.npz"), **out)
     print("wrote nextrows.npz:", sorted(out))
 
