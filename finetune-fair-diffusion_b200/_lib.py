@@ -61,6 +61,8 @@ SIGNATURES = {
     "fg_face_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _i, _f, _p, _p, _z, _i, _p]),
     "fg_face_loss_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _z, _i, _p]),
     "fg_face_loss_target_rows": (_i, [_p, _i, _i, _p, _p]),
+    "fg_grad_bucket_pack": (_i, [_p, _p, _i, _i64, _p, _p, _i, _p]),
+    "fg_grad_bucket_unpack": (_i, [_p, _p, _i, _i64, _p, _d, _d, _i, _p]),
 }
 
 _lib = None
@@ -105,6 +107,7 @@ KERNELS_PER_CALL = {
     "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2, "fg_align_matrices": 1, "fg_aligned_warp_fwd": 1,
     "fg_aligned_warp_bwd": 1, "fg_feats_normalize_fwd": 1, "fg_feats_normalize_bwd": 1, "fg_face_search_top1": 2,
     "fg_face_loss_fwd": 4, "fg_face_loss_bwd": 1, "fg_face_loss_target_rows": 0,
+    "fg_grad_bucket_pack": 2, "fg_grad_bucket_unpack": 1,
 }
 
 

@@ -130,46 +130,60 @@ aligned_warp_fwd_kernel(const T* __restrict__ images, const float* __restrict__ 
     }
 }
 
-// backward: grid (ceil(Ws/32), ceil(Hs/8), n), block (32, 8); thread = one source pixel, all channels
+// backward: persistent CTAs of 8 warps; a CTA walks the images round-robin and, inside an image, the 32x8-pixel tiles of
+// the bounding box of the taps only (the whole image when it has to write the zeros as well) -- a grid over all tiles
+// of all images spent its time launching ~1M empty CTAs.  thread = one source pixel, all channels.
 template <typename T>
 __global__ void __launch_bounds__(256)
 aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ params, const uint8_t* __restrict__ indicators,
-                        int C, int Hs, int Ws, int Hd, int Wd, int accumulate, T* __restrict__ g_images) {
-    const int img = blockIdx.z;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= Ws || y >= Hs) return;
-    const float* P = params + (size_t)img * ALIGN_PARAMS;
-    const bool face = !indicators || indicators[img];
-    const bool inside = face && x >= (int)P[12] && x <= (int)P[14] && y >= (int)P[13] && y <= (int)P[15];
-    T* g = g_images + (size_t)img * C * Hs * Ws + (size_t)y * Ws + x;
-    if (!inside) {
-        if (!accumulate) for (int c = 0; c < C; c++) g[(size_t)c * Hs * Ws] = from_f32<T>(0.f);
-        return;
-    }
-    // candidate output pixels: q = D p + d, within the parallelogram D (p + (-1,1)^2)
-    const float qx = fmaf(P[6], (float)x, fmaf(P[7], (float)y, P[10]));
-    const float qy = fmaf(P[8], (float)x, fmaf(P[9], (float)y, P[11]));
-    const float hx = fabsf(P[6]) + fabsf(P[7]), hy = fabsf(P[8]) + fabsf(P[9]);
-    const int j0 = max((int)ceilf(qx - hx - 1e-3f), 0), j1 = min((int)floorf(qx + hx + 1e-3f), Wd - 1);
-    const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const T* go = g_out + (size_t)img * C * Hd * Wd;
-    for (int i = i0; i <= i1; i++) {
-        for (int j = j0; j <= j1; j++) {
-            // the same fp32 expressions as the forward, so the tap weights are bit-identical
-            const float xs = fmaf(P[0], (float)j, fmaf(P[1], (float)i, P[2]));
-            const float ys = fmaf(P[3], (float)j, fmaf(P[4], (float)i, P[5]));
-            const float fx0 = floorf(xs), fy0 = floorf(ys);
-            const int tx = x - (int)fx0, ty = y - (int)fy0;              // 0 or 1 when this pixel is a tap
-            if ((unsigned)tx > 1u || (unsigned)ty > 1u) continue;
-            const float wx1 = xs - fx0, wy1 = ys - fy0;
-            const float w = (tx ? wx1 : 1.f - wx1) * (ty ? wy1 : 1.f - wy1);
-            for (int c = 0; c < C && c < 4; c++) acc[c] = fmaf(w, to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)i * Wd + j)), acc[c]);
+                        int n, int C, int Hs, int Ws, int Hd, int Wd, int accumulate, T* __restrict__ g_images) {
+    const int tx_ = threadIdx.x & 31, ty_ = threadIdx.x >> 5;
+    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+        const float* P = params + (size_t)img * ALIGN_PARAMS;
+        const bool face = !indicators || indicators[img];
+        const int bx0 = (int)P[12], by0 = (int)P[13], bx1 = (int)P[14], by1 = (int)P[15];
+        if (accumulate && (!face || bx1 < bx0 || by1 < by0)) continue;
+        // tile range: the bounding box (accumulate) or the whole image (overwrite)
+        const int X0 = accumulate ? (bx0 & ~31) : 0, Y0 = accumulate ? (by0 & ~7) : 0;
+        const int X1 = accumulate ? bx1 : Ws - 1, Y1 = accumulate ? by1 : Hs - 1;
+        const int tiles_x = (X1 - X0) / 32 + 1, tiles_y = (Y1 - Y0) / 8 + 1;
+        const float d00 = P[6], d01 = P[7], d10 = P[8], d11 = P[9], d02 = P[10], d12 = P[11];
+        const float c00 = P[0], c01 = P[1], c02 = P[2], c10 = P[3], c11 = P[4], c12 = P[5];
+        const float hx = fabsf(d00) + fabsf(d01), hy = fabsf(d10) + fabsf(d11);
+        const T* go = g_out + (size_t)img * C * Hd * Wd;
+        for (int tile = 0; tile < tiles_x * tiles_y; tile++) {
+            const int x = X0 + (tile % tiles_x) * 32 + tx_, y = Y0 + (tile / tiles_x) * 8 + ty_;
+            if (x >= Ws || y >= Hs) continue;
+            T* g = g_images + (size_t)img * C * Hs * Ws + (size_t)y * Ws + x;
+            const bool inside = face && x >= bx0 && x <= bx1 && y >= by0 && y <= by1;
+            if (!inside) {
+                if (!accumulate) for (int c = 0; c < C; c++) g[(size_t)c * Hs * Ws] = from_f32<T>(0.f);
+                continue;
+            }
+            // candidate output pixels: q = D p + d, within the parallelogram D (p + (-1,1)^2)
+            const float qx = fmaf(d00, (float)x, fmaf(d01, (float)y, d02));
+            const float qy = fmaf(d10, (float)x, fmaf(d11, (float)y, d12));
+            const int j0 = max((int)ceilf(qx - hx - 1e-3f), 0), j1 = min((int)floorf(qx + hx + 1e-3f), Wd - 1);
+            const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = i0; i <= i1; i++) {
+                for (int j = j0; j <= j1; j++) {
+                    // the same fp32 expressions as the forward, so the tap weights are bit-identical
+                    const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
+                    const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
+                    const float fx0 = floorf(xs), fy0 = floorf(ys);
+                    const int tx = x - (int)fx0, ty = y - (int)fy0;              // 0 or 1 when this pixel is a tap
+                    if ((unsigned)tx > 1u || (unsigned)ty > 1u) continue;
+                    const float wx1 = xs - fx0, wy1 = ys - fy0;
+                    const float w = (tx ? wx1 : 1.f - wx1) * (ty ? wy1 : 1.f - wy1);
+                    for (int c = 0; c < C && c < 4; c++) acc[c] = fmaf(w, to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)i * Wd + j)), acc[c]);
+                }
+            }
+            for (int c = 0; c < C && c < 4; c++) {
+                T* gc = g + (size_t)c * Hs * Ws;
+                *gc = from_f32<T>(accumulate ? to_f32(*gc) + acc[c] : acc[c]);
+            }
         }
-    }
-    for (int c = 0; c < C && c < 4; c++) {
-        T* gc = g + (size_t)c * Hs * Ws;
-        *gc = from_f32<T>(accumulate ? to_f32(*gc) + acc[c] : acc[c]);
     }
 }
 
@@ -264,12 +278,19 @@ face_search_kernel(const float* __restrict__ queries, const uint8_t* __restrict_
     unsigned long long my_best = 0ull;                                // lane q keeps query q's best
     const int rows_per_cta = (D + gridDim.x - 1) / gridDim.x;
     const int r_begin = blockIdx.x * rows_per_cta, r_end = min(D, r_begin + rows_per_cta);
-    for (int r = r_begin + warp; r < r_end; r += 8) {
-        const float* row = db + (size_t)r * d;
-        if (d == SEARCH_D) {
-            float4 v[4];
+    if (d == SEARCH_D) {
+        // the next row is fetched while the current one is multiplied (one row = 4 x 16-byte loads per lane)
+        float4 v[4], nx[4];
+        int r = r_begin + warp;
+        if (r < r_end) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = __ldg(reinterpret_cast<const float4*>(row) + lane + 32 * k);
+            for (int k = 0; k < 4; k++) v[k] = __ldg(reinterpret_cast<const float4*>(db + (size_t)r * d) + lane + 32 * k);
+        }
+        for (; r < r_end; r += 8) {
+            if (r + 8 < r_end) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) nx[k] = __ldg(reinterpret_cast<const float4*>(db + (size_t)(r + 8) * d) + lane + 32 * k);
+            }
             for (int q = 0; q < nq; q++) {
                 const float4* qv = reinterpret_cast<const float4*>(q_s + (size_t)q * d);
                 float acc = 0.f;
@@ -282,7 +303,12 @@ face_search_kernel(const float* __restrict__ queries, const uint8_t* __restrict_
                 const unsigned long long key = ((unsigned long long)fkey32(acc) << 32) | (unsigned)(~r);
                 if (lane == q && key > my_best) my_best = key;
             }
-        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = nx[k];
+        }
+    } else {
+        for (int r = r_begin + warp; r < r_end; r += 8) {
+            const float* row = db + (size_t)r * d;
             for (int q = 0; q < nq; q++) {
                 float acc = 0.f;
                 for (int k = lane; k < d; k += 32) acc = fmaf(__ldg(row + k), q_s[(size_t)q * d + k], acc);
@@ -373,10 +399,9 @@ extern "C" int fg_aligned_warp_bwd(const void* g_out, int n, int C, int Hd, int 
     if (n < 0 || C < 1 || C > 4 || Hs < 2 || Ws < 2 || Hd < 1 || Wd < 1) return FG_ERR_INVALID_ARG;
     if (n == 0) return FG_OK;
     if (!g_out || !params || !g_images) return FG_ERR_INVALID_ARG;
-    if (n > 65535) return FG_ERR_LIMIT;
-    dim3 grid((Ws + 31) / 32, (Hs + 7) / 8, n), block(32, 8);
+    const int grid = n < 8 * FG_NUM_SMS ? n : 8 * FG_NUM_SMS;       // persistent: up to 8 CTAs of 256 threads per SM
     FG_DISPATCH_DTYPE(dtype, T,
-        aligned_warp_bwd_kernel<T><<<grid, block, 0, fg_stream(stream)>>>((const T*)g_out, params, indicators, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
+        aligned_warp_bwd_kernel<T><<<grid, 256, 0, fg_stream(stream)>>>((const T*)g_out, params, indicators, n, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -405,13 +430,13 @@ extern "C" int fg_feats_normalize_bwd(const float* g_f, const float* f, const fl
 
 static int launch_search(const float* queries, const uint8_t* selector, uint8_t want, int m, const float* db, int D, int d,
                          unsigned long long* keys, cudaStream_t st) {
-    const size_t smem = (size_t)SEARCH_Q * d * sizeof(float);
+    const size_t smem = (size_t)(m < SEARCH_Q ? m : SEARCH_Q) * d * sizeof(float);      // few queries -> more CTAs per SM
     if (smem > 200 * 1024) return FG_ERR_LIMIT;
     cudaError_t e = cudaFuncSetAttribute(face_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int groups = (m + SEARCH_Q - 1) / SEARCH_Q;
     int slabs = (D + 63) / 64;                                          // >= 64 database rows per CTA
-    if (slabs > 2 * FG_NUM_SMS) slabs = 2 * FG_NUM_SMS;
+    if (slabs > 4 * FG_NUM_SMS) slabs = 4 * FG_NUM_SMS;
     if (slabs < 1) slabs = 1;
     face_search_kernel<<<dim3(slabs, groups), 256, smem, st>>>(queries, selector, want, m, db, D, d, keys);
     FG_LAUNCH_CHECK();

@@ -543,6 +543,112 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
     __syncthreads();
 }
 
+// Price search for problems whose fp32 cost copy does not fit in shared memory (modes 1 / 2 of ot_solve_kernel).  Streaming
+// the whole copy from L2 every round made the search L2-bound (~30 B/clk per SM with 100 CTAs doing the same), so the
+// rows are split three ways and only the remainder is streamed: the first 4 x 512 rows stay in registers for all rounds
+// (as in price_search_reg), the next `slice_rows` rows sit in the shared memory the member lists leave free (class-major
+// slice), the rest is read from global memory.  Histogram and price update as in price_search.
+template <int KK>
+__device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const float* __restrict__ Mf, float* __restrict__ slice,
+                                                    int slice_rows, int N, int dual_iters, float step0) {
+    constexpr int RPT = 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
+    int my_prev = 0, best_resid = 0x7fffffff;
+    const int my_b = lane < KK ? sm.b[lane] : 0;
+    const int reg_rows = min(N, RPT * SOLVER_THREADS);
+    slice_rows = min(slice_rows, N - reg_rows);
+    const int glob_begin = reg_rows + slice_rows;
+    float x[RPT][KK];
+    bool have[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+        const int i = tid + r * SOLVER_THREADS;
+        have[r] = i < N;
+#pragma unroll
+        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? __ldg(Mf + (size_t)l * N + i) : 0.f;
+    }
+    for (int e = tid; e < KK * slice_rows; e += SOLVER_THREADS) {
+        const int l = e / slice_rows, j = e - l * slice_rows;
+        slice[e] = __ldg(Mf + (size_t)l * N + reg_rows + j);
+    }
+    __syncthreads();
+    for (int it = 0; it <= dual_iters; it++) {
+        float pr[KK];
+#pragma unroll
+        for (int l = 0; l < KK; l++) pr[l] = __shfl_sync(0xffffffffu, my_price, l);
+        unsigned acc[KP / 2];
+#pragma unroll
+        for (int w = 0; w < KP / 2; w++) acc[w] = 0u;
+        unsigned long long h = 0ull; int pending = 0;
+        auto count_row = [&](float (&y)[KK]) {
+            int idx[KK];
+#pragma unroll
+            for (int l = 0; l < KK; l++) { y[l] -= pr[l]; idx[l] = l; }
+#pragma unroll
+            for (int st = 1; st < KK; st *= 2)
+#pragma unroll
+                for (int l = 0; l < KK; l += 2 * st)
+                    if (y[l + st] < y[l]) { y[l] = y[l + st]; idx[l] = idx[l + st]; }      // strict: the lower class wins ties
+            h += 1ull << (4 * idx[0]);
+            if (++pending == 15) {                 // 4-bit fields are full: spill into the 16-bit accumulators
+#pragma unroll
+                for (int w = 0; w < KP / 2; w++) acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+                h = 0ull; pending = 0;
+            }
+        };
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            if (have[r]) {
+                float y[KK];
+#pragma unroll
+                for (int l = 0; l < KK; l++) y[l] = x[r][l];
+                count_row(y);
+            }
+        }
+        for (int j = tid; j < slice_rows; j += SOLVER_THREADS) {
+            float y[KK];
+#pragma unroll
+            for (int l = 0; l < KK; l++) y[l] = slice[l * slice_rows + j];
+            count_row(y);
+        }
+#pragma unroll 2
+        for (int i = glob_begin + tid; i < N; i += SOLVER_THREADS) {
+            float y[KK];
+#pragma unroll
+            for (int l = 0; l < KK; l++) y[l] = __ldg(Mf + (size_t)l * N + i);
+            count_row(y);
+        }
+#pragma unroll
+        for (int w = 0; w < KK / 2; w++) {
+            acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+            acc[w] = __reduce_add_sync(0xffffffffu, acc[w]);           // N <= 65535: a 16-bit field cannot overflow
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < KK / 2; w++) sm.whist[it & 1][warp][w] = acc[w];
+        }
+        __syncthreads();
+        int cnt = 0;
+        if (lane < KK) {
+#pragma unroll
+            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu);
+        }
+        const int err = lane < KK ? my_b - cnt : 0;
+        const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
+        if (resid < best_resid) { best_resid = resid; my_best = my_price; }
+        if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
+        if (lane < KK) {
+            const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
+            if (sg * my_prev < 0) my_step *= 0.5f; else if (sg * my_prev > 0) my_step *= 1.2f;
+            my_prev = sg;
+            my_price += my_step * (float)sg;                           // too few rows -> cheaper class
+        }
+    }
+    if (warp == 0 && lane < KP) sm.best_pricef[lane] = my_best;
+    __syncthreads();
+}
+
 // One CTA solves one transport problem exactly.
 //
 //  1. price search (all warps):  `dual_iters` rounds of sign-based dual ascent on the K class prices
@@ -569,7 +675,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
                 const double* __restrict__ prices_in, double* __restrict__ prices_out, int dual_iters, double step0,
                 Demand demand_by_value, const int* __restrict__ hist,
                 int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
-                int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global) {
+                int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global, int slice_rows) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
@@ -629,6 +735,11 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     } else if (MODE == 0 && m_in_smem && N <= 4 * SOLVER_THREADS) {
         if (K == 16) price_search_reg<16, 4>(sm, v.Mf, N, dual_iters, (float)step0);
         else price_search_reg<8, 4>(sm, v.Mf, N, dual_iters, (float)step0);
+    } else if (MODE != 0 && m_in_smem) {
+        // the shared memory behind the last view holds a slice of the cost copy during the search
+        float* slice = reinterpret_cast<float*>(dyn_smem + (MODE == 1 ? solver_off_M(N, K) : solver_off_members(N)));
+        if (K == 16) price_search_hybrid<16>(sm, v.Mf, slice, slice_rows, N, dual_iters, (float)step0);
+        else price_search_hybrid<8>(sm, v.Mf, slice, slice_rows, N, dual_iters, (float)step0);
     } else if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     else price_search<8>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
@@ -923,11 +1034,21 @@ static int solver_mode(int N, int K) {
     if (solver_off_M(N, K) <= 220 * 1024) return 1;
     return 2;
 }
+// modes 1 / 2: rows of the cost copy kept in the shared memory the views leave free during the price search
+static int solver_slice_rows(int N, int K) {
+    const int mode = solver_mode(N, K);
+    if (mode == 0) return 0;
+    const size_t base = mode == 1 ? solver_off_M(N, K) : solver_off_members(N);
+    long rows = ((long)220 * 1024 - (long)base) / (long)(K * sizeof(float));
+    const long want = (long)N - 4 * SOLVER_THREADS;
+    if (rows > want) rows = want;
+    return rows > 0 ? (int)(rows & ~3L) : 0;
+}
 static int solver_smem_bytes(int N, int K) {
     const int mode = solver_mode(N, K);
     if (mode == 0) return (int)(solver_off_M(N, K) + (size_t)N * K * sizeof(float));
-    if (mode == 1) return (int)solver_off_M(N, K);
-    return (int)solver_off_members(N);
+    const size_t base = mode == 1 ? solver_off_M(N, K) : solver_off_members(N);
+    return (int)(base + (size_t)solver_slice_rows(N, K) * K * sizeof(float));
 }
 static size_t solver_members_bytes(int N, int K, int S) {      // global member lists of mode 2
     return solver_mode(N, K) == 2 ? (size_t)(S > 0 ? S : 1) * K * N * sizeof(uint16_t) : 0;
@@ -953,9 +1074,10 @@ __global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict
     do {                                                                                                              \
         const int mode_ = solver_mode(N_, K_);                                                                        \
         const int smem_ = solver_smem_bytes(N_, K_);                                                                  \
-        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                        \
-        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                   \
-        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__);                                   \
+        const int slice_ = solver_slice_rows(N_, K_);                                                                 \
+        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);                \
+        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);           \
+        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);                           \
     } while (0)
 
 // expected demand for n rows: largest-remainder rounding of n*q

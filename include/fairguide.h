@@ -270,6 +270,20 @@ int fg_face_loss_bwd(const void* g_loss, const float* feats_ori, const float* db
 /* Test hook: which target every row of the last fg_face_loss_fwd used (>= 0 database row, -2 feats_ori, -1 none). */
 int fg_face_loss_target_rows(const void* workspace, int n, int d, int64_t* target_row, void* stream);
 
+/* f4: bucketed gradient synchronisation, the manual all-reduce of E1:1996-2011 (same loop in E3:2217-2229).
+ * grad_ptrs [n_tensors] (DEVICE array of device addresses of the .grad tensors, all of `dtype`), offsets [n_tensors+1]
+ * int64 (DEVICE; prefix sums of the element counts, offsets[n_tensors] == total).
+ * fg_grad_bucket_pack: bucket [total+1] float32 receives the gradients back to back and, in the last slot, the number of
+ *   non-finite values found (also written to nonfinite_count, int32 on the device) -- the reference's
+ *   `torch.isfinite(p.grad).all()` for every tensor, without a host round trip per tensor.  The caller all-reduces the
+ *   bucket (SUM), which also sums the counts over the ranks.
+ * fg_grad_bucket_unpack: p.grad = bucket / divisor_a / divisor_b (num_processes, N_backward), rounded like the two eager
+ *   divisions. */
+int fg_grad_bucket_pack(const uint64_t* grad_ptrs, const int64_t* offsets, int n_tensors, int64_t total, float* bucket,
+                        int32_t* nonfinite_count, int dtype, void* stream);
+int fg_grad_bucket_unpack(const uint64_t* grad_ptrs, const int64_t* offsets, int n_tensors, int64_t total,
+                          const float* bucket, double divisor_a, double divisor_b, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,3 +48,29 @@ def evaluate_metrics(probs_gender_all, probs_race_all, probs_age_all=None):
         a0, a1 = (pa == 0).float().mean().item(), (pa == 1).float().mean().item()
         out += [a0, a1, (a.max(dim=-1).values < 0.8).float().mean().item(), (abs(a0 - 0.75) + abs(a1 - 0.25)) / 2]
     return tuple(out)
+
+
+# ----------------------------------------------------------------------------- f4: consumer side
+def adjusted_dft_grad_coefs(alphas_cumprod, alphas, timesteps):
+    """E1:1104-1109 (inside generate_image_w_gradient)."""
+    import math
+    grad_coefs = []
+    for t in timesteps:
+        grad_coefs.append(alphas_cumprod[t].sqrt().item() * (1 - alphas_cumprod[t]).sqrt().item() / (1 - alphas[t].item()))
+    grad_coefs = np.array(grad_coefs)
+    grad_coefs /= (math.prod(grad_coefs) ** (1 / len(grad_coefs)))
+    return grad_coefs
+
+
+def allreduce_average_gradients(grads_per_rank, n_backward):
+    """E1:1999-2011 for a simulated world: ``grads_per_rank[r][k]`` = rank r's gradient of parameter k.  Returns the list
+    every rank ends up with and the per-rank ``grad_is_finite`` flags (checked BEFORE the all-reduce, like the reference)."""
+    world = len(grads_per_rank)
+    finite = [all(bool(torch.isfinite(g).all()) for g in grads) for grads in grads_per_rank]
+    out = []
+    for k in range(len(grads_per_rank[0])):
+        s = grads_per_rank[0][k].clone()
+        for r in range(1, world):
+            s = s + grads_per_rank[r][k]                 # all_reduce(SUM)
+        out.append(s / world / n_backward)
+    return out, finite

@@ -154,6 +154,25 @@ def main():
         lm = ((oalign.TEMPLATE_112 - 56.0) @ (R.T * s) + [[90, 70], [30, 120], [150, 80]][c] + rng.normal(size=(5, 2))).astype(np.float32)
         res = fn(img, lm)
         out[f"align_img_{c}"], out[f"align_lm_{c}"], out[f"align_out_{c}"] = img.numpy(), lm, res.numpy()
+    # ---- adjusted-DFT gradient coefficients (E1:1104-1109): the statements that build grad_coefs inside generate_image_w_gradient
+    fn_node = find_function(tree, "generate_image_w_gradient")
+    stmts = []
+    for node in fn_node.body:
+        seg = ast.get_source_segment(open(os.path.join(a.ref, E1)).read(), node) or ""
+        if "grad_coefs" in seg and "register_hook" not in seg:
+            stmts.append(node)
+    assert len(stmts) == 4, [ast.dump(n)[:60] for n in stmts]
+    code = compile(ast.Module(body=stmts, type_ignores=[]), "<reference>", "exec")
+    for c, (T, steps) in enumerate([(1000, 20), (1000, 25), (500, 7)]):
+        betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, T, dtype=torch.float32) ** 2        # Stable Diffusion's scaled-linear schedule
+        alphas = 1.0 - betas
+        sched = types.SimpleNamespace(alphas=alphas, alphas_cumprod=torch.cumprod(alphas, dim=0),
+                                      timesteps=torch.linspace(T - 1, 0, steps).round().long())
+        ns = {"noise_scheduler": sched, "np": np, "math": math}
+        exec(code, ns)
+        out[f"dft_alphas_{c}"], out[f"dft_alphas_cumprod_{c}"] = sched.alphas.numpy(), sched.alphas_cumprod.numpy()
+        out[f"dft_timesteps_{c}"], out[f"dft_coefs_{c}"] = sched.timesteps.numpy(), np.asarray(ns["grad_coefs"], dtype=np.float64)
+    out["dft_n_cases"] = np.array(3)
     np.savez_compressed(os.path.join(HERE, "nextrows.npz"), **out)
     print("wrote nextrows.npz:", sorted(out))
 

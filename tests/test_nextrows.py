@@ -152,3 +152,70 @@ def test_gpu_race_assignment_no_faces():
     p = torch.full((5, 4), -1.0).cuda()
     t, u = fg.generate_dynamic_targets_race(p, True)
     assert (t == -1).all() and (u == -1).all()
+
+
+# ----------------------------------------------------------------------------- f4: adjusted-DFT coefficients, bucketed gradient sync
+def test_adjusted_dft_coefs_golden():
+    """Oracle and product host code against the reference's own statements (E1:1104-1109)."""
+    import fairguide as fg
+    from oracle import nextrows
+    for c in range(int(GOLD["dft_n_cases"])):
+        ac, al = torch.tensor(GOLD[f"dft_alphas_cumprod_{c}"]), torch.tensor(GOLD[f"dft_alphas_{c}"])
+        ts = torch.tensor(GOLD[f"dft_timesteps_{c}"])
+        want = GOLD[f"dft_coefs_{c}"]
+        assert np.array_equal(nextrows.adjusted_dft_grad_coefs(ac, al, ts), want)
+        assert np.array_equal(fg.adjusted_dft_grad_coefs(ac, al, ts), want)
+        np.testing.assert_allclose(np.prod(want) ** (1 / len(want)), 1.0, rtol=1e-12)
+    assert fg.make_grad_hook(0.5)(torch.tensor([2.0, 4.0])).tolist() == [1.0, 2.0]
+
+
+def test_grad_bucket_layout():
+    import fairguide as fg
+    assert fg.GradBucket.layout([4, 1, 7]) == [0, 4, 5, 12]
+    assert fg.GradBucket.layout([]) == [0]
+
+
+def _lora_like_grads(seed, dtype, n_tensors=37):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(50, 320 + 64 * (k % 5)) if k % 2 == 0 else (320 + 64 * (k % 5), 50) for k in range(n_tensors)] + [(7,), (1,)]
+    return [torch.randn(*s, generator=g).to(dtype) * 10 ** float(torch.randint(-3, 2, (1,), generator=g)) for s in shapes]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dname", ["float32", "bfloat16"])
+def test_gpu_grad_bucket_vs_oracle(dname):
+    """Two simulated ranks on one GPU: pack each rank's gradients, add the buckets (what the all-reduce does), unpack with
+    the two divisors; against the per-tensor loop of the reference."""
+    import fairguide as fg
+    from oracle import nextrows
+    dt = DTYPES[dname]
+    ga, gb = _lora_like_grads(1, dt), _lora_like_grads(2, dt)
+    want, finite = nextrows.allreduce_average_gradients([[g.float() for g in ga], [g.float() for g in gb]], 3)
+    pa = [torch.nn.Parameter(torch.zeros_like(g).cuda()) for g in ga]
+    pb = [torch.nn.Parameter(torch.zeros_like(g).cuda()) for g in gb]
+    for p, g in zip(pa + pb, ga + gb):
+        p.grad = g.clone().cuda()
+    A, B = fg.GradBucket(pa), fg.GradBucket(pb)
+    A.pack(); B.pack()
+    assert int(A.nonfinite.item()) == 0 and A.bucket[A.total].item() == 0
+    flat = torch.cat([g.flatten().float() for g in ga])
+    assert torch.equal(A.bucket[:-1].cpu(), flat)                                  # pack is a pure copy
+    A.bucket.add_(B.bucket)
+    A.unpack(2, 3)
+    for p, w in zip(pa, want):
+        if dt == torch.float32:
+            # (x * (1/2)) * (1/3) in fp32 (ATen multiplies by the reciprocal of a scalar divisor) vs the oracle's two divisions
+            np.testing.assert_allclose(p.grad.cpu().numpy(), w.numpy(), rtol=3e-7, atol=0)
+        else:
+            np.testing.assert_allclose(p.grad.float().cpu().numpy(), w.numpy(), rtol=2e-2, atol=0)
+    # non-finite gradients are counted, and the count travels in the last slot of the bucket
+    pb[3].grad[0, 5] = float("inf"); pb[10].grad[2, 2] = float("nan")
+    B.pack()
+    assert int(B.nonfinite.item()) == 2 and B.bucket[B.total].item() == 2.0
+    # world size 1 through the drop-in entry point
+    for p, g in zip(pa, ga):
+        p.grad = g.clone().cuda()
+    assert fg.allreduce_average_gradients(pa, n_backward=4) is True
+    np.testing.assert_allclose(pa[0].grad.float().cpu().numpy(), (ga[0].float() / 1 / 4).numpy(), rtol=1e-2 if dt != torch.float32 else 3e-7)
+    ok, total = B.sync(num_processes=1, n_backward=1)
+    assert ok is False and total == 2
