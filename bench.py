@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96, help="images per step of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a step from Python instead of replaying a CUDA graph")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's image count per GPU (default); strong: that count in total, sharded")
     a = ap.parse_args()
@@ -236,10 +237,12 @@ def main():
         probe.enabled = True
         c0 = dict(_lib.CALLS)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures the timed steps only
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        torch.cuda.profiler.stop()
         barrier()
         probe.enabled = False
         ms = e0.elapsed_time(e1)
@@ -255,14 +258,32 @@ def main():
         sampler.start()
     result = {}
 
-    def step_resident():
+    def step_eager():
         result["out"] = path.step(batch, num_valid=num_valid, probe=probe)
 
-    ms_step, calls = timed(step_resident, a.steps, a.warmup)
-    clocks = sampler.summary() if sampler else None
-    launches = sum(_lib.KERNELS_PER_CALL.get(k, 1) * v for k, v in calls.items())
-    launches += calls.get("fg_ot_plan_counts", 0) * _lib.ot_levels(num_valid)
+    # the timed step: one CUDA-graph replay of GuidancePath.step (the same launches, enqueued by one driver call); the eager
+    # loop below it supplies the per-stage CUDA events and the launch count (events cannot be read back from a graph)
+    captured, graph_note = None, "off (--no-graph)"
+    if not a.no_graph:
+        try:
+            captured = pipeline.CapturedStep(path, batch, num_valid)
+            graph_note = "on"
+        except Exception as ex:                                    # noqa: BLE001  (keep measuring, say why)
+            captured, graph_note = None, f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"
+            torch.cuda.synchronize()
+
+    def step_resident():
+        result["out"] = captured.replay() if captured is not None else path.step(batch, num_valid=num_valid)
+
+    ms_eager, calls = timed(step_eager, max(3, a.steps // 2), a.warmup)
+    launches_per_step = (sum(_lib.KERNELS_PER_CALL.get(k, 1) * v for k, v in calls.items())
+                         + calls.get("fg_ot_plan_counts", 0) * _lib.ot_levels(num_valid)) // max(3, a.steps // 2)
     stage_ms = {k: probe.mean_ms(k) for k in ("sample_fwd", "assign", "image_grad")}
+    if sampler:
+        sampler.rows.clear()
+    ms_step, _ = timed(step_resident, a.steps, a.warmup)
+    clocks = sampler.summary() if sampler else None
+    launches = launches_per_step * a.steps
     value = n_global / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers
@@ -280,6 +301,21 @@ def main():
                     "targets": [torch.empty(n_local, dtype=torch.int64).pin_memory() for _ in range(cfg.n_attr)]}
         d2h = 4 + 8 * n_local * cfg.n_attr
 
+        captured_e2e = None
+        if captured is not None:
+            for k, v in host.items():                              # real values in the staging buffers before they are captured
+                if torch.is_tensor(v):
+                    stage[k].copy_(v)
+                elif isinstance(v, list):
+                    for d, s_ in zip(stage[k], v):
+                        d.copy_(s_)
+            torch.cuda.synchronize()
+            try:
+                captured_e2e = pipeline.CapturedStep(path, stage, num_valid)      # the staging buffers are the graph's inputs
+            except Exception:                                      # noqa: BLE001
+                captured_e2e = None
+                torch.cuda.synchronize()
+
         def step_e2e():
             for k, v in host.items():
                 if torch.is_tensor(v):
@@ -287,7 +323,7 @@ def main():
                 elif isinstance(v, list):
                     for d, s in zip(stage[k], v):
                         d.copy_(s, non_blocking=True)
-            out = path.step(stage, num_valid=num_valid)
+            out = captured_e2e.replay() if captured_e2e is not None else path.step(stage, num_valid=num_valid)
             out_host["loss"].copy_(out["loss_mean"], non_blocking=True)
             for d, s in zip(out_host["targets"], out["targets"]):
                 d.copy_(s, non_blocking=True)
@@ -345,9 +381,8 @@ def main():
                        "faces_in_batch": num_valid, "parallelism": f"dp{world}",
                        "backbone": "excluded (stand-in pooled features and chip gradient; SURVEY.md 8d)",
                        "l2": f"inputs larger than L2 ({(fwd_b + bwd_b) * n_local / 1e6:.0f} MB touched per step per GPU vs 126 MB)"},
-            "stage_ms": stage_ms, "gpu_launches": launches * a.steps // a.steps, "gpu_launches_per_step": launches // a.steps,
+            "stage_ms": stage_ms, "ms_per_step_eager": ms_eager, "cuda_graph": graph_note, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
-    line["gpu_launches"] = launches
     if with_backbone:
         line["with_backbone"] = with_backbone
     print(json.dumps(line))

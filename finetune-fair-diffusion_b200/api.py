@@ -454,4 +454,10 @@ def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_cl
         tensor, acc, return_tensor_other_processes)
     ns.stage_detector_input = stage_detector_input
     ns.get_evaluate_metrics = get_evaluate_metrics
+    ns.generate_dynamic_targets_race = generate_dynamic_targets_race                 # exp-6
+    ns.image_pipeline, ns.aligned_face_chips = image_pipeline, aligned_face_chips   # E1:292
+    ns.get_face_feats, ns.FaceFeatsModel, ns.face_realism_loss = get_face_feats, FaceFeatsModel, face_realism_loss
+    from . import sync
+    ns.make_grad_hook, ns.adjusted_dft_grad_coefs = sync.make_grad_hook, sync.adjusted_dft_grad_coefs
+    ns.allreduce_average_gradients = sync.allreduce_average_gradients
     return ns

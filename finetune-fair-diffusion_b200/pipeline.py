@@ -231,6 +231,31 @@ class GuidancePath:
                     bbox_ori=bbox_ori)
 
 
+class CapturedStep:
+    """``GuidancePath.step`` recorded once into a CUDA graph and replayed: the ~15 launches (and, with several ranks, the
+    two collectives) of a step are enqueued by one driver call, which removes the host-side gaps between the small
+    kernels.  The batch tensors are static: refresh them in place (``copy_``) before ``replay``; ``out`` holds the
+    step's result tensors, overwritten by every replay.  The Monte-Carlo draws advance with every replay (torch's
+    graph-safe generator), exactly like consecutive eager steps."""
+
+    def __init__(self, path, batch, num_valid):
+        self.path, self.batch = path, batch
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up off the capturing stream (allocator, lazy module loads)
+            for _ in range(2):
+                path.step(batch, num_valid=num_valid)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = path.step(batch, num_valid=num_valid)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 def smoke_check(device="cuda:0"):
     """One small invocation of the whole path on the GPU, checked stage by stage against the oracle."""
     import numpy as np

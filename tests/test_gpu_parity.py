@@ -518,3 +518,38 @@ def test_epilogue_matches_torch_cuda_ops(fg):
 def test_pipeline_smoke_vs_oracle(fg):
     from fairguide import pipeline
     assert pipeline.smoke_check("cuda:0")
+
+
+@pytest.mark.parametrize("kind", ["gender", "gender_race_age"])
+def test_captured_step_replays_the_eager_step(fg, kind):
+    """CUDA-graph replay of GuidancePath.step == the eager step: bit-identical outputs for the RNG-free E1 rule (for the
+    Monte-Carlo kinds everything up to the assignment, plus the plan invariants), and a replay sees in-place updates of the
+    batch tensors."""
+    from fairguide import pipeline
+    cfg = pipeline.GuidanceConfig(kind=kind, num_samples_per_device=12)
+    dt = torch.bfloat16
+    head = pipeline.make_head_weights(cfg, dt, DEV)
+    batch = pipeline.synth_batch_device(48, cfg, dt, torch.device(DEV), seed=11, H=512, W=512)
+    nv = int((batch["counts"] > 0).sum())
+    path = pipeline.GuidancePath(cfg, head)
+    eager = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in path.step(batch, num_valid=nv).items()}
+    cap = pipeline.CapturedStep(path, batch, nv)
+    out = cap.replay()
+    torch.cuda.synchronize()
+    same = ["indicators", "boxes", "chips", "small", "logits", "probs"] + (["loss", "g_images", "g_pooled"] if kind == "gender" else [])
+    for k in same:
+        a, b = eager[k], out[k]
+        if isinstance(a, (list, tuple)):
+            assert all(torch.equal(x, y) for x, y in zip(a, b)), k
+        else:
+            assert torch.equal(a, b), k
+    if kind == "gender":
+        assert torch.equal(eager["targets"][0], out["targets"][0])
+    else:
+        assert int(out["counts"].sum()) == nv * cfg.num_samples_per_device          # every row assigned once per draw
+    # new data in the same buffers
+    batch["images"].mul_(0.5)
+    out2 = cap.replay()
+    ref2 = path.step(batch, num_valid=nv)
+    torch.cuda.synchronize()
+    assert torch.equal(out2["chips"], ref2["chips"]) and torch.equal(out2["small"], ref2["small"])
