@@ -54,14 +54,30 @@ def gather_probs(face_indicators, probs, group=None):
     widths = [p.shape[1] for p in probs]
     if world == 1:
         return face_indicators.clone(), [p.detach().clone() for p in probs]
+    packed = pack_probs(face_indicators, probs)
+    out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    all_gather_packed(out, packed, group)
+    return unpack_probs(out, widths)
+
+
+def pack_probs(face_indicators, probs):
+    """[n, 1+sum(widths)] row block {indicator, probs_*} in the probs dtype: what one rank contributes to the all-gather."""
     dt = probs[0].dtype
-    packed = torch.cat([face_indicators.to(dt).unsqueeze(1)] + [p.detach() for p in probs], dim=1).contiguous()
-    out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=dt, device=packed.device)
+    return torch.cat([face_indicators.to(dt).unsqueeze(1)] + [p.detach() for p in probs], dim=1).contiguous()
+
+
+def all_gather_packed(out, packed, group=None):
+    """The collective itself, on caller-owned buffers (static across CUDA-graph replays)."""
     tdist.all_gather_into_tensor(out, packed, group=group)
-    ind = out[:, 0] != 0
+    return out
+
+
+def unpack_probs(gathered, widths):
+    """Inverse of pack_probs on the gathered [N, 1+sum(widths)] buffer -> (face_indicators_all bool [N], [probs_all ...])."""
+    ind = gathered[:, 0] != 0
     cols, res = 1, []
     for w in widths:
-        res.append(out[:, cols:cols + w].contiguous())
+        res.append(gathered[:, cols:cols + w].contiguous())
         cols += w
     return ind, res
 

@@ -168,35 +168,49 @@ class GuidancePath:
     def __init__(self, cfg: GuidanceConfig, head_weights, backbone=None, group=None):
         self.cfg, self.head, self.backbone, self.group = cfg, head_weights, backbone, group
 
+    # The step is written as three local phases around the two exchanges of the path, so that the
+    # phases can be recorded into CUDA graphs while the collectives stay ordinary NCCL calls between them.
     @torch.no_grad()
-    def step(self, batch, rand_tensors=None, num_valid: Optional[int] = None, probe=None):
-        """``probe``: optional object with begin(name)/end(name) (bench.py records CUDA events on the
-        current stream around the named stages)."""
+    def phase_a(self, batch, probe=None):
+        """Stages 1-4 on this rank's images, plus the packed {indicator, probs} row block the all-gather sends."""
         cfg = self.cfg
         P = probe if probe is not None else _NullProbe
         widths, col_start, k_head, K, e1_rule = KINDS[cfg.kind]
         images = batch["images"]
         n, _, H, W = images.shape
-        world, rank = fdist._world(self.group)
-
-        # 1-2
         ind, boxes = ops.select_expand_boxes(batch["cand_boxes"], batch["counts"], H, cfg.expand_coef, 1.0, -1)
         P.begin("sample_fwd")
         chips, small = ops.crop_resize_fwd(images, boxes, ind, (cfg.size_face,) * 2, (cfg.img_size_small,) * 2, cfg.fill_value)
         P.end("sample_fwd")
-        # 3-4
         pooled = batch["pooled"] if self.backbone is None else self.backbone(chips)
         logits, hidden = ops.head_fwd(pooled, *self.head)
         preds, probs, logits_attr = ops.head_attributes(logits, None, ind, n, col_start, widths, cfg.fill_value, images.dtype)
-        # 5
-        P.begin("assign")
-        ind_all, probs_all = fdist.gather_probs(ind, probs, self.group)
-        # 6
-        if cfg.kind == "gender":
-            t_all, _ = ops.assign_rank_binom(probs_all[0], cfg.target_ratio, cfg.uncertainty_threshold, True)
-            targets_all = [t_all]
-            counts = None
+        st = dict(ind=ind, boxes=boxes, chips=chips, small=small, logits=logits, hidden=hidden, preds=preds, probs=probs,
+                  logits_attr=logits_attr)
+        world, _ = fdist._world(self.group)
+        if world > 1:
+            st["packed"] = fdist.pack_probs(ind, probs)
+            st["gathered"] = torch.empty((world * n, st["packed"].shape[1]), dtype=st["packed"].dtype, device=images.device)
+        return st
+
+    def exchange_1(self, st):
+        """Stage 5: the all-gather (no-op with one rank)."""
+        if "packed" in st:
+            fdist.all_gather_packed(st["gathered"], st["packed"], self.group)
+
+    @torch.no_grad()
+    def phase_b(self, st, batch, rand_tensors=None, num_valid=None):
+        """Stage 6 up to the second exchange: this rank's Monte-Carlo plan counts over the gathered rows."""
+        cfg = self.cfg
+        widths, col_start, k_head, K, e1_rule = KINDS[cfg.kind]
+        images = batch["images"]
+        if "gathered" in st:
+            ind_all, probs_all = fdist.unpack_probs(st["gathered"], widths)
         else:
+            ind_all, probs_all = st["ind"], st["probs"]
+        st["ind_all"], st["probs_all"] = ind_all, probs_all
+        st["counts"] = None
+        if cfg.kind != "gender":
             n_all = ind_all.shape[0]
             nv = num_valid if num_valid is not None else int(ind_all.sum().item())
             ws = ops.OtWorkspace(n_all, K, cfg.num_samples_per_device, images.device)
@@ -206,29 +220,62 @@ class GuidancePath:
                 rand_tensors = tuple(torch.rand([len(widths), cfg.num_samples_per_device, nv], dtype=images.dtype,
                                                 device=images.device).unbind(0))
             pa = probs_all[2] if len(widths) == 3 else None
-            counts = ops.ot_plan_counts(probs_all[0], probs_all[1], pa, rand_tensors or (), nv, ws)
-            if nv > 0:
-                fdist.all_reduce_counts(counts, self.group)
-            targets_all, _ = ops.ot_targets(counts, probs_all[0], probs_all[1], nv, ws, cfg.uncertainty_threshold, True)
+            st["counts"] = ops.ot_plan_counts(probs_all[0], probs_all[1], pa, rand_tensors or (), nv, ws)
+            st["nv"], st["ws"] = nv, ws
+        return st
+
+    def exchange_2(self, st):
+        """The all-reduce of the plan counts (E3:1535; no-op with one rank or for the E1 rule)."""
+        if st.get("counts") is not None and st["nv"] > 0:
+            fdist.all_reduce_counts(st["counts"], self.group)
+
+    @torch.no_grad()
+    def phase_c(self, st, batch, probe=None, close_assign=False):
+        """Rest of stage 6 (targets, threshold, local slice) and stages 7-10."""
+        cfg = self.cfg
+        P = probe if probe is not None else _NullProbe
+        widths, col_start, k_head, K, e1_rule = KINDS[cfg.kind]
+        images = batch["images"]
+        n, _, H, W = images.shape
+        _, rank = fdist._world(self.group)
+        ind, boxes, probs_all = st["ind"], st["boxes"], st["probs_all"]
+        if cfg.kind == "gender":
+            t_all, _ = ops.assign_rank_binom(probs_all[0], cfg.target_ratio, cfg.uncertainty_threshold, True)
+            targets_all = [t_all]
+        else:
+            targets_all, _ = ops.ot_targets(st["counts"], probs_all[0], probs_all[1], st["nv"], st["ws"], cfg.uncertainty_threshold, True)
         targets = [t[n * rank:n * (rank + 1)] for t in targets_all]
-        P.end("assign")
+        if close_assign:
+            P.end("assign")
         # 7-9: hook factors, then CE of every attribute + loss assembly + gradient wrt the head logits in one launch
         bbox_ori = batch["bbox_ori"] if "bbox_ori" in batch else torch.where(ind.unsqueeze(1), boxes + batch["bbox_jitter"], boxes)
         region, scale, dyn_w = ops.guidance_factors(ind, boxes, bbox_ori, targets, batch["preds_ori"],
                                                     cfg.factors2[:len(widths)], cfg.factors1[:len(widths)], e1_rule, H, W)
         loss_fair, loss, g_logits = ops.fair_loss_fused(
-            logits_attr, targets, col_start, k_head, ind, 1.0 / n, dyn_w, batch["loss_clip"], batch["loss_dino"],
+            st["logits_attr"], targets, col_start, k_head, ind, 1.0 / n, dyn_w, batch["loss_clip"], batch["loss_dino"],
             batch["loss_face"], cfg.weight_loss_img, cfg.weight_loss_face, -1.0)
-        g_pooled = ops.head_bwd(g_logits, hidden, self.head[0], self.head[2])
+        g_pooled = ops.head_bwd(g_logits, st["hidden"], self.head[0], self.head[2])
         # 10
         P.begin("image_grad")
         g_images = ops.image_grad(batch["g_chips"], batch["g_small"], boxes, ind, region, scale, tuple(images.shape),
                                   images.dtype, images.device)
         P.end("image_grad")
-        return dict(indicators=ind, boxes=boxes, chips=chips, small=small, logits=logits, preds=preds, probs=probs,
-                    targets=targets, targets_all=targets_all, counts=counts, loss_fair=loss_fair, g_pooled=g_pooled,
-                    region=region, scale=scale, dyn_weights=dyn_w, loss=loss, loss_mean=loss.mean(), g_images=g_images,
-                    bbox_ori=bbox_ori)
+        return dict(indicators=ind, boxes=boxes, chips=st["chips"], small=st["small"], logits=st["logits"], preds=st["preds"],
+                    probs=st["probs"], targets=targets, targets_all=targets_all, counts=st["counts"], loss_fair=loss_fair,
+                    g_pooled=g_pooled, region=region, scale=scale, dyn_weights=dyn_w, loss=loss, loss_mean=loss.mean(),
+                    g_images=g_images, bbox_ori=bbox_ori)
+
+    @torch.no_grad()
+    def step(self, batch, rand_tensors=None, num_valid: Optional[int] = None, probe=None):
+        """``probe``: optional object with begin(name)/end(name) (bench.py records CUDA events on the
+        current stream around the named stages)."""
+        P = probe if probe is not None else _NullProbe
+        st = self.phase_a(batch, probe)
+        P.begin("assign")
+        self.exchange_1(st)
+        self.phase_b(st, batch, rand_tensors, num_valid)
+        self.exchange_2(st)
+        return self.phase_c(st, batch, probe, close_assign=True)
 
 
 class CapturedStep:
@@ -240,6 +287,7 @@ class CapturedStep:
 
     def __init__(self, path, batch, num_valid):
         self.path, self.batch = path, batch
+        world, _ = fdist._world(path.group)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                       # warm-up off the capturing stream (allocator, lazy module loads)
@@ -247,12 +295,36 @@ class CapturedStep:
                 path.step(batch, num_valid=num_valid)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = path.step(batch, num_valid=num_valid)
+        self.graphs = []
+        if world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = path.step(batch, num_valid=num_valid)
+            self.graphs = [g]
+            self.state = None
+        else:
+            # one graph per local phase; the two collectives run between the replays as ordinary NCCL calls on the
+            # static buffers the graphs read and write
+            ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                st = path.phase_a(batch)
+            path.exchange_1(st)
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                path.phase_b(st, batch, None, num_valid)
+            path.exchange_2(st)
+            with torch.cuda.graph(gc, pool=ga.pool()):
+                self.out = path.phase_c(st, batch)
+            self.graphs, self.state = [ga, gb, gc], st
 
     def replay(self):
-        self.graph.replay()
+        if self.state is None:
+            self.graphs[0].replay()
+        else:
+            self.graphs[0].replay()
+            self.path.exchange_1(self.state)
+            self.graphs[1].replay()
+            self.path.exchange_2(self.state)
+            self.graphs[2].replay()
         return self.out
 
 
