@@ -199,6 +199,8 @@ def main():
         print(json.dumps(line))
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     import fairguide
