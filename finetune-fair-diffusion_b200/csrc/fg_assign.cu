@@ -58,6 +58,7 @@ struct OtWs {
     int* pos;           // [n_all] original row -> compacted row or -1
     double* M;          // [n_valid, K]
     float* Mf;          // [K, n_valid]  fp32, class-major (the solver's search / screening copy)
+    int* Mk;            // [K, n_valid]  integer search keys of the same costs (cost_key), class-major
     int* hist;          // [S, KP]
     double* prices;     // [KP]
     uint8_t* sigma0;    // [n_valid]
@@ -76,12 +77,35 @@ static OtWs ot_carve(void* base, int n_all, int K, int S) {
     w.pos = (int*)take((size_t)n_all * sizeof(int));
     w.M = (double*)take((size_t)n_all * K * sizeof(double));
     w.Mf = (float*)take((size_t)n_all * K * sizeof(float));
+    w.Mk = (int*)take((size_t)n_all * K * sizeof(int));
     w.hist = (int*)take((size_t)(S > 0 ? S : 1) * KP * sizeof(int));
     w.prices = (double*)take(KP * sizeof(double));
     w.sigma0 = (uint8_t*)take((size_t)n_all);
     w.members = (uint16_t*)take(solver_members_bytes(n_all, K, S));
     w.total = off;
     return w;
+}
+
+// Integer search key of a cost for the price search: the cost in units of 2^-22 (costs are norms of probability
+// differences, < 4; the fp32 spacing at 2..4 is exactly one unit), shifted left by four with the class index in the low
+// bits.  Subtracting a price key (a multiple of 16) keeps the class bits, so the cheapest class of a row is ONE integer
+// minimum over its K keys -- value and index together, ties to the lower class -- instead of a compare/select tree that
+// carries the index separately (~30 instead of ~70 instructions per row at K = 16).  The search is a heuristic (any
+// prices are admissible), so the quantisation only costs an occasional extra repair step.
+constexpr float KEY_SCALE = 4194304.f;             // 2^22
+__device__ __forceinline__ int cost_key(float x, int l) { return (__float2int_rn(fminf(fmaxf(x, 0.f), 16.f) * KEY_SCALE) << 4) | l; }
+__device__ __forceinline__ int price_key(float p) { return __float2int_rn(fminf(fmaxf(p, -8.f), 8.f) * KEY_SCALE) << 4; }
+__device__ __forceinline__ float price_of_key(int pk) { return (float)(pk >> 4) * (1.f / KEY_SCALE); }
+__device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
+template <int KK>
+__device__ __forceinline__ int min_key(const int (&y)[KK]) {
+    if (KK == 16) {
+        const int a0 = min3(y[0], y[1], y[2]), a1 = min3(y[3], y[4], y[5]), a2 = min3(y[6], y[7], y[8]);
+        const int a3 = min3(y[9], y[10], y[11]), a4 = min3(y[12], y[13], y[14]);
+        return min(min3(a0, a1, a2), min3(a3, a4, y[15]));
+    }
+    const int a0 = min3(y[0], y[1], y[2]), a1 = min3(y[3], y[4], y[5]);
+    return min3(a0, a1, min(y[6], y[KK - 1]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,14 +183,14 @@ __device__ __forceinline__ void cost_row(const T* __restrict__ pg, const T* __re
 template <typename T>
 __global__ void __launch_bounds__(256)
 cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
-                 const int* __restrict__ idx, int N, int K, double* __restrict__ M, float* __restrict__ Mf, int cost_blocks,
+                 const int* __restrict__ idx, int N, int K, double* __restrict__ M, float* __restrict__ Mf, int* __restrict__ Mk, int cost_blocks,
                  const T* __restrict__ rg, const T* __restrict__ rr, const T* __restrict__ ra, int S,
                  int* __restrict__ hist, int32_t* __restrict__ counts_to_zero) {
     if ((int)blockIdx.x < cost_blocks) {
         int r = blockIdx.x * 256 + threadIdx.x;
         if (r < N) {
             cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
-            if (Mf) for (int j = 0; j < K; j++) Mf[(size_t)j * N + r] = (float)M[(size_t)r * K + j];
+            if (Mf) for (int j = 0; j < K; j++) { const float c = (float)M[(size_t)r * K + j]; Mf[(size_t)j * N + r] = c; Mk[(size_t)j * N + r] = cost_key(c, j); }
             if (counts_to_zero) for (int j = 0; j < K; j++) counts_to_zero[(size_t)r * K + j] = 0;
         }
         return;
@@ -471,53 +495,55 @@ __device__ __forceinline__ void price_search(SolverSmem& sm, const float* __rest
 }
 
 // Register-resident variant of the price search for problems with at most RPT rows per thread (N <= RPT * 512, RPT <= 4):
-// the thread's rows of the fp32 cost copy are loaded once and stay in registers for all rounds, the per-thread class
-// histogram uses 8-bit fields (32 lanes x RPT rows <= 128 per class and warp), so four REDUX sums give the warp counts
-// with no unpacking, and the K prices reach the lanes through a per-warp shared-memory row instead of K shuffles.
+// the thread's rows are loaded once as integer search keys (cost_key) and stay in registers for all rounds; a row's
+// cheapest class is one integer minimum (min_key), the per-thread class histogram uses 4-bit fields of one 64-bit word
+// (<= 4 rows per thread), widened to 8-bit fields for the four REDUX warp sums (<= 128 rows per class and warp), and the K
+// price keys reach the lanes through a per-warp shared-memory row instead of K shuffles.
 template <int KK, int RPT>
 __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __restrict__ Mf, int N, int dual_iters, float step0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
     int my_prev = 0, best_resid = 0x7fffffff;
     const int my_b = lane < KK ? sm.b[lane] : 0;
-    float x[RPT][KK];
+    int x[RPT][KK];
     bool have[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
         const int i = tid + r * SOLVER_THREADS;
         have[r] = i < N;
 #pragma unroll
-        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? Mf[l * N + i] : 0.f;
+        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? cost_key(Mf[l * N + i], l) : 0;
     }
-    float* wp = sm.wprice[warp];
+    int* wp = reinterpret_cast<int*>(sm.wprice[warp]);
     for (int it = 0; it <= dual_iters; it++) {
-        if (lane < KK) wp[lane] = my_price;
+        const int my_pk = price_key(my_price);
+        if (lane < KK) wp[lane] = my_pk;
         __syncwarp();
-        float pr[KK];
+        int pk[KK];
 #pragma unroll
         for (int l = 0; l < KK; l += 4) {
-            const float4 q = *reinterpret_cast<const float4*>(wp + l);
-            pr[l] = q.x; pr[l + 1] = q.y; pr[l + 2] = q.z; pr[l + 3] = q.w;
+            const int4 q = *reinterpret_cast<const int4*>(wp + l);
+            pk[l] = q.x; pk[l + 1] = q.y; pk[l + 2] = q.z; pk[l + 3] = q.w;
         }
         __syncwarp();
-        unsigned long long hlo = 0ull, hhi = 0ull;          // 8-bit count per class: classes 0-7 / 8-15
+        unsigned long long h = 0ull;                         // 4-bit count per class
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-            float y[KK]; int idx[KK];
+            int y[KK];
 #pragma unroll
-            for (int l = 0; l < KK; l++) { y[l] = x[r][l] - pr[l]; idx[l] = l; }
-#pragma unroll
-            for (int st = 1; st < KK; st *= 2)
-#pragma unroll
-                for (int l = 0; l < KK; l += 2 * st)
-                    if (y[l + st] < y[l]) { y[l] = y[l + st]; idx[l] = idx[l + st]; }      // strict: the lower class wins ties
-            const unsigned long long one = have[r] ? 1ull : 0ull;
-            if (KK <= 8) hlo += one << (8 * idx[0]);
-            else { hlo += (idx[0] < 8 ? one : 0ull) << (8 * (idx[0] & 7)); hhi += (idx[0] < 8 ? 0ull : one) << (8 * (idx[0] & 7)); }
+            for (int l = 0; l < KK; l++) y[l] = x[r][l] - pk[l];
+            const int m = min_key<KK>(y);
+            h += (have[r] ? 1ull : 0ull) << ((m & 15) << 2);
         }
+        // widen: even classes / odd classes of the low and high halves -> 8-bit fields, one REDUX each
+        const unsigned lo = (unsigned)h, hi = (unsigned)(h >> 32);
         unsigned acc[4];
-        acc[0] = __reduce_add_sync(0xffffffffu, (unsigned)hlo); acc[1] = __reduce_add_sync(0xffffffffu, (unsigned)(hlo >> 32));
-        if (KK > 8) { acc[2] = __reduce_add_sync(0xffffffffu, (unsigned)hhi); acc[3] = __reduce_add_sync(0xffffffffu, (unsigned)(hhi >> 32)); }
+        acc[0] = __reduce_add_sync(0xffffffffu, lo & 0x0F0F0F0Fu);            // classes 0,2,4,6
+        acc[1] = __reduce_add_sync(0xffffffffu, (lo >> 4) & 0x0F0F0F0Fu);     // classes 1,3,5,7
+        if (KK > 8) {
+            acc[2] = __reduce_add_sync(0xffffffffu, hi & 0x0F0F0F0Fu);        // classes 8,10,12,14
+            acc[3] = __reduce_add_sync(0xffffffffu, (hi >> 4) & 0x0F0F0F0Fu); // classes 9,11,13,15
+        }
         if (lane == 0) {
 #pragma unroll
             for (int w = 0; w < KK / 4; w++) sm.whist[it & 1][warp][w] = acc[w];
@@ -525,12 +551,13 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
         __syncthreads();
         int cnt = 0;
         if (lane < KK) {
+            const int word = ((lane >> 3) << 1) | (lane & 1), sh = ((lane & 7) >> 1) * 8;
 #pragma unroll
-            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][lane >> 2] >> ((lane & 3) * 8)) & 0xFFu);
+            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][word] >> sh) & 0xFFu);
         }
         const int err = lane < KK ? my_b - cnt : 0;
         const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
-        if (resid < best_resid) { best_resid = resid; my_best = my_price; }
+        if (resid < best_resid) { best_resid = resid; my_best = price_of_key(my_pk); }      // the price the rows actually saw
         if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
         if (lane < KK) {
             const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
@@ -549,8 +576,8 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
 // (as in price_search_reg), the next `slice_rows` rows sit in the shared memory the member lists leave free (class-major
 // slice), the rest is read from global memory.  Histogram and price update as in price_search.
 template <int KK>
-__device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const float* __restrict__ Mf, float* __restrict__ slice,
-                                                    int slice_rows, int N, int dual_iters, float step0) {
+__device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* __restrict__ Mk,
+                                                    int* __restrict__ slice, int slice_rows, int N, int dual_iters, float step0) {
     constexpr int RPT = 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
@@ -559,38 +586,35 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const float*
     const int reg_rows = min(N, RPT * SOLVER_THREADS);
     slice_rows = min(slice_rows, N - reg_rows);
     const int glob_begin = reg_rows + slice_rows;
-    float x[RPT][KK];
+    auto key_at = [&](int l, int i) { return __ldg(Mk + (size_t)l * N + i); };      // (a float fallback in these loops cost 25 %: code size)
+    int x[RPT][KK];
     bool have[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
         const int i = tid + r * SOLVER_THREADS;
         have[r] = i < N;
 #pragma unroll
-        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? __ldg(Mf + (size_t)l * N + i) : 0.f;
+        for (int l = 0; l < KK; l++) x[r][l] = have[r] ? key_at(l, i) : 0;
     }
     for (int e = tid; e < KK * slice_rows; e += SOLVER_THREADS) {
         const int l = e / slice_rows, j = e - l * slice_rows;
-        slice[e] = __ldg(Mf + (size_t)l * N + reg_rows + j);
+        slice[e] = key_at(l, reg_rows + j);
     }
     __syncthreads();
     for (int it = 0; it <= dual_iters; it++) {
-        float pr[KK];
+        const int my_pk = price_key(my_price);
+        int pk[KK];
 #pragma unroll
-        for (int l = 0; l < KK; l++) pr[l] = __shfl_sync(0xffffffffu, my_price, l);
+        for (int l = 0; l < KK; l++) pk[l] = __shfl_sync(0xffffffffu, my_pk, l);
         unsigned acc[KP / 2];
 #pragma unroll
         for (int w = 0; w < KP / 2; w++) acc[w] = 0u;
         unsigned long long h = 0ull; int pending = 0;
-        auto count_row = [&](float (&y)[KK]) {
-            int idx[KK];
+        auto count_row = [&](int (&y)[KK]) {
 #pragma unroll
-            for (int l = 0; l < KK; l++) { y[l] -= pr[l]; idx[l] = l; }
-#pragma unroll
-            for (int st = 1; st < KK; st *= 2)
-#pragma unroll
-                for (int l = 0; l < KK; l += 2 * st)
-                    if (y[l + st] < y[l]) { y[l] = y[l + st]; idx[l] = idx[l + st]; }      // strict: the lower class wins ties
-            h += 1ull << (4 * idx[0]);
+            for (int l = 0; l < KK; l++) y[l] -= pk[l];
+            const int m = min_key<KK>(y);
+            h += 1ull << ((m & 15) << 2);
             if (++pending == 15) {                 // 4-bit fields are full: spill into the 16-bit accumulators
 #pragma unroll
                 for (int w = 0; w < KP / 2; w++) acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
@@ -600,23 +624,23 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const float*
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
             if (have[r]) {
-                float y[KK];
+                int y[KK];
 #pragma unroll
                 for (int l = 0; l < KK; l++) y[l] = x[r][l];
                 count_row(y);
             }
         }
         for (int j = tid; j < slice_rows; j += SOLVER_THREADS) {
-            float y[KK];
+            int y[KK];
 #pragma unroll
             for (int l = 0; l < KK; l++) y[l] = slice[l * slice_rows + j];
             count_row(y);
         }
 #pragma unroll 2
         for (int i = glob_begin + tid; i < N; i += SOLVER_THREADS) {
-            float y[KK];
+            int y[KK];
 #pragma unroll
-            for (int l = 0; l < KK; l++) y[l] = __ldg(Mf + (size_t)l * N + i);
+            for (int l = 0; l < KK; l++) y[l] = key_at(l, i);
             count_row(y);
         }
 #pragma unroll
@@ -636,7 +660,7 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const float*
         }
         const int err = lane < KK ? my_b - cnt : 0;
         const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
-        if (resid < best_resid) { best_resid = resid; my_best = my_price; }
+        if (resid < best_resid) { best_resid = resid; my_best = price_of_key(my_pk); }      // the price the rows actually saw
         if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
         if (lane < KK) {
             const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
@@ -675,7 +699,8 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
                 const double* __restrict__ prices_in, double* __restrict__ prices_out, int dual_iters, double step0,
                 Demand demand_by_value, const int* __restrict__ hist,
                 int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
-                int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global, int slice_rows) {
+                int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global, int slice_rows,
+                const int* __restrict__ Mk_global) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
@@ -735,11 +760,11 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     } else if (MODE == 0 && m_in_smem && N <= 4 * SOLVER_THREADS) {
         if (K == 16) price_search_reg<16, 4>(sm, v.Mf, N, dual_iters, (float)step0);
         else price_search_reg<8, 4>(sm, v.Mf, N, dual_iters, (float)step0);
-    } else if (MODE != 0 && m_in_smem) {
+    } else if (MODE != 0 && m_in_smem && Mk_global) {
         // the shared memory behind the last view holds a slice of the cost copy during the search
-        float* slice = reinterpret_cast<float*>(dyn_smem + (MODE == 1 ? solver_off_M(N, K) : solver_off_members(N)));
-        if (K == 16) price_search_hybrid<16>(sm, v.Mf, slice, slice_rows, N, dual_iters, (float)step0);
-        else price_search_hybrid<8>(sm, v.Mf, slice, slice_rows, N, dual_iters, (float)step0);
+        int* slice = reinterpret_cast<int*>(dyn_smem + (MODE == 1 ? solver_off_M(N, K) : solver_off_members(N)));
+        if (K == 16) price_search_hybrid<16>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0);
+        else price_search_hybrid<8>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0);
     } else if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     else price_search<8>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
@@ -1065,19 +1090,19 @@ static int solver_prepare(int N, int K) {
 
 // fp32 class-major copy of a row-major fp64 cost matrix (fg_ot_solve_single in modes 1 / 2; the plan path gets it from
 // cost_hist_kernel)
-__global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict__ Mf, int N, int K) {
+__global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict__ Mf, int* __restrict__ Mk, int N, int K) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < N * K) { const int i = e / K, l = e - i * K; Mf[(size_t)l * N + i] = (float)M[e]; }
+    if (e < N * K) { const int i = e / K, l = e - i * K; const float c = (float)M[e]; Mf[(size_t)l * N + i] = c; Mk[(size_t)l * N + i] = cost_key(c, l); }
 }
 
-#define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, ...)                                                                      \
+#define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, MK_, ...)                                                                     \
     do {                                                                                                              \
         const int mode_ = solver_mode(N_, K_);                                                                        \
         const int smem_ = solver_smem_bytes(N_, K_);                                                                  \
         const int slice_ = solver_slice_rows(N_, K_);                                                                 \
-        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);                \
-        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);           \
-        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_);                           \
+        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);           \
+        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);      \
+        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);                      \
     } while (0)
 
 // expected demand for n rows: largest-remainder rounding of n*q
@@ -1110,7 +1135,7 @@ static int launch_base(const double* M, const float* Mf, int N, int K, OtWs& w, 
     int rc = solver_prepare(N, K);
     if (rc) return rc;
     Demand d; expected_demand(N, K, &d);
-    FG_SOLVE_LAUNCH(N, K, 1, st, M, Mf, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0, d, nullptr, nullptr, nullptr, w.status, 2,
+    FG_SOLVE_LAUNCH(N, K, 1, st, (Mf ? w.Mk : nullptr), M, Mf, N, K, nullptr, w.prices, BASE_DUAL_ITERS, BASE_STEP0, d, nullptr, nullptr, nullptr, w.status, 2,
                     1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
@@ -1128,7 +1153,7 @@ constexpr double RACE_PAD = 1.0e3;
 // fp32 einsum of the fp32 probabilities (numpy reduces the 4 products pairwise) and X.Y^T is exact in fp64.
 template <typename T>
 __global__ void __launch_bounds__(256)
-race_cost_kernel(const T* __restrict__ pr, const int* __restrict__ idx, int N, double* __restrict__ M, float* __restrict__ Mf) {
+race_cost_kernel(const T* __restrict__ pr, const int* __restrict__ idx, int N, double* __restrict__ M, float* __restrict__ Mf, int* __restrict__ Mk) {
     const int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= N) return;
     const int i = idx[r];
@@ -1144,6 +1169,7 @@ race_cost_kernel(const T* __restrict__ pr, const int* __restrict__ idx, int N, d
         }
         M[(size_t)r * 8 + j] = c;
         Mf[(size_t)j * N + r] = (float)c;
+        Mk[(size_t)j * N + r] = cost_key((float)c, j);
     }
 }
 
@@ -1209,7 +1235,7 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int cost_blocks = (n_valid + 255) / 256;
     FG_DISPATCH_DTYPE(dtype, T,
         cost_hist_kernel<T><<<cost_blocks + S, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age,
-            w.idx, n_valid, K, w.M, w.Mf, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist, counts));
+            w.idx, n_valid, K, w.M, w.Mf, w.Mk, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist, counts));
     FG_LAUNCH_CHECK();
     if (S == 0) return FG_OK;
     // Every draw runs the whole price search from zero prices in its own CTA.  (A serial "base" solve of the expected
@@ -1218,7 +1244,7 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     int rc = solver_prepare(n_valid, K);
     if (rc) return rc;
     Demand none = {};
-    FG_SOLVE_LAUNCH(n_valid, K, S, st, w.M, w.Mf, n_valid, K, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, w.hist, nullptr, counts,
+    FG_SOLVE_LAUNCH(n_valid, K, S, st, w.Mk, w.M, w.Mf, n_valid, K, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, w.hist, nullptr, counts,
                     w.status, 3, 1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
@@ -1255,12 +1281,12 @@ extern "C" int fg_ot_solve_single(const double* M, int n, int K, const int64_t* 
     if (e != cudaSuccess) return (int)e;
     const float* Mf = nullptr;                     // mode 0 builds its shared-memory copy from M
     if (solver_mode(n, K) != 0) {
-        mf_from_m_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(M, w.Mf, n, K);
+        mf_from_m_kernel<<<(n * K + 255) / 256, 256, 0, st>>>(M, w.Mf, w.Mk, n, K);
         Mf = w.Mf;
     }
     int rc = launch_base(M, Mf, n, K, w, st);
     if (rc) return rc;
-    FG_SOLVE_LAUNCH(n, K, 1, st, M, Mf, n, K, w.prices, nullptr, WARM_DUAL_ITERS, WARM_STEP0, d, nullptr, assign, nullptr, w.status, 3,
+    FG_SOLVE_LAUNCH(n, K, 1, st, (Mf ? w.Mk : nullptr), M, Mf, n, K, w.prices, nullptr, WARM_DUAL_ITERS, WARM_STEP0, d, nullptr, assign, nullptr, w.status, 3,
                     1, w.members);
     FG_LAUNCH_CHECK();
     return FG_OK;
@@ -1278,7 +1304,7 @@ extern "C" int fg_ot_cost_matrix(const void* probs_gender, const void* probs_rac
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status);
         if (n_valid > 0) cost_hist_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
-            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
+            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -1323,12 +1349,12 @@ extern "C" int fg_assign_race_enumerated(const void* probs_race, int n_all, int 
     FG_LAUNCH_CHECK();
     if (n_valid > 0) {
         FG_DISPATCH_DTYPE(dtype, T,
-            race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf));
+            race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf, w.ot.Mk));
         FG_LAUNCH_CHECK();
         int rc = solver_prepare(n_valid, 8);
         if (rc) return rc;
         Demand none = {};
-        FG_SOLVE_LAUNCH(n_valid, 8, S, st, w.ot.M, w.ot.Mf, n_valid, 8, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, demands, w.sigma,
+        FG_SOLVE_LAUNCH(n_valid, 8, S, st, w.ot.Mk, w.ot.M, w.ot.Mf, n_valid, 8, nullptr, nullptr, DRAW_DUAL_ITERS, DRAW_STEP0, none, demands, w.sigma,
                         nullptr, w.ot.status, 3, 1, w.ot.members);
         FG_LAUNCH_CHECK();
     }
@@ -1348,7 +1374,7 @@ extern "C" int fg_race_cost_matrix(const void* probs_race, int n_all, int n_vali
     cudaStream_t st = fg_stream(stream);
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)nullptr, (const T*)probs_race, n_all, n_valid, w.ot.idx, w.ot.pos, w.ot.status);
-        if (n_valid > 0) race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf));
+        if (n_valid > 0) race_cost_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_race, w.ot.idx, n_valid, w.ot.M, w.ot.Mf, w.ot.Mk));
     FG_LAUNCH_CHECK();
     if (n_valid > 0) {
         cudaError_t e = cudaMemcpy2DAsync(M4, 4 * sizeof(double), w.ot.M, 8 * sizeof(double), 4 * sizeof(double), n_valid,
