@@ -155,29 +155,28 @@ compact_kernel(const T* __restrict__ pg, const T* __restrict__ pr, int n_all, in
 // cost matrix (fixed IEEE op order, identical to oracle/emd_rowinsert.c) + per-draw histograms
 __device__ __forceinline__ double dsq(double x) { return __dmul_rn(x, x); }
 
+// one element M[i,j]; every thread of a row recomputes the row's norms (a few fp64 square roots) so that the matrix is
+// spread over 16x more threads than one-thread-per-row -- the kernel sits on the critical path of the assignment
 template <typename T>
-__device__ __forceinline__ void cost_row(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
-                                         int i, int K, double* __restrict__ out) {
-    double g[2] = {(double)to_f32(pg[2 * i]), (double)to_f32(pg[2 * i + 1])};
+__device__ __forceinline__ double cost_elem(const T* __restrict__ pg, const T* __restrict__ pr, const T* __restrict__ pa,
+                                            int i, int K, int j) {
+    const double g[2] = {(double)to_f32(pg[2 * i]), (double)to_f32(pg[2 * i + 1])};
     double r[4];
     for (int q = 0; q < 4; q++) r[q] = (double)to_f32(pr[4 * i + q]);
-    double ca[2] = {0.0, 0.0};
+    int gi, ri, ai = 0;
+    if (K == 8) { gi = j >> 2; ri = j & 3; } else { gi = j >> 3; ri = (j >> 1) & 3; ai = j & 1; }
+    const double ng = __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(g[0], gi == 0 ? 1.0 : 0.0)), dsq(__dsub_rn(g[1], gi == 1 ? 1.0 : 0.0))));
+    double s4 = dsq(__dsub_rn(r[0], ri == 0 ? 1.0 : 0.0));
+    for (int q = 1; q < 4; q++) s4 = __dadd_rn(s4, dsq(__dsub_rn(r[q], ri == q ? 1.0 : 0.0)));
+    const double nr = __dsqrt_rn(s4);
+    double c = __dadd_rn(dsq(ng), dsq(nr));
     if (K == 16) {
-        double a0 = (double)to_f32(pa[2 * i]), a1 = (double)to_f32(pa[2 * i + 1]);
-        ca[0] = __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(a0, 1.0)), dsq(__dsub_rn(a1, 0.0))));
-        ca[1] = __dsqrt_rn(__dadd_rn(dsq(__dmul_rn(__dsub_rn(a0, 0.0), 2.0)), dsq(__dsub_rn(a1, 1.0))));
+        const double a0 = (double)to_f32(pa[2 * i]), a1 = (double)to_f32(pa[2 * i + 1]);
+        const double ca = ai == 0 ? __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(a0, 1.0)), dsq(__dsub_rn(a1, 0.0))))
+                                  : __dsqrt_rn(__dadd_rn(dsq(__dmul_rn(__dsub_rn(a0, 0.0), 2.0)), dsq(__dsub_rn(a1, 1.0))));
+        c = __dadd_rn(c, dsq(ca));
     }
-    for (int j = 0; j < K; j++) {
-        int gi, ri, ai = 0;
-        if (K == 8) { gi = j >> 2; ri = j & 3; } else { gi = j >> 3; ri = (j >> 1) & 3; ai = j & 1; }
-        double ng = __dsqrt_rn(__dadd_rn(dsq(__dsub_rn(g[0], gi == 0 ? 1.0 : 0.0)), dsq(__dsub_rn(g[1], gi == 1 ? 1.0 : 0.0))));
-        double s4 = dsq(__dsub_rn(r[0], ri == 0 ? 1.0 : 0.0));
-        for (int q = 1; q < 4; q++) s4 = __dadd_rn(s4, dsq(__dsub_rn(r[q], ri == q ? 1.0 : 0.0)));
-        double nr = __dsqrt_rn(s4);
-        double c = __dadd_rn(dsq(ng), dsq(nr));
-        if (K == 16) c = __dadd_rn(c, dsq(ca[ai]));
-        out[j] = __dsqrt_rn(c);
-    }
+    return __dsqrt_rn(c);
 }
 
 template <typename T>
@@ -187,11 +186,14 @@ cost_hist_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T* __
                  const T* __restrict__ rg, const T* __restrict__ rr, const T* __restrict__ ra, int S,
                  int* __restrict__ hist, int32_t* __restrict__ counts_to_zero) {
     if ((int)blockIdx.x < cost_blocks) {
-        int r = blockIdx.x * 256 + threadIdx.x;
+        // 256 threads = 256 / K rows x K classes
+        const int e = blockIdx.x * 256 + threadIdx.x;
+        const int r = e / K, j = e - r * K;
         if (r < N) {
-            cost_row<T>(pg, pr, pa, idx[r], K, M + (size_t)r * K);
-            if (Mf) for (int j = 0; j < K; j++) { const float c = (float)M[(size_t)r * K + j]; Mf[(size_t)j * N + r] = c; Mk[(size_t)j * N + r] = cost_key(c, j); }
-            if (counts_to_zero) for (int j = 0; j < K; j++) counts_to_zero[(size_t)r * K + j] = 0;
+            const double c = cost_elem<T>(pg, pr, pa, idx[r], K, j);
+            M[(size_t)r * K + j] = c;
+            if (Mf) { Mf[(size_t)j * N + r] = (float)c; Mk[(size_t)j * N + r] = cost_key((float)c, j); }
+            if (counts_to_zero) counts_to_zero[(size_t)r * K + j] = 0;
         }
         return;
     }
@@ -1232,7 +1234,7 @@ extern "C" int fg_ot_plan_counts(const void* probs_gender, const void* probs_rac
     FG_LAUNCH_CHECK();
     if (n_valid == 0) return FG_OK;
     if (!counts || (S > 0 && (!rand_gender || !rand_race || (K == 16 && !rand_age)))) return FG_ERR_INVALID_ARG;
-    int cost_blocks = (n_valid + 255) / 256;
+    int cost_blocks = (n_valid * K + 255) / 256;
     FG_DISPATCH_DTYPE(dtype, T,
         cost_hist_kernel<T><<<cost_blocks + S, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age,
             w.idx, n_valid, K, w.M, w.Mf, w.Mk, cost_blocks, (const T*)rand_gender, (const T*)rand_race, (const T*)rand_age, S, w.hist, counts));
@@ -1303,8 +1305,8 @@ extern "C" int fg_ot_cost_matrix(const void* probs_gender, const void* probs_rac
     if (e != cudaSuccess) return (int)e;
     FG_DISPATCH_DTYPE(dtype, T,
         compact_kernel<T><<<1, 1024, 0, st>>>((const T*)probs_gender, (const T*)probs_race, n_all, n_valid, w.idx, w.pos, w.status);
-        if (n_valid > 0) cost_hist_kernel<T><<<(n_valid + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
-            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, nullptr, (n_valid + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
+        if (n_valid > 0) cost_hist_kernel<T><<<(n_valid * K + 255) / 256, 256, 0, st>>>((const T*)probs_gender, (const T*)probs_race,
+            (const T*)probs_age, w.idx, n_valid, K, M, nullptr, nullptr, (n_valid * K + 255) / 256, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
