@@ -281,8 +281,6 @@ def main():
     launches_per_step = (sum(_lib.KERNELS_PER_CALL.get(k, 1) * v for k, v in calls.items())
                          + calls.get("fg_ot_plan_counts", 0) * _lib.ot_levels(num_valid)) // max(3, a.steps // 2)
     stage_ms = {k: probe.mean_ms(k) for k in ("sample_fwd", "assign", "image_grad")}
-    if sampler:
-        sampler.rows.clear()
     ms_step, _ = timed(step_resident, a.steps, a.warmup)
     clocks = sampler.summary() if sampler else None
     launches = launches_per_step * a.steps
