@@ -132,17 +132,13 @@ aligned_warp_fwd_kernel(const T* __restrict__ images, const float* __restrict__ 
 
 // backward: persistent CTAs of 8 warps; a CTA walks the images round-robin and, inside an image, the 32x8-pixel tiles of
 // the bounding box of the taps only (the whole image when it has to write the zeros as well) -- a grid over all tiles
-// of all images spent its time launching ~1M empty CTAs.  thread = one source pixel, all channels.  The output-gradient
-// pixels a tile can touch (the image of the tile under the inverse map, a few hundred values at the usual 2x down-scale)
-// are staged in shared memory first and the accumulate target is loaded before the candidate loop, so the per-pixel
-// gather runs on shared-memory latency; tiles whose footprint exceeds the staging buffer (strong up-sampling) read the
-// gradient through L2 instead.
-constexpr int BWD_STAGE = 1536;          // staged output-gradient pixels per channel (3 channels x 4 B x 1536 = 18 KB)
+// of all images spent its time launching ~1M empty CTAs.  thread = one source pixel, all channels.  Measured slower and
+// dropped: staging the tile's output-gradient footprint in shared memory (two block barriers per tile, 2.75 ms vs 1.71 ms) and
+// four pixels per thread with their accumulate targets loaded up front (2.27 ms).
 template <typename T>
 __global__ void __launch_bounds__(256)
 aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ params, const uint8_t* __restrict__ indicators,
                         int n, int C, int Hs, int Ws, int Hd, int Wd, int accumulate, T* __restrict__ g_images) {
-    __shared__ float stage[3 * BWD_STAGE];
     const int tx_ = threadIdx.x & 31, ty_ = threadIdx.x >> 5;
     for (int img = blockIdx.x; img < n; img += gridDim.x) {
         const float* P = params + (size_t)img * ALIGN_PARAMS;
@@ -158,69 +154,37 @@ aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ p
         const float hx = fabsf(d00) + fabsf(d01), hy = fabsf(d10) + fabsf(d11);
         const T* go = g_out + (size_t)img * C * Hd * Wd;
         for (int tile = 0; tile < tiles_x * tiles_y; tile++) {
-            const int tx0 = X0 + (tile % tiles_x) * 32, ty0 = Y0 + (tile / tiles_x) * 8;
-            const int x = tx0 + tx_, y = ty0 + ty_;
-            const bool in_img = x < Ws && y < Hs;
-            const bool inside = in_img && face && x >= bx0 && x <= bx1 && y >= by0 && y <= by1;
-            // does the tile meet the box at all?  (uniform over the CTA)
-            const bool tile_hit = face && tx0 <= bx1 && tx0 + 31 >= bx0 && ty0 <= by1 && ty0 + 7 >= by0;
-            // footprint of the tile in the output: corners (+-1 px) under q = D p + d
-            int sj0 = 0, sj1 = -1, si0 = 0, si1 = -1, sw = 0;
-            bool staged = false;
-            if (tile_hit) {
-                float qxmin = INFINITY, qxmax = -INFINITY, qymin = INFINITY, qymax = -INFINITY;
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    const float px = (float)(tx0 + ((cc & 1) ? 32 : -1)), py = (float)(ty0 + ((cc & 2) ? 8 : -1));
-                    const float qx = fmaf(d00, px, fmaf(d01, py, d02)), qy = fmaf(d10, px, fmaf(d11, py, d12));
-                    qxmin = fminf(qxmin, qx); qxmax = fmaxf(qxmax, qx); qymin = fminf(qymin, qy); qymax = fmaxf(qymax, qy);
-                }
-                sj0 = max((int)floorf(qxmin) - 1, 0); sj1 = min((int)ceilf(qxmax) + 1, Wd - 1);
-                si0 = max((int)floorf(qymin) - 1, 0); si1 = min((int)ceilf(qymax) + 1, Hd - 1);
-                sw = sj1 - sj0 + 1;
-                const int sh = si1 - si0 + 1;
-                staged = C <= 3 && sw > 0 && sh > 0 && sw * sh <= BWD_STAGE;
-                if (staged) {
-                    for (int e = threadIdx.x; e < sw * sh * C; e += 256) {
-                        const int c = e / (sw * sh), r = e - c * sw * sh, ii = r / sw, jj = r - ii * sw;
-                        stage[c * BWD_STAGE + r] = to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)(si0 + ii) * Wd + sj0 + jj));
-                    }
-                }
-            }
-            T* g = g_images + (size_t)img * C * Hs * Ws + (size_t)(in_img ? y : 0) * Ws + (in_img ? x : 0);
-            float old[4] = {0.f, 0.f, 0.f, 0.f};
-            if (inside && accumulate) for (int c = 0; c < C && c < 4; c++) old[c] = to_f32(g[(size_t)c * Hs * Ws]);
-            if (tile_hit) __syncthreads();
-            if (in_img && !inside) {
+            const int x = X0 + (tile % tiles_x) * 32 + tx_, y = Y0 + (tile / tiles_x) * 8 + ty_;
+            if (x >= Ws || y >= Hs) continue;
+            T* g = g_images + (size_t)img * C * Hs * Ws + (size_t)y * Ws + x;
+            const bool inside = face && x >= bx0 && x <= bx1 && y >= by0 && y <= by1;
+            if (!inside) {
                 if (!accumulate) for (int c = 0; c < C; c++) g[(size_t)c * Hs * Ws] = from_f32<T>(0.f);
-            } else if (inside) {
-                // candidate output pixels: q = D p + d, within the parallelogram D (p + (-1,1)^2)
-                const float qx = fmaf(d00, (float)x, fmaf(d01, (float)y, d02));
-                const float qy = fmaf(d10, (float)x, fmaf(d11, (float)y, d12));
-                const int j0 = max((int)ceilf(qx - hx - 1e-3f), 0), j1 = min((int)floorf(qx + hx + 1e-3f), Wd - 1);
-                const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int i = i0; i <= i1; i++) {
-                    for (int j = j0; j <= j1; j++) {
-                        // the same fp32 expressions as the forward, so the tap weights are bit-identical
-                        const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
-                        const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
-                        const float fx0 = floorf(xs), fy0 = floorf(ys);
-                        const int tx = x - (int)fx0, ty = y - (int)fy0;              // 0 or 1 when this pixel is a tap
-                        if ((unsigned)tx > 1u || (unsigned)ty > 1u) continue;
-                        const float wx1 = xs - fx0, wy1 = ys - fy0;
-                        const float w = (tx ? wx1 : 1.f - wx1) * (ty ? wy1 : 1.f - wy1);
-                        if (staged && i >= si0 && i <= si1 && j >= sj0 && j <= sj1) {
-                            const int r = (i - si0) * sw + (j - sj0);
-                            for (int c = 0; c < C && c < 3; c++) acc[c] = fmaf(w, stage[c * BWD_STAGE + r], acc[c]);
-                        } else {
-                            for (int c = 0; c < C && c < 4; c++) acc[c] = fmaf(w, to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)i * Wd + j)), acc[c]);
-                        }
-                    }
-                }
-                for (int c = 0; c < C && c < 4; c++) g[(size_t)c * Hs * Ws] = from_f32<T>(old[c] + acc[c]);
+                continue;
             }
-            if (tile_hit) __syncthreads();                      // the staging buffer is reused by the next tile
+            // candidate output pixels: q = D p + d, within the parallelogram D (p + (-1,1)^2)
+            const float qx = fmaf(d00, (float)x, fmaf(d01, (float)y, d02));
+            const float qy = fmaf(d10, (float)x, fmaf(d11, (float)y, d12));
+            const int j0 = max((int)ceilf(qx - hx - 1e-3f), 0), j1 = min((int)floorf(qx + hx + 1e-3f), Wd - 1);
+            const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = i0; i <= i1; i++) {
+                for (int j = j0; j <= j1; j++) {
+                    // the same fp32 expressions as the forward, so the tap weights are bit-identical
+                    const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
+                    const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
+                    const float fx0 = floorf(xs), fy0 = floorf(ys);
+                    const int tx = x - (int)fx0, ty = y - (int)fy0;              // 0 or 1 when this pixel is a tap
+                    if ((unsigned)tx > 1u || (unsigned)ty > 1u) continue;
+                    const float wx1 = xs - fx0, wy1 = ys - fy0;
+                    const float w = (tx ? wx1 : 1.f - wx1) * (ty ? wy1 : 1.f - wy1);
+                    for (int c = 0; c < C && c < 4; c++) acc[c] = fmaf(w, to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)i * Wd + j)), acc[c]);
+                }
+            }
+            for (int c = 0; c < C && c < 4; c++) {
+                T* gc = g + (size_t)c * Hs * Ws;
+                *gc = from_f32<T>(accumulate ? to_f32(*gc) + acc[c] : acc[c]);
+            }
         }
     }
 }
