@@ -18,7 +18,11 @@ E3 = exp-3-debias-gender-race/1-main-debias.py, E4 = exp-4-debias-gender-race-ag
                 gen_dynamic_weights E1:1619-1633 / E3:1787-1803 / E4:1870-1895
     loss.py     loss assembly E1:1912-1933 / E3:2114-2147 / E4:2238-2283
     emd.py      exact transport solve standing in for POT ``ot.emd`` (not installed)
-    nextrows.py detector staging E1:1317/1326, get_evaluate_metrics E3:1716-1749 / E4:1780-1821
+    nextrows.py detector staging E1:1317/1326, get_evaluate_metrics E3:1716-1749 / E4:1780-1821, adjusted-DFT
+                coefficients E1:1104-1109, per-parameter gradient all-reduce E1:1996-2011
+    assign.py   also generate_dynamic_targets_race (exp-6-debias-race/1-main-debias.py:1413-1482) with POT's ot.dist restated
+    align.py    image_pipeline E1:292-312 (skimage Umeyama + kornia warp_affine restated), get_face_feats E1:1179-1190,
+                FaceFeatsModel.semantic_search E1:96-117, face-realism loss E1:1917-1929 / E3:2124-2143 / E4:2253-2272
 
 Parity pinning: the reference has no tests or golden vectors.  The
 oracle is pinned instead against outputs of the reference's OWN function bodies, executed
@@ -31,6 +35,11 @@ substituted there and here, which is the residual unpinned part:
   * ``torchvision.transforms.Resize``: torchvision 0.16.2 resized tensors WITHOUT antialias
     by default; the installed 0.26 defaults to antialias=True, so ``antialias=False`` is
     passed explicitly.
+  * next rows: ``ot.dist`` (POT), ``skimage.transform.SimilarityTransform``, ``kornia.warp_affine`` and
+    sentence-transformers' ``semantic_search`` are absent as well; their published arithmetic is restated
+    (assign.py, align.py) and cross-checked against OpenCV / an independent closed form in tests/test_align.py.
+    PARITY UNPINNED for exactly those third-party pieces; the reference's own statements around them are pinned by
+    tests/golden/make_golden_next.py.
 """
 
-from . import boxes, crop, head, assign, hooks, loss, emd  # noqa: F401
+from . import boxes, crop, head, assign, hooks, loss, emd, align, nextrows  # noqa: F401
