@@ -333,6 +333,29 @@ def main():
         e2e = {"value": n_global / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e}
 
+    # ---- fairness-only sub-path: crop without the resize, chip gradient without the semantics branch
+    fairness_only = None
+    try:
+        if world > 1:
+            raise RuntimeError("reported at 1 GPU only (rank-local kernels)")
+        from fairguide import ops as _ops
+        o = result["out"]
+        boxes_f, ind_f = o["boxes"], o["indicators"]
+
+        def step_fair():
+            _ops.crop_resize_fwd(batch["images"], boxes_f, ind_f, (cfg.size_face,) * 2, None, cfg.fill_value)
+            _ops.image_grad(batch["g_chips"], None, boxes_f, ind_f, None, None, tuple(batch["images"].shape), dtype, dev)
+
+        ms_fair, _ = timed(step_fair, max(3, a.steps // 2), 3)
+        side = (boxes_f[:, 2] - boxes_f[:, 0]).clamp(min=0).double()
+        box_px = float((torch.where(ind_f, side * side, torch.zeros_like(side))).sum().item())       # sum of s_i^2 over the faces
+        alg_fair = (3 * box_px + n_local * (3 * cfg.size_face ** 2 * 2 + 3 * 512 * 512)) * esize
+        fairness_only = {"ms": ms_fair, "GBps": alg_fair / (ms_fair * 1e-3) / 1e9,
+                         "algorithmic_bytes": alg_fair, "note": "crop forward + chip-gradient backward only (no resize / semantics branch)"}
+    except Exception as ex:                                        # noqa: BLE001
+        fairness_only = {"error": f"{type(ex).__name__}: {str(ex)[:100]}"}
+        torch.cuda.synchronize()
+
     with_backbone = None
     if a.backbone:
         import torchvision
@@ -382,7 +405,7 @@ def main():
                        "backbone": "excluded (stand-in pooled features and chip gradient; SURVEY.md 8d)",
                        "l2": f"inputs larger than L2 ({(fwd_b + bwd_b) * n_local / 1e6:.0f} MB touched per step per GPU vs 126 MB)"},
             "stage_ms": stage_ms, "ms_per_step_eager": ms_eager, "cuda_graph": graph_note, "gpu_launches": launches, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+            "clocks": clocks, "roofline": roofline, "fairness_only": fairness_only, "e2e": e2e, "cpu_baseline": cpu}
     if with_backbone:
         line["with_backbone"] = with_backbone
     print(json.dumps(line))
