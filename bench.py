@@ -337,7 +337,7 @@ def main():
     fairness_only = None
     try:
         if world > 1:
-            raise RuntimeError("reported at 1 GPU only (rank-local kernels)")
+            raise NotImplementedError
         from fairguide import ops as _ops
         o = result["out"]
         boxes_f, ind_f = o["boxes"], o["indicators"]
@@ -352,6 +352,8 @@ def main():
         alg_fair = (3 * box_px + n_local * (3 * cfg.size_face ** 2 * 2 + 3 * 512 * 512)) * esize
         fairness_only = {"ms": ms_fair, "GBps": alg_fair / (ms_fair * 1e-3) / 1e9,
                          "algorithmic_bytes": alg_fair, "note": "crop forward + chip-gradient backward only (no resize / semantics branch)"}
+    except NotImplementedError:
+        fairness_only = {"note": "reported at 1 GPU only (rank-local kernels)"}
     except Exception as ex:                                        # noqa: BLE001
         fairness_only = {"error": f"{type(ex).__name__}: {str(ex)[:100]}"}
         torch.cuda.synchronize()
