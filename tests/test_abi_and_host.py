@@ -78,6 +78,23 @@ pg = torch.rand(n, 2) + rank; pr = torch.rand(n, 4) + rank
 ind_all, (pg_all, pr_all) = fdist.gather_probs(ind, [pg, pr])
 assert ind_all.shape == (world * n,) and torch.equal(pg_all[rank * n:(rank + 1) * n], pg) and torch.equal(pr_all[rank * n:(rank + 1) * n], pr)
 assert torch.equal(ind_all[rank * n:(rank + 1) * n], ind)
+# the same exchange in the form the captured (CUDA-graph) step uses: static send / receive buffers, unpack afterwards
+packed = fdist.pack_probs(ind, [pg, pr])
+assert packed.shape == (n, 7) and packed.dtype == pg.dtype
+recv = torch.empty((world * n, 7), dtype=packed.dtype)
+for _ in range(2):                                   # replayable: same buffers, same result
+    fdist.all_gather_packed(recv, packed)
+    ind2, (pg2, pr2) = fdist.unpack_probs(recv, [2, 4])
+    assert torch.equal(ind2, ind_all) and torch.equal(pg2, pg_all) and torch.equal(pr2, pr_all)
+# bucketed gradient sync, host side: every rank derives the same layout; the flat sum equals the per-tensor sums
+numels = [6, 1, 10]
+off = fairguide.GradBucket.layout(numels)
+grads = [torch.full((m,), float(rank + 1 + k)) for k, m in enumerate(numels)]
+flat = torch.cat(grads + [torch.zeros(1)])
+dist.all_reduce(flat)
+for k in range(len(numels)):
+    per_tensor = grads[k].clone(); dist.all_reduce(per_tensor)
+    assert torch.equal(flat[off[k]:off[k + 1]], per_tensor)
 c = torch.full((7, 8), rank + 1, dtype=torch.int32)
 fdist.all_reduce_counts(c)
 assert (c == sum(range(1, world + 1))).all()
