@@ -317,8 +317,9 @@ class FaceFeatsModel(torch.nn.Module):
 
     def __init__(self, face_feats):
         super().__init__()
-        self.face_feats = torch.nn.Parameter(ops.feats_normalize_fwd(face_feats)[0] if face_feats.is_cuda
-                                             else torch.nn.functional.normalize(face_feats.float(), dim=-1), requires_grad=False)
+        # normalised on the device by the same kernel as the queries (a host tensor is moved first; no CPU arithmetic here)
+        feats = face_feats if face_feats.is_cuda else face_feats.cuda()
+        self.face_feats = torch.nn.Parameter(ops.feats_normalize_fwd(feats)[0], requires_grad=False)
 
     def forward(self, x):
         return None

@@ -48,6 +48,8 @@ class GradBucket:
         dev = self.params[0].device
         self.dtype = self.params[0].dtype
         assert all(p.dtype == self.dtype and p.device == dev for p in self.params), "one dtype / device per bucket"
+        if dev.type != "cuda":
+            raise RuntimeError("fairguide ops run on CUDA tensors only (no CPU fallback)")
         self.offsets = torch.tensor(self.offsets_host, dtype=torch.int64, device=dev)
         self.bucket = torch.empty((self.total + 1,), dtype=torch.float32, device=dev)
         self.nonfinite = torch.zeros((1,), dtype=torch.int32, device=dev)

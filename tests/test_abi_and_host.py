@@ -44,6 +44,14 @@ def test_no_cpu_fallback():
         fairguide.ops.crop_resize_fwd(torch.zeros(1, 3, 8, 8), torch.zeros(1, 4, dtype=torch.int64), None, (4, 4), None)
     with pytest.raises(RuntimeError):
         fairguide.generate_dynamic_targets(torch.rand(4, 2), w_uncertainty=True)
+    with pytest.raises(RuntimeError):
+        fairguide.generate_dynamic_targets_race(torch.rand(4, 4))
+    with pytest.raises(RuntimeError):
+        fairguide.aligned_face_chips(torch.zeros(1, 3, 8, 8), torch.zeros(1, 5, 2))
+    with pytest.raises(RuntimeError):
+        fairguide.ops.face_search_top1(torch.rand(2, 8), None, torch.rand(4, 8))
+    with pytest.raises(RuntimeError):
+        fairguide.GradBucket([torch.nn.Parameter(torch.zeros(3))])
 
 
 def test_product_does_not_import_oracle():
