@@ -173,6 +173,82 @@ def main():
         out[f"dft_alphas_{c}"], out[f"dft_alphas_cumprod_{c}"] = sched.alphas.numpy(), sched.alphas_cumprod.numpy()
         out[f"dft_timesteps_{c}"], out[f"dft_coefs_{c}"] = sched.timesteps.numpy(), np.asarray(ns["grad_coefs"], dtype=np.float64)
     out["dft_n_cases"] = np.array(3)
+    # ---- face-realism loss: FaceFeatsModel (E1:82-117) and the loss_face_ij block of the training loop (E1:1917-1929,
+    #      E3:2124-2143, E4:2253-2272), lifted unmodified.  sentence-transformers is absent: util.semantic_search / dot_score
+    #      are stubbed (dot-product matrix + topk); get_face_feats is replaced by the identity on pre-normalised feature rows
+    #      (the network is external to the path).
+    import pickle
+    import tempfile
+
+    def _dot_score(a, b):
+        return a @ b.T
+
+    def _semantic_search(query, corpus, score_function=None, top_k=1):
+        scores = score_function(query, corpus)
+        vals, idx = scores.topk(top_k, dim=1)
+        return [[{"corpus_id": int(i), "score": float(v)} for v, i in zip(vr, ir)] for vr, ir in zip(vals, idx)]
+
+    util_stub = types.SimpleNamespace(semantic_search=_semantic_search, dot_score=_dot_score)
+
+    def loss_block(tree_):
+        for node in ast.walk(tree_):
+            body = getattr(node, "body", None)
+            if not isinstance(body, list):
+                continue
+            for k, stmt in enumerate(body):
+                if (isinstance(stmt, ast.Assign) and getattr(stmt.targets[0], "id", None) == "loss_face_ij"
+                        and "torch.ones" in ast.unparse(stmt.value)):
+                    stmts = []
+                    for nxt in body[k:]:
+                        if isinstance(nxt, ast.Assign) and getattr(nxt.targets[0], "id", None) == "dynamic_weights":
+                            break
+                        stmts.append(nxt)
+                    return compile(ast.Module(body=stmts, type_ignores=[]), "<reference>", "exec")
+        raise KeyError("loss_face_ij block")
+
+    E1_tree = ast.parse(open(os.path.join(a.ref, E1)).read())
+    cls_node = next(n for n in ast.walk(E1_tree) if isinstance(n, ast.ClassDef) and n.name == "FaceFeatsModel")
+    ns_cls = {"torch": torch, "nn": torch.nn, "pkl": pickle, "util": util_stub}
+    exec(compile(ast.Module(body=[cls_node], type_ignores=[]), "<reference>", "exec"), ns_cls)
+    gen = torch.Generator().manual_seed(500)
+    D, d, n = 300, 64, 23
+    raw_db = torch.randn(D, d, generator=gen) * 2
+    with tempfile.NamedTemporaryFile(suffix=".pkl") as tf:
+        pickle.dump((raw_db, None, None), tf)
+        tf.flush()
+        model = ns_cls["FaceFeatsModel"](tf.name)
+    out["face_db_raw"], out["face_db"] = raw_db.numpy(), model.face_feats.data.numpy()
+    names = {1: (E1, ["targets_ij"], ["preds_gender_ori_ij"], ["probs_gender_ori_ij"]),
+             2: (E3, ["targets_gender_ij", "targets_race_ij"], ["preds_gender_ori_ij", "preds_race_ori_ij"],
+                 ["probs_gender_ori_ij", "probs_race_ori_ij"]),
+             3: (E4, ["targets_gender_ij", "targets_race_ij", "targets_age_ij"],
+                 ["preds_gender_ori_ij", "preds_race_ori_ij", "preds_age_ori_ij"],
+                 ["probs_gender_ori_ij", "probs_race_ori_ij", "probs_age_ori_ij"])}
+    widths = [2, 4, 2]
+    for n_attr, (rel, tn, pn, qn) in names.items():
+        code = loss_block(ast.parse(open(os.path.join(a.ref, rel)).read()))
+        feats = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1)
+        feats_ori = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1)
+        face = torch.rand(n, generator=gen) > 0.2
+        ns = {"torch": torch, "weight_dtype": torch.float32, "accelerator": types.SimpleNamespace(device="cpu"),
+              "args": types.SimpleNamespace(face_gender_confidence_level=0.75, face_gender_race_confidence_level=0.75,
+                                            face_gender_race_age_confidence_level=0.75),
+              "idxs_ij": list(range(n)), "face_indicators_ij": face, "get_face_feats": lambda net, chips: chips,
+              "face_feats_net": None, "aligned_face_chips_ij": feats, "face_feats_ori_ij": feats_ori, "face_feats_model": model}
+        for k in range(n_attr):
+            t = torch.randint(-1, widths[k], (n,), generator=gen)
+            ns[tn[k]] = t
+            ns[pn[k]] = torch.where(torch.rand(n, generator=gen) < 0.85, t.clamp(min=0), torch.randint(0, widths[k], (n,), generator=gen))
+            ns[qn[k]] = torch.softmax(torch.randn(n, widths[k], generator=gen) * 4, -1)
+            out[f"face_t{k}_{n_attr}"], out[f"face_p{k}_{n_attr}"], out[f"face_q{k}_{n_attr}"] = ns[tn[k]].numpy(), ns[pn[k]].numpy(), ns[qn[k]].numpy()
+        exec(code, ns)
+        out[f"face_feats_{n_attr}"], out[f"face_feats_ori_{n_attr}"], out[f"face_ind_{n_attr}"] = feats.numpy(), feats_ori.numpy(), face.numpy()
+        out[f"face_loss_{n_attr}"] = ns["loss_face_ij"].numpy()
+    # semantic_search on its own, with a selector and similarities
+    q = torch.nn.functional.normalize(torch.randn(9, d, generator=gen), dim=-1)
+    sel = torch.tensor([True, False, True, True, False, True, True, True, False])
+    tgt, sim = model.semantic_search(q, sel, return_similarity=True)
+    out["search_q"], out["search_sel"], out["search_target"], out["search_sim"] = q.numpy(), sel.numpy(), tgt.numpy(), sim.numpy()
     np.savez_compressed(os.path.join(HERE, "nextrows.npz"), **out)
     print("wrote nextrows.npz:", sorted(out))
 

@@ -245,3 +245,49 @@ def test_gpu_get_face_feats_vs_oracle():
     np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-3, atol=1e-5)
     g = ref_in.grad.numpy()
     np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=1e-3, atol=1e-3 * np.abs(g).max())
+
+
+# ----------------------------------------------------------------------------- oracle pinned to the reference's own statements
+def test_oracle_face_db_and_search_golden():
+    """FaceFeatsModel.__init__ / semantic_search (E1:82-117), executed from the reference source by make_golden_next.py."""
+    from oracle import align
+    db = torch.nn.functional.normalize(torch.tensor(GOLD["face_db_raw"]), dim=-1)                  # E1:88
+    assert np.array_equal(db.numpy(), GOLD["face_db"])
+    t, s = align.semantic_search(db, torch.tensor(GOLD["search_q"]), torch.tensor(GOLD["search_sel"]), return_similarity=True)
+    assert np.array_equal(t.numpy(), GOLD["search_target"])
+    np.testing.assert_allclose(s.numpy(), GOLD["search_sim"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_attr", [1, 2, 3])
+def test_oracle_face_loss_golden(n_attr):
+    """The loss_face_ij block of the training loop (E1:1917-1929 / E3:2124-2143 / E4:2253-2272), executed from the reference
+    source: which rows take the original features, which the database search, which stay -1."""
+    from oracle import align
+    db = torch.tensor(GOLD["face_db"])
+    f, fo, face = (torch.tensor(GOLD[f"face_{k}_{n_attr}"]) for k in ("feats", "feats_ori", "ind"))
+    ts = [torch.tensor(GOLD[f"face_t{k}_{n_attr}"]) for k in range(n_attr)]
+    ps = [torch.tensor(GOLD[f"face_p{k}_{n_attr}"]) for k in range(n_attr)]
+    qs = [torch.tensor(GOLD[f"face_q{k}_{n_attr}"]) for k in range(n_attr)]
+    got = align.face_loss(f, db, face, ts, ps, qs, fo, 0.75)
+    want = GOLD[f"face_loss_{n_attr}"]
+    assert np.array_equal(got.numpy() == -1, want == -1)
+    np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=1e-6)
+    assert (want == -1).any() and (want != -1).any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_attr", [1, 2, 3])
+def test_gpu_face_loss_golden(n_attr):
+    """The CUDA path against the same golden vectors (features already normalised: the kernel's normalisation is then the
+    identity up to rounding)."""
+    import fairguide as fg
+    db = torch.tensor(GOLD["face_db"]).to(DEV)
+    f, fo, face = (torch.tensor(GOLD[f"face_{k}_{n_attr}"]).to(DEV) for k in ("feats", "feats_ori", "ind"))
+    attr = []
+    for k in range(n_attr):
+        attr += [torch.tensor(GOLD[f"face_t{k}_{n_attr}"]).to(DEV), torch.tensor(GOLD[f"face_p{k}_{n_attr}"]).to(DEV),
+                 torch.tensor(GOLD[f"face_q{k}_{n_attr}"]).to(DEV)]
+    loss = fg.face_realism_loss(f, fo, db, face, *attr, confidence_level=0.75)
+    want = GOLD[f"face_loss_{n_attr}"]
+    assert np.array_equal(loss.cpu().numpy() == -1, want == -1)
+    np.testing.assert_allclose(loss.cpu().numpy(), want, rtol=1e-3, atol=1e-5)
