@@ -96,12 +96,15 @@ class GradBucket:
         return flags[0] == 0, int(flags[1])
 
 
-def allreduce_average_gradients(params, num_processes=None, n_backward=1, group=None, _cache={}):
+_BUCKETS = {}      # parameter-list identity -> GradBucket (the LoRA parameter lists are fixed for a run)
+
+
+def allreduce_average_gradients(params, num_processes=None, n_backward=1, group=None):
     """Drop-in for the loop at E1:1999-2011: sums ``p.grad`` over the ranks and divides by num_processes and N_backward;
     returns ``grad_is_finite``."""
     params = list(params)
     key = tuple(id(p) for p in params)
-    if key not in _cache:
-        _cache.clear()
-        _cache[key] = GradBucket(params)
-    return _cache[key].sync(num_processes, n_backward, group)[0]
+    bucket = _BUCKETS.get(key)
+    if bucket is None or any(a is not b for a, b in zip(bucket.params, params)):
+        bucket = _BUCKETS[key] = GradBucket(params)
+    return bucket.sync(num_processes, n_backward, group)[0]

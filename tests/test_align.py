@@ -291,3 +291,30 @@ def test_gpu_face_loss_golden(n_attr):
     want = GOLD[f"face_loss_{n_attr}"]
     assert np.array_equal(loss.cpu().numpy() == -1, want == -1)
     np.testing.assert_allclose(loss.cpu().numpy(), want, rtol=1e-3, atol=1e-5)
+
+
+def test_oracle_warp_equals_the_closed_form_map_the_kernel_uses():
+    """kornia's normalise -> invert -> affine_grid -> grid_sample(align_corners=False) chain collapses to one affine map per
+    image, `output pixel -> source pixel`:  u = (j+0.5)(Wd-1)/Wd, (x,y) = M^-1 (u,v,1), xs = x Ws/(Ws-1) - 0.5  (csrc/fg_align.cu).
+    Checked here in numpy against the oracle's torch chain, including taps outside the image (zero padding)."""
+    from oracle import align
+    Hs, Ws, Hd, Wd = 96, 128, 112, 112
+    img = smooth_images(1, Hs, Ws, 9)[0]
+    for lm in landmarks_for(4, Hs, Ws, 10, scale_range=(0.4, 1.2)):
+        M = align.similarity_matrix(lm).astype(np.float32).astype(np.float64)
+        ref = align.warp_affine(img.unsqueeze(0), torch.tensor(M).unsqueeze(0).float(), (Hd, Wd), align_corners=False)[0].numpy()
+        Minv = np.linalg.inv(np.vstack([M, [0, 0, 1]]))
+        jj, ii = np.meshgrid(np.arange(Wd), np.arange(Hd))
+        u, v = (jj + 0.5) * (Wd - 1) / Wd, (ii + 0.5) * (Hd - 1) / Hd
+        xs = (Minv[0, 0] * u + Minv[0, 1] * v + Minv[0, 2]) * Ws / (Ws - 1) - 0.5
+        ys = (Minv[1, 0] * u + Minv[1, 1] * v + Minv[1, 2]) * Hs / (Hs - 1) - 0.5
+        x0, y0 = np.floor(xs).astype(int), np.floor(ys).astype(int)
+        fx, fy = xs - x0, ys - y0
+
+        def tap(c, y, x):
+            ok = (x >= 0) & (x < Ws) & (y >= 0) & (y < Hs)
+            return np.where(ok, c[np.clip(y, 0, Hs - 1), np.clip(x, 0, Ws - 1)], 0.0)
+
+        mine = np.stack([(tap(c, y0, x0) * (1 - fx) + tap(c, y0, x0 + 1) * fx) * (1 - fy)
+                         + (tap(c, y0 + 1, x0) * (1 - fx) + tap(c, y0 + 1, x0 + 1) * fx) * fy for c in img.numpy().astype(np.float64)])
+        assert np.abs(mine - ref).max() < 2e-5
