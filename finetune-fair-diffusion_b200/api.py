@@ -182,7 +182,7 @@ def generate_dynamic_targets(probs, target_ratio=0.5, w_uncertainty=False, *, un
 
 @torch.no_grad()
 def _mc_targets(probs, w_uncertainty, num_samples_per_device, rand_tensors, num_valid, uncertainty_threshold, group,
-                return_counts=False):
+                return_counts=False, check_status=True):
     pg, pr = probs[0], probs[1]
     pa = probs[2] if len(probs) == 3 else None
     K = 16 if pa is not None else 8
@@ -200,6 +200,10 @@ def _mc_targets(probs, w_uncertainty, num_samples_per_device, rand_tensors, num_
         fdist.all_reduce_counts(counts, group)            # E3:1535, on exact int32 counts
     thr = -1.0 if uncertainty_threshold is None else float(uncertainty_threshold)
     ts, us = ops.ot_targets(counts, pg, pr, num_valid, ws, thr, w_uncertainty)
+    if check_status:
+        # one 16-byte read: a wrong ``num_valid`` or an inexact plan raises instead of returning wrong targets (the
+        # reference's caller synchronises right after this call anyway: E3:2026 prints ``.sum().item()``)
+        ws.check(num_valid)
     out = []
     for a in range(len(ts)):
         out.append(ts[a])
@@ -269,7 +273,9 @@ def generate_dynamic_targets_race(probs, w_uncertainty=False, *, num_valid=None,
         demands = torch.from_numpy(d16).to(probs.device)
         weights = torch.from_numpy(w).to(probs.device)
     thr = -1.0 if uncertainty_threshold is None else float(uncertainty_threshold)
-    targets, unc, _ = ops.assign_race_enumerated(probs, num_valid, demands, weights, thr, w_uncertainty)
+    targets, unc, ws = ops.assign_race_enumerated(probs, num_valid, demands, weights, thr, w_uncertainty)
+    if probs.shape[0] > 0:
+        ops.check_ot_status(ws[:16].view(torch.int32).tolist(), num_valid)
     return (targets, unc) if w_uncertainty else targets
 
 

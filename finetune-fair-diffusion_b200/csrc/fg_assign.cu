@@ -145,6 +145,9 @@ compact_kernel(const T* __restrict__ pg, const T* __restrict__ pr, int n_all, in
         if (threadIdx.x == 0) base += warp_sums[31];
         __syncthreads();
     }
+    // A caller that over-reports n_valid makes the cost kernel walk idx[] past the rows found here: point those entries
+    // at row 0 so that nothing is read out of bounds (the mismatch is flagged; the Python side raises on it).
+    for (int i = base + threadIdx.x; i < n_all; i += 1024) idx[i] = 0;
     if (threadIdx.x == 0) {
         status[1] = base;
         if (n_valid_expected >= 0 && base != n_valid_expected) atomicOr(&status[0], ST_NVALID_MISMATCH);
@@ -906,6 +909,7 @@ __global__ void ot_targets_kernel(const int32_t* __restrict__ counts, const int*
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_all) return;
     int p = n_valid > 0 ? pos[i] : -1;
+    if (p >= n_valid) p = -1;            // the caller under-reported n_valid (flagged by compact_kernel): stay inside counts[]
     const int n_attr = K == 16 ? 3 : 2;
     long long* tout[3] = {tg, tr, ta};
     T* uout[3] = {ug, ur, ua};
@@ -1184,7 +1188,7 @@ __global__ void race_accumulate_kernel(const int32_t* __restrict__ sigma, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_all) return;
     const int p = pos[i];
-    if (p < 0) { targets[i] = -1; if (unc) unc[i] = from_f32<T>(-1.f); return; }
+    if (p < 0 || p >= N) { targets[i] = -1; if (unc) unc[i] = from_f32<T>(-1.f); return; }
     double tp[4] = {0.0, 0.0, 0.0, 0.0};
     for (int s = 0; s < S; s++) {
         const int c = sigma[(size_t)s * N + p];

@@ -98,14 +98,25 @@ def image_grad(g_chips, g_small, boxes, indicators, region, scale, image_shape, 
         sh, sw = g_small.shape[-2:]
     out = torch.empty((n, C, H, W), dtype=dtype, device=device)
     ind = _u8(indicators)
+    region, scale = _region_scale(region, scale)
     check(_lib.lib().fg_image_grad(_p(g_chips), _p(g_small), _p(boxes) if g_chips is not None else None, _p(ind),
                                    _p(region), _p(scale), _p(out), n, C, H, W, ch, cw, sh, sw, _DT[dtype], _stream()),
           "fg_image_grad")
     return out
 
 
+def _region_scale(region, scale):
+    """region int32 [n,4] / scale float32 [n], whatever integer / floating dtype the caller holds them in."""
+    if (region is None) != (scale is None):
+        raise RuntimeError("fairguide: region and scale go together")
+    if region is None:
+        return None, None
+    return region.to(torch.int32).contiguous(), scale.to(torch.float32).contiguous()
+
+
 def region_scale(g, region, scale):
     _cuda(g, region, scale)
+    region, scale = _region_scale(region, scale)
     g = g.contiguous()
     n, C, H, W = g.shape
     out = torch.empty_like(g)
@@ -264,6 +275,26 @@ class OtWorkspace:
     def status(self):
         """[status bits, n_valid seen on the device, base augmentations, draw augmentations] (synchronises)."""
         return self.buf[:16].view(torch.int32).tolist()
+
+    def status_tensor(self):
+        """The four status words as a device view (copy it to the host together with the step's outputs)."""
+        return self.buf[:16].view(torch.int32)
+
+    def check(self, n_valid=None):
+        """Raise if the assignment kernels flagged a problem (one 16-byte device-to-host read)."""
+        check_ot_status(self.status(), n_valid)
+
+
+OT_STATUS_BITS = {1: "n_valid passed by the caller differs from the rows with a face found on the device",
+                  2: "no augmenting path (infeasible demand)", 4: "augmenting path too long", 8: "repair-step cap reached (plan inexact)",
+                  16: "class demands do not sum to the number of rows"}
+
+
+def check_ot_status(words, n_valid=None):
+    bits = int(words[0])
+    if bits:
+        why = "; ".join(msg for b, msg in OT_STATUS_BITS.items() if bits & b)
+        raise RuntimeError(f"fairguide assignment failed (status {bits}: {why}; n_valid given {n_valid}, on device {int(words[1])})")
 
 
 def ot_plan_counts(probs_gender, probs_race, probs_age, rands, n_valid, ws):

@@ -67,8 +67,18 @@ class GradBucket:
         grads = [p.grad for p in self.params]
         assert all(g is not None and g.is_contiguous() for g in grads), "every parameter needs a contiguous .grad"
         key = tuple(g.data_ptr() for g in grads)
-        if key != self._ptr_key:                       # .grad tensors are normally allocated once and reused
-            self._ptrs = torch.tensor(key, dtype=torch.int64, device=self.bucket.device)
+        if key != self._ptr_key:
+            # .grad tensors that stay allocated between steps (``zero_grad(set_to_none=False)``) keep their addresses and
+            # skip this upload; otherwise the table goes up from pinned memory without blocking the host
+            if self._ptrs is None:
+                self._ptrs = torch.empty((len(key),), dtype=torch.int64, device=self.bucket.device)
+                self._ptrs_host = torch.empty((len(key),), dtype=torch.int64, pin_memory=True)
+            else:
+                self._ptr_event.synchronize()          # the previous upload has consumed the pinned buffer
+            self._ptrs_host.copy_(torch.tensor(key, dtype=torch.int64))
+            self._ptrs.copy_(self._ptrs_host, non_blocking=True)
+            self._ptr_event = torch.cuda.Event()
+            self._ptr_event.record()
             self._ptr_key = key
         return self._ptrs
 
@@ -96,15 +106,25 @@ class GradBucket:
         return flags[0] == 0, int(flags[1])
 
 
-_BUCKETS = {}      # parameter-list identity -> GradBucket (the LoRA parameter lists are fixed for a run)
+_BUCKETS = {}      # parameter-list identity -> GradBucket; bounded (the reference has at most two lists: UNet and text-encoder LoRA)
+_MAX_BUCKETS = 4
+
+
+def clear_gradient_buckets():
+    """Drop the cached buckets (and the fp32 staging memory they hold), e.g. after rebuilding the models."""
+    _BUCKETS.clear()
 
 
 def allreduce_average_gradients(params, num_processes=None, n_backward=1, group=None):
     """Drop-in for the loop at E1:1999-2011: sums ``p.grad`` over the ranks and divides by num_processes and N_backward;
-    returns ``grad_is_finite``."""
+    returns ``grad_is_finite``.  The bucket of a parameter list is cached (least recently used of at most four lists is
+    dropped, so changing lists cannot grow memory without bound); ``clear_gradient_buckets()`` frees them explicitly."""
     params = list(params)
     key = tuple(id(p) for p in params)
-    bucket = _BUCKETS.get(key)
+    bucket = _BUCKETS.pop(key, None)
     if bucket is None or any(a is not b for a, b in zip(bucket.params, params)):
-        bucket = _BUCKETS[key] = GradBucket(params)
+        bucket = GradBucket(params)
+    _BUCKETS[key] = bucket                               # re-inserted last: dict order is the LRU order
+    while len(_BUCKETS) > _MAX_BUCKETS:
+        _BUCKETS.pop(next(iter(_BUCKETS)))
     return bucket.sync(num_processes, n_backward, group)[0]

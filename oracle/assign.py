@@ -108,6 +108,8 @@ def cost_matrix_literal(pg, pr, pa=None):
     1.26 every expression below is promoted to float64 anyway (array - int64 array; float32
     scalar - Python int), whereas NumPy 2 would keep the age residual in float32."""
     M = []
+    if pg.dtype == torch.bfloat16:      # numpy has no bfloat16 (the reference itself only runs fp16 / fp32 here); exact widening
+        pg, pr, pa = pg.float(), pr.float(), (None if pa is None else pa.float())
     for i in range(pg.shape[0]):
         g = np.array(pg[i].cpu()).astype(np.float64)
         r = np.array(pr[i].cpu()).astype(np.float64)

@@ -41,3 +41,19 @@ def peaked_probs(rng, n, k, sharp=4.0):
     z = z - z.max(axis=1, keepdims=True)
     p = np.exp(z)
     return (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+
+
+def half_tensor(arr, dtype_name):
+    """Decode a 16-bit fixture of half.npz (raw uint16 patterns; numpy has no bfloat16) into a torch tensor."""
+    import torch
+    if arr.dtype != np.uint16:
+        return torch.tensor(arr)
+    dt = {"f16": torch.float16, "bf16": torch.bfloat16}[dtype_name]
+    return torch.tensor(arr.view(np.int16)).view(dt)
+
+
+def half_equal(t, arr):
+    """Bit-for-bit comparison of a 16-bit torch tensor with a raw-pattern fixture."""
+    import torch
+    got = t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    return got.shape == arr.shape and np.array_equal(got, arr)

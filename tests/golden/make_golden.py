@@ -182,6 +182,11 @@ class _LegacyNp:
         return getattr(np, name)
 
     def array(self, x, *a, **k):
+        if torch.is_tensor(x) and x.dtype == torch.bfloat16:
+            # EXTENSION beyond the reference: ``np.array(bf16_tensor)`` raises (numpy has no bfloat16), so the
+            # reference's Monte-Carlo assignment only runs in fp16 / fp32.  Widening to fp32 (exact) is the one natural
+            # continuation and is what the bf16 fixtures of gen_half() use.
+            x = x.float()
         out = np.array(x, *a, **k)
         if out.dtype in (np.float32, np.float16):
             out = out.astype(np.float64)
@@ -471,6 +476,93 @@ def gen_hooks(ref, out):
     np.savez_compressed(os.path.join(out, "hooks.npz"), **res)
 
 
+HALF_DTYPES = (("f16", torch.float16), ("bf16", torch.bfloat16))
+THRESHOLD = 0.2          # every shipped YAML (e.g. exp-3-debias-gender-race/configs/debias-text-encoder.yaml:10)
+
+
+def _bits(t):
+    """16-bit tensors are stored as their raw uint16 patterns (numpy has no bfloat16)."""
+    return t.contiguous().view(torch.int16).numpy().view(np.uint16) if t.dtype in (torch.float16, torch.bfloat16) else t.numpy()
+
+
+def gen_half(ref, out):
+    """The heads, the three assignments and the caller's thresholding statement (E3:2022-2023) on the 16-bit
+    probability dtypes: fp16 is what the reference itself runs (weight_dtype, E1:933), bf16 is the dtype of the
+    BASELINE headline config.  World sizes are simulated as in gen_assign_mc; cases keep world * S within the
+    integers the dtype represents exactly (fp16: 2048, bf16: 256), because beyond that the reference's own
+    all-reduce(SUM) in that dtype is order-dependent (NCCL ring vs tree) and has no single answer."""
+    rng = np.random.Generator(np.random.PCG64(21))
+    torch.manual_seed(5991)
+    res = {}
+    # ---- heads: softmax / argmax / scatter in the 16-bit dtype
+    n = 29
+    selector = rng.uniform(size=n) > 0.25
+    m = int(selector.sum())
+    chips = torch.zeros(n, 1)
+    for dn, dt in HALF_DTYPES:
+        for tag, path, fn, kh in (("e1", E1, "get_face_gender", 80), ("e3", E3, "get_face_gender_race", 6),
+                                  ("e4", E4, "get_face_gender_race_age", 8)):
+            logits = torch.tensor((rng.normal(size=(m, kh)) * 2.5).astype(np.float32)).to(dt)
+            state = {"next": logits}
+            clf = lambda x, s=state: s["next"].clone()
+            ns = make_namespace(_Recorder(), {"gender_classifier": clf, "gender_race_classifier": clf,
+                                              "gender_race_age_classifier": clf})
+            compile_into(ns, lift(os.path.join(ref, path), [fn]).values())
+            outs = ns[fn](chips, selector=torch.tensor(selector), fill_value=-1)
+            res[f"heads_{dn}_{tag}_logits"] = _bits(logits)
+            for k, o in enumerate(outs):
+                res[f"heads_{dn}_{tag}_out{k}"] = _bits(o)
+    res["heads_selector"] = selector
+    # ---- E1 rank / binomial assignment (tie-free second column: argsort is unstable)
+    ns = make_namespace(_Recorder())
+    compile_into(ns, lift(os.path.join(ref, E1), ["generate_dynamic_targets"]).values())
+    for dn, dt in HALF_DTYPES:
+        for c, (n, frac, ratio) in enumerate([(64, 0.1, 0.5), (150, 0.05, 0.5), (41, 0.0, 0.3)]):
+            lo, hi = (0.05, 0.95)
+            vals = torch.linspace(lo, hi, 4 * n).to(dt).unique()          # distinct 16-bit values
+            pick = torch.tensor(rng.permutation(vals.numel())[:n])
+            p1 = vals[pick]
+            p = torch.stack([(1 - p1.float()).to(dt), p1], dim=1)
+            miss = torch.tensor(rng.uniform(size=n) < frac)
+            p[miss] = -1
+            t, u = ns["generate_dynamic_targets"](p, target_ratio=ratio, w_uncertainty=True)
+            t_thr = t.clone(); t_thr[u > THRESHOLD] = -1                     # E1:1835
+            res[f"e1_{dn}_probs_{c}"] = _bits(p); res[f"e1_{dn}_ratio_{c}"] = np.array(ratio)
+            res[f"e1_{dn}_targets_{c}"] = t.numpy(); res[f"e1_{dn}_unc_{c}"] = _bits(u); res[f"e1_{dn}_thr_{c}"] = t_thr.numpy()
+        res[f"e1_{dn}_n_cases"] = np.array(3)
+    # ---- E3 / E4 Monte-Carlo assignment
+    cases = {"f16": [(48, 0.1, 1, 100, 2.5), (40, 0.0, 2, 100, 2.5), (36, 0.1, 8, 100, 2.5), (30, 0.0, 1, 100, 0.6), (44, 0.0, 4, 100, 1.2)],
+             "bf16": [(48, 0.1, 1, 100, 2.5), (40, 0.0, 2, 100, 2.5), (32, 0.0, 4, 60, 2.5), (30, 0.0, 1, 100, 0.6), (44, 0.1, 2, 128, 1.2)]}
+    for tag, path, fn, widths in (("e3", E3, "generate_dynamic_targets_gender_race", (2, 4)),
+                                  ("e4", E4, "generate_dynamic_targets_gender_race_age", (2, 4, 2))):
+        rec = _Recorder()
+        ns = make_namespace(rec, {"np": _LegacyNp()})
+        compile_into(ns, lift(os.path.join(ref, path), [fn]).values())
+        for dn, dt in HALF_DTYPES:
+            for c, (n, frac, world, S, sharp) in enumerate(cases[dn]):
+                miss = rng.uniform(size=n) < frac
+                probs = []
+                for w in widths:
+                    p = torch.tensor(peaked_probs(rng, n, w, sharp)).to(dt)
+                    p[torch.tensor(miss)] = -1
+                    probs.append(p)
+                draws, outs = _run_world(ns, fn, rec, probs, world, S)
+                key = f"{tag}_{dn}"
+                for k, p in enumerate(probs):
+                    res[f"{key}_probs{k}_{c}"] = _bits(p)
+                res[f"{key}_world_{c}"] = np.array(world); res[f"{key}_S_{c}"] = np.array(S)
+                for r, dr in enumerate(draws):
+                    for k, d in enumerate(dr):
+                        res[f"{key}_rand{k}_r{r}_{c}"] = _bits(d)
+                for k, o in enumerate(outs):
+                    res[f"{key}_out{k}_{c}"] = _bits(o)
+                for a in range(len(widths)):                               # E3:2022-2023 / E4:2129-2131
+                    t = outs[2 * a].clone(); t[outs[2 * a + 1] > THRESHOLD] = -1
+                    res[f"{key}_thr{a}_{c}"] = t.numpy()
+            res[f"{tag}_{dn}_n_cases"] = np.array(len(cases[dn]))
+    np.savez_compressed(os.path.join(out, "half.npz"), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -484,6 +576,7 @@ def main():
     gen_assign_e1(a.ref, a.out)
     gen_assign_mc(a.ref, a.out)
     gen_hooks(a.ref, a.out)
+    gen_half(a.ref, a.out)
     with open(os.path.join(a.out, "VERSIONS.txt"), "w") as f:
         f.write(f"torch {torch.__version__}\ntorchvision {torchvision.__version__}\nnumpy {np.__version__}\nscipy {scipy.__version__}\n")
     print("golden fixtures written to", a.out)

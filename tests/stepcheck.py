@@ -1,0 +1,174 @@
+"""Checker shared by ``__graft_entry__.smoke()`` and the ``-m gpu`` tests: runs ``GuidancePath.step`` on the GPU and
+compares it, stage by stage, with the oracle (``oracle/``).  Test infrastructure -- nothing in the product imports it.
+
+Two checks:
+
+* ``check_small_steps``   -- the three experiment kinds end to end on 12 fp32 images of 256x256 (every stage, incl. the
+  head, from the same fp32 inputs on both sides).
+* ``check_step_vs_oracle`` -- one step at a BASELINE shape (512x512 images, 224x224 crops, any dtype / batch), compared
+  piecewise so that each bar of BASELINE.json applies to the stage it names:
+    boxes                       bit-exact
+    head logits                 within ``rtol`` of the fp32 torch reference of the same weights
+    probabilities / argmax      the oracle's softmax of the DEVICE logits (<= 1 unit in the last place; preds exact)
+    target classes              bit-exact against the oracle's assignment of the DEVICE probabilities and the same draws
+                                (``literal=False``: same arithmetic, vectorised), before and after thresholding
+    losses                      within ``rtol``
+    crops, resized images and the image gradient, on ``n_grad`` images, within ``rtol`` (gradient: of its largest entry)
+"""
+import numpy as np
+import torch
+
+RTOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2, torch.float16: 5e-3}      # BASELINE.json north_star: 1e-3 fp32, 2e-2 bf16
+
+
+def _to(v, device):
+    if torch.is_tensor(v):
+        return v.to(device)
+    if isinstance(v, list):
+        return [_to(x, device) for x in v]
+    return v
+
+
+def check_small_steps(device="cuda:0"):
+    from fairguide import pipeline
+    from oracle import pipeline as opipe
+    torch.cuda.set_device(device)
+    for kind in ("gender", "gender_race", "gender_race_age"):
+        cfg = pipeline.GuidanceConfig(kind=kind, num_samples_per_device=20)
+        host = pipeline.synth_batch(12, cfg, torch.float32, "cpu", seed=7, H=256, W=256, max_faces=2, host=True)
+        head = pipeline.make_head_weights(cfg, torch.float32, "cpu")
+        dev_batch = {k: _to(v, device) for k, v in host.items()}
+        nv = int((host["counts"] > 0).sum())
+        rands = None
+        if kind != "gender":
+            g = torch.Generator().manual_seed(3)
+            rands = tuple(torch.rand(cfg.num_samples_per_device, nv, generator=g) for _ in range(cfg.n_attr))
+        out = pipeline.GuidancePath(cfg, tuple(t.to(device) for t in head)).step(
+            dev_batch, rand_tensors=None if rands is None else tuple(r.to(device) for r in rands), num_valid=nv)
+        ref = opipe.step(host, cfg, head, rand_tensors=rands)
+        torch.cuda.synchronize()
+        assert torch.equal(out["boxes"].cpu(), ref["boxes"]), kind
+        for a in range(cfg.n_attr):
+            assert torch.equal(out["targets"][a].cpu(), ref["targets"][a]), (kind, a)
+        np.testing.assert_allclose(out["chips"].cpu().numpy(), ref["chips"].numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(out["small"].cpu().numpy(), ref["small"].numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(out["loss"].cpu().numpy(), ref["loss"].numpy(), rtol=1e-3, atol=1e-4)
+        gref = ref["g_images"].numpy()
+        np.testing.assert_allclose(out["g_images"].cpu().numpy(), gref, rtol=1e-3, atol=1e-3 * float(np.abs(gref).max()))
+    return True
+
+
+def _ulps16(a, b):
+    return (a.contiguous().view(torch.int16).long() - b.contiguous().view(torch.int16).long()).abs()
+
+
+def check_step_vs_oracle(kind="gender_race_age", n=1024, dtype=torch.bfloat16, n_grad=32, S=100, seed=5991, device="cuda:0",
+                         max_faces=1, captured=False):
+    """One ``GuidancePath.step`` (or its CUDA-graph replay) on ``n`` synthetic 512x512 images against the oracle; see the
+    module docstring for what is compared with what.  Returns a dict of the measured errors."""
+    from fairguide import pipeline
+    from oracle import assign as oassign, boxes as oboxes, crop as ocrop, head as ohead, hooks as ohooks, loss as oloss
+    dev = torch.device(device)
+    torch.cuda.set_device(dev)
+    rtol = RTOL[dtype]
+    cfg = pipeline.GuidanceConfig(kind=kind, num_samples_per_device=S)
+    widths, col_start, k_head, K, e1_rule = pipeline.KINDS[kind]
+    n_attr = len(widths)
+    head = pipeline.make_head_weights(cfg, dtype, dev)
+    batch = pipeline.synth_batch_device(n, cfg, dtype, dev, seed=seed, max_faces=max_faces)
+    nv = int((batch["counts"] > 0).sum())
+    rands = None
+    if kind != "gender":
+        g = torch.Generator().manual_seed(seed + 1)
+        rands = tuple(torch.rand(S, nv, generator=g).to(dtype) for _ in range(n_attr))
+    rands_dev = None if rands is None else tuple(r.to(dev) for r in rands)
+    path = pipeline.GuidancePath(cfg, head)
+    out = path.step(batch, rand_tensors=rands_dev, num_valid=nv)
+    torch.cuda.synchronize()
+    cpu = lambda t: t.detach().cpu()
+    report = {}
+
+    # ---- boxes: bit-exact
+    ind_ref, boxes_ref = oboxes.select_and_expand(cpu(batch["cand_boxes"]).numpy(), cpu(batch["counts"]).numpy(), 512, cfg.expand_coef, 1, -1)
+    assert np.array_equal(cpu(out["indicators"]).numpy(), ind_ref) and np.array_equal(cpu(out["boxes"]).numpy(), boxes_ref)
+    ind = torch.tensor(ind_ref)
+    boxes = torch.tensor(boxes_ref)
+
+    # ---- head: logits vs the fp32 torch reference of the same (dtype-rounded) weights
+    w1, b1, w2, b2 = [cpu(t).float() for t in head]
+    ref_logits = ohead.mobilenet_head_reference(cpu(batch["pooled"]).float(), w1, b1, w2, b2)
+    err = (cpu(out["logits"]).float() - ref_logits).abs().max().item()
+    report["logits_max_err"] = err
+    assert err <= rtol * float(ref_logits.abs().max()), ("head logits", err)
+
+    # ---- probabilities / predictions: the oracle's 16-bit (or fp32) softmax of the DEVICE logits
+    dev_logits = cpu(out["logits"]).to(dtype)
+    fn = {"gender": ohead.get_face_gender, "gender_race": ohead.get_face_gender_race, "gender_race_age": ohead.get_face_gender_race_age}[kind]
+    houts = fn(lambda x: dev_logits[ind], torch.zeros(n, 1, dtype=dtype), selector=ind, fill_value=-1)
+    probs_dev = [cpu(p) for p in out["probs"]]
+    for a in range(n_attr):
+        assert torch.equal(cpu(out["preds"][a]), houts[3 * a]), ("preds", a)
+        if dtype == torch.float32:
+            assert torch.allclose(probs_dev[a], houts[3 * a + 1], rtol=1e-5, atol=1e-7), ("probs", a)
+        else:
+            assert int(_ulps16(probs_dev[a], houts[3 * a + 1]).max()) <= 1, ("probs", a)
+
+    # ---- assignment: bit-exact on the device probabilities and the same draws
+    if kind == "gender":
+        t_all, u_all = oassign.generate_dynamic_targets(probs_dev[0], cfg.target_ratio, True)
+        res = (t_all, u_all)
+    elif kind == "gender_race":
+        res = oassign.generate_dynamic_targets_gender_race(probs_dev[0], probs_dev[1], True, S, rand_tensors=rands, literal=False)
+    else:
+        res = oassign.generate_dynamic_targets_gender_race_age(probs_dev[0], probs_dev[1], probs_dev[2], True, S, rand_tensors=rands,
+                                                               literal=False)
+    targets = []
+    for a in range(n_attr):
+        t = res[2 * a].clone()
+        t[res[2 * a + 1] > cfg.uncertainty_threshold] = -1                                   # E3:2022-2023
+        targets.append(t)
+        assert torch.equal(cpu(out["targets"][a]), t), ("targets", a, int((cpu(out["targets"][a]) != t).sum()))
+    report["rows_with_target"] = [int((t != -1).sum()) for t in targets]
+
+    # ---- losses
+    logits_attr = [cpu(out["logits"])[:, c:c + w] for c, w in zip(col_start, widths)]
+    logits_attr = [l.to(dtype).float() for l in logits_attr]
+    loss_fair = [oloss.fairness_ce(logits_attr[a], targets[a], ind, torch.float32) for a in range(n_attr)]
+    preds_ori = [cpu(p) for p in batch["preds_ori"]]
+    f2, f1 = list(cfg.factors2[:n_attr]), list(cfg.factors1[:n_attr])
+    dyn_w = ohooks.gen_dynamic_weights(ind, targets, preds_ori, f1, torch.float32, e1_rule)
+    assert torch.equal(cpu(out["dyn_weights"]), dyn_w)
+    loss = oloss.assemble(loss_fair, dyn_w, cpu(batch["loss_clip"]).float(), cpu(batch["loss_dino"]).float(), cpu(batch["loss_face"]).float(),
+                          cfg.weight_loss_img, cfg.weight_loss_face)
+    np.testing.assert_allclose(cpu(out["loss"]).float().numpy(), loss.numpy(), rtol=rtol, atol=rtol)
+    for a in range(n_attr):
+        np.testing.assert_allclose(cpu(out["loss_fair"][a]).float().numpy(), loss_fair[a].numpy(), rtol=rtol, atol=rtol)
+
+    # ---- crops, resized images, image gradient on a subset (first n_grad images + every no-face image among the first 4*n_grad)
+    idx = list(range(min(n_grad, n))) + [i for i in range(min(n_grad, n), min(4 * n_grad, n)) if not bool(ind[i])][:2]
+    idx_t = torch.tensor(idx)
+    x = cpu(batch["images"][idx_t.to(dev)]).float().requires_grad_(True)
+    sub = lambda t: t[idx_t]
+    bbox_ori = cpu(out["bbox_ori"])
+    chips_ref = ocrop.crop_faces(x, sub(boxes), sub(ind), cfg.size_face, cfg.fill_value)
+    hooked = ohooks.apply_grad_hook_face(x, sub(boxes), sub(bbox_ori), [sub(t) for t in targets], [sub(p) for p in preds_ori], f2, e1_rule)
+    small_ref = ocrop.resize_small(hooked, cfg.img_size_small)
+    gc, gs = cpu(batch["g_chips"][idx_t.to(dev)]).float(), cpu(batch["g_small"][idx_t.to(dev)]).float()
+    ((chips_ref * gc).sum() + (small_ref * gs).sum()).backward()
+    atol16 = rtol if dtype != torch.float32 else 1e-5
+    np.testing.assert_allclose(cpu(out["chips"][idx_t.to(dev)]).float().numpy(), chips_ref.detach().numpy(), rtol=rtol, atol=atol16)
+    np.testing.assert_allclose(cpu(out["small"][idx_t.to(dev)]).float().numpy(), small_ref.detach().numpy(), rtol=rtol, atol=atol16)
+    gref = x.grad.numpy()
+    got = cpu(out["g_images"][idx_t.to(dev)]).float().numpy()
+    report["g_images_max_err_rel"] = float(np.abs(got - gref).max() / np.abs(gref).max())
+    np.testing.assert_allclose(got, gref, rtol=rtol, atol=rtol * float(np.abs(gref).max()))
+
+    # ---- the CUDA-graph replay of the same step (what bench.py times) returns the same integers
+    if captured:
+        cap = pipeline.CapturedStep(path, batch, nv)
+        o2 = cap.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o2["boxes"], out["boxes"]) and torch.equal(o2["chips"], out["chips"]) and torch.equal(o2["small"], out["small"])
+        if kind == "gender":
+            assert torch.equal(o2["g_images"], out["g_images"])
+    return report

@@ -60,9 +60,9 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             for line in src.splitlines():
-                if re.match(r"\s*(from|import)\s+oracle\b", line):
-                    # the only permitted import is inside smoke_check (the oracle as checker)
-                    assert fn == "pipeline.py" and "opipe" in line, (fn, line)
+                # no import of the oracle or of the tests' checker anywhere in the product package
+                assert not re.match(r"\s*(from|import)\s+(oracle|tests)\b", line), (fn, line)
+            assert "oracle" not in src.replace("the oracle", "").replace("oracle sees", "").replace("oracle's", ""), fn
 
 
 _WORKER = r"""

@@ -514,10 +514,110 @@ def test_epilogue_matches_torch_cuda_ops(fg):
         close(us[0], ref_u.cpu().numpy(), rtol=0, atol=3e-7)
 
 
+# ----------------------------------------------------------------------------- 16-bit probability dtypes (half.npz)
+def _ulp_diff(t, arr):
+    """|difference| in units of the last place between a 16-bit tensor and a raw-pattern fixture (same-sign values)."""
+    got = t.detach().cpu().contiguous().view(torch.int16).numpy().astype(np.int64)
+    return np.abs(got - arr.view(np.int16).astype(np.int64))
+
+
+@pytest.mark.parametrize("dn", ["f16", "bf16"])
+@pytest.mark.parametrize("tag,kind", [("e1", "gender"), ("e3", "gender_race"), ("e4", "gender_race_age")])
+def test_head_attributes_half_golden(fg, dn, tag, kind):
+    """Softmax / argmax / scatter in the reference's fp16 (E1:933) and in bf16 (BASELINE C5), against the outputs of the
+    reference's own function bodies on 16-bit logits: predictions and scattered logits bit-exact, probabilities within one
+    unit in the last place (device expf vs the host's) and identical wherever the reference's argmax is decided."""
+    from tests._golden import half_equal, half_tensor
+    g = load("half")
+    sel = torch.tensor(g["heads_selector"], device=DEV)
+    logits = half_tensor(g[f"heads_{dn}_{tag}_logits"], dn)
+    dt = logits.dtype
+    outs = fg.api._heads(kind, lambda x: logits.float().to(DEV), torch.zeros(sel.shape[0], 1, device=DEV, dtype=dt), sel, -1)
+    for k, o in enumerate(outs):
+        ref = g[f"heads_{dn}_{tag}_out{k}"]
+        if o.dtype == torch.int64:
+            assert np.array_equal(o.cpu().numpy(), ref), (dn, tag, k)
+        elif k % 3 == 2:
+            assert half_equal(o, ref), (dn, tag, k)
+        else:
+            assert o.dtype == dt and _ulp_diff(o, ref).max() <= 1, (dn, tag, k)
+
+
+@pytest.mark.parametrize("dn", ["f16", "bf16"])
+def test_assign_e1_half_golden(fg, dn):
+    from tests._golden import half_tensor
+    g = load("half")
+    for c in range(int(g[f"e1_{dn}_n_cases"])):
+        p = half_tensor(g[f"e1_{dn}_probs_{c}"], dn).to(DEV)
+        ratio = float(g[f"e1_{dn}_ratio_{c}"])
+        t, u = fg.generate_dynamic_targets(p, target_ratio=ratio, w_uncertainty=True)
+        assert np.array_equal(t.cpu().numpy(), g[f"e1_{dn}_targets_{c}"])
+        assert u.dtype == p.dtype and _ulp_diff(u, g[f"e1_{dn}_unc_{c}"]).max() <= 1       # lgamma-based CDF vs Boost's
+        t2, _ = fg.generate_dynamic_targets(p, target_ratio=ratio, w_uncertainty=True, uncertainty_threshold=0.2)
+        assert np.array_equal(t2.cpu().numpy(), g[f"e1_{dn}_thr_{c}"])
+
+
+@pytest.mark.parametrize("dn", ["f16", "bf16"])
+@pytest.mark.parametrize("tag", ["e3", "e4"])
+def test_assign_mc_half_golden(fg, dn, tag):
+    """The Monte-Carlo assignment on 16-bit probabilities and 16-bit draws (what BASELINE C5 and the reference's fp16 runs
+    feed it): targets, uncertainty BIT PATTERNS and thresholded targets equal the reference's own function body, with
+    simulated world sizes up to 8 (per-rank int32 counts summed like the all-reduce; rank sums up to 800)."""
+    from tests._golden import half_equal, half_tensor
+    g = load("half")
+    n_attr = 2 if tag == "e3" else 3
+    K = 8 if tag == "e3" else 16
+    key = f"{tag}_{dn}"
+    for c in range(int(g[f"{key}_n_cases"])):
+        probs = [half_tensor(g[f"{key}_probs{k}_{c}"], dn).to(DEV) for k in range(n_attr)]
+        world, S = int(g[f"{key}_world_{c}"]), int(g[f"{key}_S_{c}"])
+        nv = int(((probs[0] != -1).all(-1) * (probs[1] != -1).all(-1)).sum())
+        ws = fg.ops.OtWorkspace(probs[0].shape[0], K, S, DEV)
+        total = None
+        for r in range(world):
+            rands = tuple(half_tensor(g[f"{key}_rand{k}_r{r}_{c}"], dn).to(DEV) for k in range(n_attr))
+            cnt = fg.ops.ot_plan_counts(probs[0], probs[1], probs[2] if n_attr == 3 else None, rands, nv, ws)
+            assert ws.status()[0] == 0
+            total = cnt if total is None else total + cnt
+        ts, us = fg.ops.ot_targets(total, probs[0], probs[1], nv, ws, -1.0, True)
+        ts2, _ = fg.ops.ot_targets(total, probs[0], probs[1], nv, ws, 0.2, True)
+        for a in range(n_attr):
+            assert np.array_equal(ts[a].cpu().numpy(), g[f"{key}_out{2 * a}_{c}"]), (key, c, a)
+            assert half_equal(us[a], g[f"{key}_out{2 * a + 1}_{c}"]), (key, c, a)
+            assert np.array_equal(ts2[a].cpu().numpy(), g[f"{key}_thr{a}_{c}"]), (key, c, a)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,kind,S", [(1024, "e4", 100), (2048, "e3", 40)])
+def test_assign_mc_half_large_vs_oracle(fg, dtype, N, kind, S):
+    """BASELINE-size assignment (C5: 1024 rows, K = 16, 100 draws) on 16-bit probabilities and draws vs the oracle."""
+    from oracle import assign as oassign
+    n_attr = 2 if kind == "e3" else 3
+    rng = np.random.default_rng(N + 1)
+    probs = [torch.tensor(peaked_probs(rng, N, w, 1.5)).to(dtype) for w in ([2, 4] if n_attr == 2 else [2, 4, 2])]
+    miss = torch.tensor(rng.uniform(size=N) < 0.05)
+    for p in probs:
+        p[miss] = -1
+    nv = int((~miss).sum())
+    gen = torch.Generator().manual_seed(N)
+    rands = tuple(torch.rand(S, nv, generator=gen).to(dtype) for _ in range(n_attr))
+    fn = oassign.generate_dynamic_targets_gender_race if n_attr == 2 else oassign.generate_dynamic_targets_gender_race_age
+    ref = fn(*probs, True, S, rand_tensors=rands, literal=False)
+    api_fn = fg.generate_dynamic_targets_gender_race if n_attr == 2 else fg.generate_dynamic_targets_gender_race_age
+    out = api_fn(*[p.to(DEV) for p in probs], True, S, rand_tensors=tuple(r.to(DEV) for r in rands), num_valid=nv)
+    for a in range(2 * n_attr):
+        assert torch.equal(out[a].cpu(), ref[a]), (kind, N, a)
+    thr = api_fn(*[p.to(DEV) for p in probs], True, S, rand_tensors=tuple(r.to(DEV) for r in rands), num_valid=nv,
+                 uncertainty_threshold=0.2)
+    for a in range(n_attr):
+        t_ref, _ = oassign.threshold_and_slice(ref[2 * a], ref[2 * a + 1], 0.2, N, 0)
+        assert torch.equal(thr[2 * a].cpu(), t_ref), (kind, N, a)
+
+
 # ----------------------------------------------------------------------------- whole path
 def test_pipeline_smoke_vs_oracle(fg):
-    from fairguide import pipeline
-    assert pipeline.smoke_check("cuda:0")
+    from tests import stepcheck
+    assert stepcheck.check_small_steps("cuda:0")
 
 
 @pytest.mark.parametrize("kind", ["gender", "gender_race_age"])

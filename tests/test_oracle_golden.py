@@ -123,3 +123,56 @@ def test_hooks_and_weights(tag):
 
 def test_oracle_header_says_test_infrastructure():
     assert "TEST INFRASTRUCTURE" in oracle.__doc__
+
+
+# ----------------------------------------------------------------------------- 16-bit probability dtypes (half.npz)
+HALF = ["f16", "bf16"]
+
+
+@pytest.mark.parametrize("dn", HALF)
+@pytest.mark.parametrize("tag,fn", [("e1", ohead.get_face_gender), ("e3", ohead.get_face_gender_race), ("e4", ohead.get_face_gender_race_age)])
+def test_heads_half(dn, tag, fn):
+    """fp16 is the reference's own classifier dtype (E1:933), bf16 the BASELINE headline dtype."""
+    from tests._golden import half_equal, half_tensor
+    g = load("half")
+    sel = torch.tensor(g["heads_selector"])
+    logits = half_tensor(g[f"heads_{dn}_{tag}_logits"], dn)
+    outs = fn(lambda x: logits.clone(), torch.zeros(sel.shape[0], 1), selector=sel, fill_value=-1)
+    for k, o in enumerate(outs):
+        ref = g[f"heads_{dn}_{tag}_out{k}"]
+        assert (np.array_equal(o.numpy(), ref) if o.dtype == torch.int64 else half_equal(o, ref)), (dn, tag, k)
+
+
+@pytest.mark.parametrize("dn", HALF)
+def test_assign_e1_half(dn):
+    from tests._golden import half_equal, half_tensor
+    g = load("half")
+    for c in range(int(g[f"e1_{dn}_n_cases"])):
+        p = half_tensor(g[f"e1_{dn}_probs_{c}"], dn)
+        t, u = oassign.generate_dynamic_targets(p, target_ratio=float(g[f"e1_{dn}_ratio_{c}"]), w_uncertainty=True)
+        assert np.array_equal(t.numpy(), g[f"e1_{dn}_targets_{c}"]) and half_equal(u, g[f"e1_{dn}_unc_{c}"])
+        t_thr, _ = oassign.threshold_and_slice(t, u, 0.2, t.shape[0], 0)
+        assert np.array_equal(t_thr.numpy(), g[f"e1_{dn}_thr_{c}"])
+
+
+@pytest.mark.parametrize("dn", HALF)
+@pytest.mark.parametrize("tag", ["e3", "e4"])
+@pytest.mark.parametrize("literal", [True, False])
+def test_assign_mc_half(dn, tag, literal):
+    """Targets, uncertainties (bit patterns) and thresholded targets of the Monte-Carlo assignment on 16-bit
+    probabilities, simulated world sizes up to 8 (fp16) / 4 (bf16)."""
+    from tests._golden import half_equal, half_tensor
+    g = load("half")
+    n_attr = 2 if tag == "e3" else 3
+    fn = oassign.generate_dynamic_targets_gender_race if tag == "e3" else oassign.generate_dynamic_targets_gender_race_age
+    key = f"{tag}_{dn}"
+    for c in range(int(g[f"{key}_n_cases"])):
+        probs = [half_tensor(g[f"{key}_probs{k}_{c}"], dn) for k in range(n_attr)]
+        world, S = int(g[f"{key}_world_{c}"]), int(g[f"{key}_S_{c}"])
+        wr = [tuple(half_tensor(g[f"{key}_rand{k}_r{r}_{c}"], dn) for k in range(n_attr)) for r in range(world)]
+        outs = fn(*probs, w_uncertainty=True, num_samples_per_device=S, world_rand=wr, literal=literal)
+        for a in range(n_attr):
+            assert np.array_equal(outs[2 * a].numpy(), g[f"{key}_out{2 * a}_{c}"]), (key, c, a)
+            assert half_equal(outs[2 * a + 1], g[f"{key}_out{2 * a + 1}_{c}"]), (key, c, a)
+            t_thr, _ = oassign.threshold_and_slice(outs[2 * a], outs[2 * a + 1], 0.2, outs[0].shape[0], 0)
+            assert np.array_equal(t_thr.numpy(), g[f"{key}_thr{a}_{c}"]), (key, c, a)
