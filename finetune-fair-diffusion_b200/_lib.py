@@ -34,6 +34,7 @@ SIGNATURES = {
     "fg_head_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _z, _i, _p]),
     "fg_head_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _z, _i, _p]),
     "fg_head_attributes": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p]),
+    "fg_head_attributes_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "fg_fair_ce_fwd": (_i, [_p, _p, _p, _i, _i, _f, _p, _i, _p]),
     "fg_fair_ce_bwd": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p]),
     "fg_fair_loss_fused": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _f, _f, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _p]),
@@ -101,7 +102,7 @@ CALLS = collections.Counter()      # C-ABI calls made so far, by entry point (be
 # kernels launched per successful call (fg_ot_plan_counts adds one per coarse-to-fine level, see ot_levels)
 KERNELS_PER_CALL = {
     "fg_select_expand_boxes": 1, "fg_crop_resize_fwd": 1, "fg_guidance_factors": 1, "fg_image_grad": 1,
-    "fg_region_scale": 1, "fg_head_fwd": 2, "fg_head_bwd": 2, "fg_head_attributes": 1, "fg_fair_ce_fwd": 1,
+    "fg_region_scale": 1, "fg_head_fwd": 2, "fg_head_bwd": 2, "fg_head_attributes": 1, "fg_head_attributes_bwd": 1, "fg_fair_ce_fwd": 1,
     "fg_fair_ce_bwd": 1, "fg_fair_loss_fused": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
     "fg_ot_solve_single": 2, "fg_ot_cost_matrix": 2, "fg_stage_detector_input": 1, "fg_bias_metrics": 1,
     "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2, "fg_align_matrices": 1, "fg_aligned_warp_fwd": 1,

@@ -26,15 +26,33 @@ _HEADS = {
     "gender": ([40], [2]),                    # E1:1370  logits.view(B,-1,2)[:,20,:]
     "gender_race": ([0, 2], [2, 4]),          # E3:1404-1407
     "gender_race_age": ([0, 2, 6], [2, 4, 2]),  # E4:1398-1403
+    "race": ([2], [4]),                       # exp-6-debias-race/1-main-debias.py:1381  logits[:,2:] of the 6-way head
 }
 
 
 # ----------------------------------------------------------------------------- boxes / crop
 def expand_bbox(bbox, expand_coef, target_ratio):
-    """E1:238-265.  ``bbox`` = 4 numbers (numpy float32 in the reference) -> list of 4 ints."""
-    b = torch.as_tensor([[float(v) for v in bbox]], dtype=torch.float32, device="cuda").view(1, 1, 4)
-    _, out = ops.select_expand_boxes(b, None, 1 << 30, expand_coef, target_ratio)
-    return [int(v) for v in out[0].tolist()]
+    """E1:238-265.  ``bbox`` = 4 numbers (numpy float32 scalars in the reference) -> list of 4 ints.
+
+    Four numbers in, four out, called once per detected face from a host loop (E1:1335): this is host work in the
+    reference and stays host work here (a kernel launch plus a blocking read-back costs ~50x the ten flops).  The
+    arithmetic is the one select_expand_kernel (csrc/fg_boxes.cu, the batched entry ``select_and_expand``) performs, spelled
+    with explicit float32 / float64 casts: width, height and their ratio are float32 (numpy float32 scalar op scalar),
+    everything that touches ``expand_coef`` / ``target_ratio`` / 0.5 (Python numbers) is float64 under the reference's
+    pinned NumPy 1.26, and ``round`` is half-to-even."""
+    f32, f64 = np.float32, np.float64
+    b = [f32(v) for v in bbox]
+    w, h = f32(b[2] - b[0]), f32(b[3] - b[1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = f32(h / w)
+    if f64(ratio) > f64(target_ratio):
+        extra_h = f64(h) * f64(expand_coef)
+        extra_w = (f64(h) + extra_h) / f64(target_ratio) - f64(w)
+    else:
+        extra_w = f64(w) * f64(expand_coef)
+        extra_h = (f64(w) + extra_w) * f64(target_ratio) - f64(h)
+    hw, hh = extra_w * f64(0.5), extra_h * f64(0.5)
+    return [int(np.rint(f64(b[0]) - hw)), int(np.rint(f64(b[1]) - hh)), int(np.rint(f64(b[2]) + hw)), int(np.rint(f64(b[3]) + hh))]
 
 
 def select_and_expand(boxes, counts, dim_max, expand_coef=0.5, target_ratio=1, fill_value=-1):
@@ -108,9 +126,9 @@ class _HeadAttributes(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, src_row, selector, n, kind, fill, dtype):
         cs, ws = _HEADS[kind]
-        preds, probs, louts = ops.head_attributes(logits, src_row, selector, n, cs, ws, fill, dtype)
-        ctx.kind, ctx.shape = kind, tuple(logits.shape)
-        ctx.save_for_backward(src_row, selector, *probs)
+        preds, probs, louts, flat = ops.head_attributes(logits, src_row, selector, n, cs, ws, fill, dtype, return_flat=True)
+        ctx.kind, ctx.shape, ctx.n = kind, tuple(logits.shape), n
+        ctx.save_for_backward(src_row, selector, flat)
         out = []
         for a in range(len(ws)):
             out += [preds[a], probs[a], louts[a]]
@@ -119,22 +137,12 @@ class _HeadAttributes(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
+        # one launch (fg_head_attributes_bwd): sliced-logit gradients plus the softmax backward of the probability gradients
         cs, ws = _HEADS[ctx.kind]
-        src_row, selector, *probs = ctx.saved_tensors
-        g_full = torch.zeros(ctx.shape, dtype=torch.float32, device=grads[0].device if grads[0] is not None else probs[0].device)
-        rows = torch.arange(g_full.shape[0], device=g_full.device) if src_row is None else None
-        for a, (c, w) in enumerate(zip(cs, ws)):
-            g_probs, g_logits = grads[3 * a + 1], grads[3 * a + 2]
-            sel = slice(None) if selector is None else selector
-            acc = None
-            if g_logits is not None:
-                acc = g_logits[sel].float()
-            if g_probs is not None:
-                p, gp = probs[a][sel].float(), g_probs[sel].float()
-                term = p * (gp - (gp * p).sum(-1, keepdim=True))
-                acc = term if acc is None else acc + term
-            if acc is not None:
-                g_full[:, c:c + w] += acc
+        src_row, selector, flat = ctx.saved_tensors
+        A = len(ws)
+        g_full = ops.head_attributes_bwd(flat, [grads[3 * a + 1] for a in range(A)], [grads[3 * a + 2] for a in range(A)],
+                                         src_row, selector, ctx.n, ctx.shape[0], ctx.shape[1], cs, ws)
         return g_full, None, None, None, None, None, None
 
 
@@ -169,6 +177,12 @@ def get_face_gender_race(face_chips, selector=None, fill_value=-1, *, gender_rac
 def get_face_gender_race_age(face_chips, selector=None, fill_value=-1, *, gender_race_age_classifier):
     """E4:1378-1475 -> 9-tuple (6-tuple when selector is None, like the reference)."""
     return _heads("gender_race_age", gender_race_age_classifier, face_chips, selector, fill_value)
+
+
+def get_face_race(face_chips, selector=None, fill_value=-1, *, race_classifier):
+    """exp-6-debias-race/1-main-debias.py:1365-1411 -> (preds_race, probs_race, logits_race): columns 2..5 of the 6-way
+    gender+race head."""
+    return _heads("race", race_classifier, face_chips, selector, fill_value)
 
 
 # ----------------------------------------------------------------------------- assignment
@@ -365,6 +379,36 @@ def _as_lists(args, n_attr):
     return [args[3 * a] for a in range(n_attr)], [args[3 * a + 1] for a in range(n_attr)]
 
 
+def _split_factors(attr_args, factors, names, defaults):
+    """The reference's signatures end in ``factor...=default`` parameters that a caller may also pass positionally
+    (E1:1584, E3:1751, E4:1823): trailing plain numbers of ``attr_args`` are those factors, in declaration order."""
+    attr_args = list(attr_args)
+    pos = []
+    while attr_args and not torch.is_tensor(attr_args[-1]) and isinstance(attr_args[-1], (int, float)):
+        pos.insert(0, attr_args.pop())
+    if len(attr_args) % 3 != 0 or not 1 <= len(attr_args) // 3 <= 3:
+        raise TypeError("expected (targets, preds_ori, probs_ori) per attribute")
+    n_attr = len(attr_args) // 3
+    names, defaults = names[n_attr], defaults[n_attr]
+    if len(pos) > n_attr:
+        raise TypeError(f"too many positional factors: {len(pos)} for {n_attr} attribute(s)")
+    unknown = set(factors) - set(names)
+    if unknown:
+        raise TypeError(f"unexpected keyword argument(s) {sorted(unknown)}")
+    vals = []
+    for k, (nm, d) in enumerate(zip(names, defaults)):
+        if k < len(pos):
+            if nm in factors:
+                raise TypeError(f"got multiple values for argument '{nm}'")
+            vals.append(pos[k])
+        else:
+            vals.append(factors.get(nm, d))
+    return attr_args, n_attr, vals
+
+
+_FACTOR_NAMES = {1: ["factor"], 2: ["factor_gender", "factor_race"], 3: ["factor_gender", "factor_race", "factor_age"]}
+
+
 def _hook(images, face_bboxs, face_bboxs_ori, targets, preds_ori, factors, e1_rule):
     H, W = images.shape[-2:]
     region, scale, _ = ops.guidance_factors(None, face_bboxs, face_bboxs_ori, targets, preds_ori, factors, None, e1_rule,
@@ -382,29 +426,16 @@ def apply_grad_hook_face(images, face_bboxs, face_bboxs_ori, *attr_args, **facto
     """E1:1584-1617 (``factor=``), E3:1751-1784 (``factor_gender=, factor_race=``), E4:1823-1867
     (``+ factor_age=``).  ``attr_args`` = (targets, preds_ori, probs_ori) per attribute, in the
     reference's positional order.  Forward is the identity; backward scales the face region."""
-    n_attr = len(attr_args) // 3
+    attr_args, n_attr, f = _split_factors(attr_args, factors, _FACTOR_NAMES, {1: [0.1], 2: [0.3, 0.3], 3: [0.2, 0.3, 0.3]})
     targets, preds = _as_lists(attr_args, n_attr)
-    if n_attr == 1:
-        return _hook(images, face_bboxs, face_bboxs_ori, targets, preds, [factors.get("factor", 0.1)], True)
-    if n_attr == 2:
-        f = [factors.get("factor_gender", 0.3), factors.get("factor_race", 0.3)]
-    else:
-        f = [factors.get("factor_gender", 0.2), factors.get("factor_race", 0.3), factors.get("factor_age", 0.3)]
-    return _hook(images, face_bboxs, face_bboxs_ori, targets, preds, f, False)
+    return _hook(images, face_bboxs, face_bboxs_ori, targets, preds, f, n_attr == 1)
 
 
 def gen_dynamic_weights(face_indicators, *attr_args, **factors):
     """E1:1619-1633 (``factor=``), E3:1787-1803, E4:1870-1895 -> weights [b] in probs_ori's dtype."""
-    n_attr = len(attr_args) // 3
+    attr_args, n_attr, f = _split_factors(attr_args, factors, _FACTOR_NAMES, {1: [0.2], 2: [0.3, 0.6], 3: [0.2, 0.6, 0.6]})
     targets, preds = _as_lists(attr_args, n_attr)
-    dtype = attr_args[2].dtype
-    if n_attr == 1:
-        return _weights(face_indicators, targets, preds, [factors.get("factor", 0.2)], True, dtype)
-    if n_attr == 2:
-        f = [factors.get("factor_gender", 0.3), factors.get("factor_race", 0.6)]
-    else:
-        f = [factors.get("factor_gender", 0.2), factors.get("factor_race", 0.6), factors.get("factor_age", 0.6)]
-    return _weights(face_indicators, targets, preds, f, False, dtype)
+    return _weights(face_indicators, targets, preds, f, n_attr == 1, attr_args[2].dtype)
 
 
 # ----------------------------------------------------------------------------- loss
@@ -434,13 +465,18 @@ def stage_detector_input(images, to_host=True):
     return host.numpy()
 
 
-def get_evaluate_metrics(probs_gender_all, probs_race_all, probs_age_all=None):
+def get_evaluate_metrics(probs_gender_all, probs_race_all=None, probs_age_all=None):
     """E3:1716-1749 (5 numbers) / E4:1780-1821 (9 numbers with ``probs_age_all``) as python floats; one launch and one
-    device-to-host read instead of one blocking ``.item()`` per number."""
+    device-to-host read instead of one blocking ``.item()`` per number.  Called with ONE tensor it is exp-6's
+    ``get_evaluate_metrics(probs_race_all)`` (exp-6-debias-race/1-main-debias.py:1624-1638): race0..3_freq, race_gap,
+    race_pred_below_08."""
+    if probs_race_all is None:
+        return tuple(ops.bias_metrics(None, probs_gender_all, None).tolist())
     return tuple(ops.bias_metrics(probs_gender_all, probs_race_all, probs_age_all).tolist())
 
 
-def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_classifier=None, accelerator=None):
+def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_classifier=None, accelerator=None,
+         race_classifier=None):
     """Closures with the reference's exact signatures (the reference captures these objects from
     ``main``): ``fg = bind(gender_race_classifier=clf, accelerator=acc); fg.get_face_gender_race(chips, sel)``."""
     ns = types.SimpleNamespace(
@@ -457,6 +493,8 @@ def bind(gender_classifier=None, gender_race_classifier=None, gender_race_age_cl
         face_chips, selector, fill_value, gender_race_classifier=gender_race_classifier)
     ns.get_face_gender_race_age = lambda face_chips, selector=None, fill_value=-1: get_face_gender_race_age(
         face_chips, selector, fill_value, gender_race_age_classifier=gender_race_age_classifier)
+    ns.get_face_race = lambda face_chips, selector=None, fill_value=-1: get_face_race(
+        face_chips, selector, fill_value, race_classifier=race_classifier)                                   # exp-6
     ns.customized_all_gather = lambda tensor, acc=accelerator, return_tensor_other_processes=False: customized_all_gather(
         tensor, acc, return_tensor_other_processes)
     ns.stage_detector_input = stage_detector_input

@@ -173,6 +173,40 @@ __global__ void head_attr_kernel(const float* __restrict__ logits, int m, int k_
     }
 }
 
+
+// backward of head_attr_kernel: one thread per image row; writes the WHOLE row of g_logits_full it owns
+// (zeros outside the attribute slices), so no memset is needed.  g_full[row, c_a + q] = g_logits_a[i,q]
+// + p_q * (g_probs_a[i,q] - sum_r g_probs_a[i,r] * p_r)   (softmax backward), rows that are not selected contribute nothing.
+struct AttrBwdPtrs { const void* g_probs[3]; const void* g_logits[3]; };
+template <typename T>
+__global__ void head_attr_bwd_kernel(const T* __restrict__ probs, AttrBwdPtrs gp, const int32_t* __restrict__ src_row,
+                                     const uint8_t* __restrict__ selector, int n, int m, int k_head, int n_attr,
+                                     int c0, int c1, int c2, int w0, int w1, int w2, float* __restrict__ g_full) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (selector && !selector[i]) return;
+    const int row = src_row ? src_row[i] : i;
+    if (row < 0 || row >= m) return;
+    float* out = g_full + (size_t)row * k_head;
+    for (int q = 0; q < k_head; q++) out[q] = 0.f;
+    const int cs[3] = {c0, c1, c2}, ws[3] = {w0, w1, w2};
+    size_t off = 0;
+    for (int a = 0; a < n_attr; a++) {
+        const int w = ws[a];
+        const T* p = probs + off + (size_t)i * w;
+        const T* g_p = reinterpret_cast<const T*>(gp.g_probs[a]);
+        const T* g_l = reinterpret_cast<const T*>(gp.g_logits[a]);
+        float dot = 0.f;
+        if (g_p) for (int q = 0; q < w; q++) dot += to_f32(g_p[(size_t)i * w + q]) * to_f32(p[q]);
+        for (int q = 0; q < w; q++) {
+            float acc = g_l ? to_f32(g_l[(size_t)i * w + q]) : 0.f;
+            if (g_p) acc += to_f32(p[q]) * (to_f32(g_p[(size_t)i * w + q]) - dot);
+            out[cs[a] + q] += acc;
+        }
+        off += (size_t)n * w;
+    }
+}
+
 #include "fg_head_tc.cuh"
 
 // tensor-core path: 16-bit operands, K and N multiples of 64, 16-byte aligned rows
@@ -331,6 +365,34 @@ extern "C" int fg_head_attributes(const float* logits, int m, int k_head, const 
         head_attr_kernel<T><<<(n + 127) / 128, 128, 0, fg_stream(stream)>>>(
             logits, m, k_head, src_row, selector, n, n_attr, c[0], c[1], c[2], w[0], w[1], w[2], fill,
             (long long*)preds, (T*)probs, (T*)logits_out));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_head_attributes_bwd(const void* probs, const void* const* g_probs, const void* const* g_logits_attr,
+                                      const int32_t* src_row, const uint8_t* selector, int n, int m, int k_head, int n_attr,
+                                      const int32_t* col_start, const int32_t* width, float* g_logits_full, int dtype, void* stream) {
+    if (n < 0 || m < 0 || k_head <= 0 || n_attr < 1 || n_attr > 3 || !col_start || !width || !g_probs || !g_logits_attr)
+        return FG_ERR_INVALID_ARG;
+    if (m == 0 || n == 0) return FG_OK;
+    if (!probs || !g_logits_full) return FG_ERR_INVALID_ARG;
+    int c[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+    AttrBwdPtrs gp;
+    for (int a = 0; a < 3; a++) { gp.g_probs[a] = nullptr; gp.g_logits[a] = nullptr; }
+    for (int a = 0; a < n_attr; a++) {
+        c[a] = col_start[a]; w[a] = width[a];
+        if (w[a] <= 0 || c[a] < 0 || c[a] + w[a] > k_head) return FG_ERR_INVALID_ARG;
+        gp.g_probs[a] = g_probs[a]; gp.g_logits[a] = g_logits_attr[a];
+    }
+    if (!src_row && !selector && m != n) return FG_ERR_INVALID_ARG;
+    if (src_row || selector) {
+        // rows of g_logits_full that no selected image maps to stay untouched: clear them first
+        cudaError_t e = cudaMemsetAsync(g_logits_full, 0, (size_t)m * k_head * sizeof(float), fg_stream(stream));
+        if (e != cudaSuccess) return (int)e;
+    }
+    FG_DISPATCH_DTYPE(dtype, T,
+        head_attr_bwd_kernel<T><<<(n + 127) / 128, 128, 0, fg_stream(stream)>>>(
+            (const T*)probs, gp, src_row, selector, n, m, k_head, n_attr, c[0], c[1], c[2], w[0], w[1], w[2], g_logits_full));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

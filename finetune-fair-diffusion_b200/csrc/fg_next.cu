@@ -131,7 +131,7 @@ bias_metrics_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T*
     __syncthreads();
     const float thr = round_to<T>(0.8f);          // `tensor < 0.8` compares in the tensor's dtype
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const bool vg = row_valid(pg + 2 * i, 2), vr = row_valid(pr + 4 * i, 4);
+        const bool vg = pg && row_valid(pg + 2 * i, 2), vr = row_valid(pr + 4 * i, 4);
         int g = -1, r = -1; float mx;
         if (vg) { g = row_argmax(pg + 2 * i, 2, &mx); atomicAdd(&cnt[MC_G + g], 1); atomicAdd(&cnt[MC_N + 0], 1); if (mx < thr) atomicAdd(&cnt[MC_LOW + 0], 1); }
         if (vr) { r = row_argmax(pr + 4 * i, 4, &mx); atomicAdd(&cnt[MC_R + r], 1); atomicAdd(&cnt[MC_N + 1], 1); if (mx < thr) atomicAdd(&cnt[MC_LOW + 1], 1); }
@@ -146,6 +146,14 @@ bias_metrics_kernel(const T* __restrict__ pg, const T* __restrict__ pr, const T*
         // a mean of 0/1 floats is count / n in fp32 (the sum is an exact integer)
         const float ng = (float)cnt[MC_N + 0], nr = (float)cnt[MC_N + 1];
         float fg[2], fr[4], fgr[8];
+        if (!pg) {
+            // exp-6 get_evaluate_metrics(probs_race_all), E6:1624-1638: the four race frequencies, their mean pairwise
+            // gap and the share of faces whose top race probability is below 0.8
+            for (int q = 0; q < 4; q++) { fr[q] = __fdiv_rn((float)cnt[MC_R + q], nr); out[q] = (double)fr[q]; }
+            out[4] = mean_pairwise_gap(fr, 4);
+            out[5] = (double)__fdiv_rn((float)cnt[MC_LOW + 1], nr);
+            return;
+        }
         for (int q = 0; q < 2; q++) fg[q] = __fdiv_rn((float)cnt[MC_G + q], ng);
         for (int q = 0; q < 4; q++) fr[q] = __fdiv_rn((float)cnt[MC_R + q], nr);
         for (int q = 0; q < 8; q++) fgr[q] = __fdiv_rn((float)cnt[MC_GR + q], ng);
@@ -186,7 +194,7 @@ extern "C" int fg_stage_detector_input(const void* images, int n, int C, int H, 
 
 extern "C" int fg_bias_metrics(const void* probs_gender, const void* probs_race, const void* probs_age, int n, double* out,
                                int dtype, void* stream) {
-    if (n < 0 || !out || (n > 0 && (!probs_gender || !probs_race))) return FG_ERR_INVALID_ARG;
+    if (n < 0 || !out || (n > 0 && !probs_race) || (!probs_gender && probs_age)) return FG_ERR_INVALID_ARG;
     FG_DISPATCH_DTYPE(dtype, T, bias_metrics_kernel<T><<<1, 256, 0, fg_stream(stream)>>>((const T*)probs_gender, (const T*)probs_race, (const T*)probs_age, n, out));
     FG_LAUNCH_CHECK();
     return FG_OK;

@@ -183,7 +183,7 @@ def head_bwd(g_logits, hidden, w1, w2):
     return g_pooled
 
 
-def head_attributes(logits, src_row, selector, n, col_start, width, fill, dtype):
+def head_attributes(logits, src_row, selector, n, col_start, width, fill, dtype, return_flat=False):
     """-> (preds [A,n] int64, probs list of [n,w_a], logits list of [n,w_a]); attribute-major flat storage."""
     _cuda(logits, src_row, selector)
     dev = logits.device
@@ -203,7 +203,26 @@ def head_attributes(logits, src_row, selector, n, col_start, width, fill, dtype)
         ps.append(probs[off:off + n * w].view(n, w))
         ls.append(lout[off:off + n * w].view(n, w))
         off += n * w
+    if return_flat:
+        return preds, ps, ls, probs
     return preds, ps, ls
+
+
+def head_attributes_bwd(probs_flat, g_probs, g_logits_attr, src_row, selector, n, m, k_head, col_start, width):
+    """Backward of head_attributes in one launch -> g_logits_full float32 [m,k_head].  ``probs_flat``: the forward's flat
+    attribute-major probs storage; g_probs / g_logits_attr: lists (one entry per attribute) of [n,w_a] tensors or None."""
+    A = len(width)
+    dt = probs_flat.dtype
+    gp = [None if g is None else g.to(dt).contiguous() for g in g_probs]
+    gl = [None if g is None else g.to(dt).contiguous() for g in g_logits_attr]
+    _cuda(probs_flat, src_row, selector, *gp, *gl)
+    g_full = torch.empty((m, k_head), dtype=torch.float32, device=probs_flat.device)
+    arr = lambda ts: (ctypes.c_void_p * A)(*[None if t is None else t.data_ptr() for t in ts])
+    sel = _u8(selector)
+    src = None if src_row is None else src_row.to(torch.int32).contiguous()
+    check(_lib.lib().fg_head_attributes_bwd(_p(probs_flat), arr(gp), arr(gl), _p(src), _p(sel), n, m, k_head, A, _iarr(col_start),
+                                            _iarr(width), _p(g_full), _DT[dt], _stream()), "fg_head_attributes_bwd")
+    return g_full
 
 
 # ------------------------------------------------------------------ loss
@@ -392,12 +411,14 @@ def stage_detector_input(images):
 
 
 def bias_metrics(probs_gender, probs_race, probs_age=None):
-    """get_evaluate_metrics (E3:1716 / E4:1780) as one launch; returns a DEVICE fp64 tensor of 5 (or 9) numbers."""
+    """get_evaluate_metrics (E3:1716 / E4:1780) as one launch; returns a DEVICE fp64 tensor of 5 (or 9) numbers.
+    ``probs_gender=None``: exp-6's race-only form (E6:1624-1638), 6 numbers."""
     _cuda(probs_gender, probs_race, probs_age)
-    pg, pr = probs_gender.contiguous(), probs_race.to(probs_gender.dtype).contiguous()
-    pa = None if probs_age is None else probs_age.to(probs_gender.dtype).contiguous()
-    out = torch.empty((9 if pa is not None else 5,), dtype=torch.float64, device=pg.device)
-    check(_lib.lib().fg_bias_metrics(_p(pg), _p(pr), _p(pa), pg.shape[0], _p(out), _dt(pg), _stream()), "fg_bias_metrics")
+    pr = probs_race.contiguous()
+    pg = None if probs_gender is None else probs_gender.to(pr.dtype).contiguous()
+    pa = None if probs_age is None else probs_age.to(pr.dtype).contiguous()
+    out = torch.empty((6 if pg is None else 9 if pa is not None else 5,), dtype=torch.float64, device=pr.device)
+    check(_lib.lib().fg_bias_metrics(_p(pg), _p(pr), _p(pa), pr.shape[0], _p(out), _dt(pr), _stream()), "fg_bias_metrics")
     return out
 
 

@@ -264,7 +264,8 @@ class GuidancePath:
                     probs=st["probs"], targets=targets, targets_all=targets_all, counts=st["counts"], loss_fair=loss_fair,
                     g_pooled=g_pooled, region=region, scale=scale, dyn_weights=dyn_w, loss=loss, loss_mean=loss.mean(),
                     g_images=g_images, bbox_ori=bbox_ori,
-                    ot_status=st["ws"].status_tensor() if st.get("counts") is not None else None, num_valid=st.get("nv"))
+                    ot_status=st["ws"].status_tensor() if st.get("counts") is not None else None, num_valid=st.get("nv"),
+                    indicators_all=st["ind_all"], probs_all=probs_all)
 
     @torch.no_grad()
     def step(self, batch, rand_tensors=None, num_valid: Optional[int] = None, probe=None):
@@ -298,21 +299,23 @@ class CapturedStep:
     (or ``pipeline.validate_step(out)``) reads the status words the kernels leave behind and raises on a mismatch instead of
     returning wrong targets -- the kernels themselves stay inside their buffers either way."""
 
-    def __init__(self, path, batch, num_valid):
+    def __init__(self, path, batch, num_valid, rand_tensors=None):
+        """``rand_tensors``: optional static [S, num_valid] draw buffers (one per attribute) that the graph reads instead
+        of drawing with torch.rand -- refresh them in place between replays (parity tests hand the same draws to the oracle)."""
         self.path, self.batch = path, batch
         world, _ = fdist._world(path.group)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                       # warm-up off the capturing stream (allocator, lazy module loads)
             for _ in range(2):
-                path.step(batch, num_valid=num_valid)
+                path.step(batch, rand_tensors=rand_tensors, num_valid=num_valid)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
         if world == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.out = path.step(batch, num_valid=num_valid)
+                self.out = path.step(batch, rand_tensors=rand_tensors, num_valid=num_valid)
             self.graphs = [g]
             self.state = None
         else:
@@ -323,7 +326,7 @@ class CapturedStep:
                 st = path.phase_a(batch)
             path.exchange_1(st)
             with torch.cuda.graph(gb, pool=ga.pool()):
-                path.phase_b(st, batch, None, num_valid)
+                path.phase_b(st, batch, rand_tensors, num_valid)
             path.exchange_2(st)
             with torch.cuda.graph(gc, pool=ga.pool()):
                 self.out = path.phase_c(st, batch)

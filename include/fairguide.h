@@ -123,6 +123,15 @@ int fg_head_attributes(const float* logits, int m, int k_head, const int32_t* sr
                        int n, int n_attr, const int32_t* col_start, const int32_t* width, float fill,
                        int64_t* preds, void* probs, void* logits_out, int dtype, void* stream);
 
+/* Backward of fg_head_attributes (the autograd edge probs / sliced logits -> classifier logits that the reference's
+ * micro-batch loop differentiates through, E3:2104 -> E3:2119-2122): g_logits_full [m,k_head] f32 receives, in the
+ * columns of attribute a, g_logits_attr[a] + softmax-backward(g_probs[a]); every other element is zero.
+ * probs: the forward's `probs` output; g_probs / g_logits_attr: HOST arrays [n_attr] of device pointers to [n,width[a]]
+ * tensors in `dtype` (NULL entries = no gradient through that output). */
+int fg_head_attributes_bwd(const void* probs, const void* const* g_probs, const void* const* g_logits_attr,
+                           const int32_t* src_row, const uint8_t* selector, int n, int m, int k_head, int n_attr,
+                           const int32_t* col_start, const int32_t* width, float* g_logits_full, int dtype, void* stream);
+
 /* ------------------------------------------------------------------ fairness loss ---------
  * CE_loss(logits[idx], targets[idx]) on idx = face & target != -1, `fill` elsewhere
  * (E1:1912-1915, E3:2114-2122, E4:2238-2251).  logits [n,k] dtype; loss [n] dtype. */
@@ -197,7 +206,9 @@ int fg_stage_detector_input(const void* images, int n, int C, int H, int W, uint
 /* f3: get_evaluate_metrics (E3:1716-1749; E4:1780-1821 when probs_age != NULL).  probs_* [n,2] / [n,4] / [n,2] dtype,
  * rows of -1 are skipped.  out (DEVICE, fp64): [0] gender_gap [1] gender_pred_below_08 [2] race_gap
  * [3] race_pred_below_08 [4] gender_race_gap, and with age [5] age0_freq [6] age1_freq [7] age_pred_below_08 [8] age_gap.
- * One launch, no host synchronisation (the reference makes one blocking .item() per number). */
+ * One launch, no host synchronisation (the reference makes one blocking .item() per number).
+ * probs_gender == NULL selects exp-6's race-only get_evaluate_metrics (exp-6-debias-race/1-main-debias.py:1624-1638):
+ * out [0..3] race0..3_freq [4] race_gap [5] race_pred_below_08. */
 int fg_bias_metrics(const void* probs_gender, const void* probs_race, const void* probs_age, int n, double* out,
                     int dtype, void* stream);
 

@@ -11,8 +11,9 @@ _SLICES = {
     "gender": lambda lg: [lg.view([lg.shape[0], -1, 2])[:, 20, :]],
     "gender_race": lambda lg: [lg[:, :2], lg[:, 2:]],
     "gender_race_age": lambda lg: [lg[:, :2], lg[:, 2:6], lg[:, 6:]],
+    "race": lambda lg: [lg[:, 2:]],                   # exp-6-debias-race/1-main-debias.py:1381
 }
-_WIDTHS = {"gender": [2], "gender_race": [2, 4], "gender_race_age": [2, 4, 2]}
+_WIDTHS = {"gender": [2], "gender_race": [2, 4], "gender_race_age": [2, 4, 2], "race": [4]}
 
 
 def _scatter(values, selector, fill_value):
@@ -57,6 +58,11 @@ def get_face_gender_race_age(classifier, face_chips, selector=None, fill_value=-
     the gender and race entries (E4:1475) -- pinned by the golden vectors and kept."""
     out = _heads("gender_race_age", classifier, face_chips, selector, fill_value)
     return out if selector is not None else out[:6]
+
+
+def get_face_race(classifier, face_chips, selector=None, fill_value=-1):
+    """exp-6-debias-race/1-main-debias.py:1365-1411 -> (preds_race, probs_race, logits_race)."""
+    return _heads("race", classifier, face_chips, selector, fill_value)
 
 
 def mobilenet_head_reference(pooled, w1, b1, w2, b2):

@@ -50,6 +50,15 @@ def evaluate_metrics(probs_gender_all, probs_race_all, probs_age_all=None):
     return tuple(out)
 
 
+def evaluate_metrics_race(probs_race_all):
+    """exp-6-debias-race/1-main-debias.py:1624-1638: the four race frequencies, their mean pairwise gap and the share of
+    faces whose top probability is below 0.8."""
+    r = _valid(probs_race_all)
+    pr = r.argmax(dim=-1)
+    fr = _freqs([pr == q for q in range(4)])
+    return tuple(f.item() for f in fr) + (_mean_offdiag_l1(fr), (r.max(dim=-1).values < 0.8).float().mean().item())
+
+
 # ----------------------------------------------------------------------------- f4: consumer side
 def adjusted_dft_grad_coefs(alphas_cumprod, alphas, timesteps):
     """E1:1104-1109 (inside generate_image_w_gradient)."""

@@ -172,3 +172,82 @@ def check_step_vs_oracle(kind="gender_race_age", n=1024, dtype=torch.bfloat16, n
         if kind == "gender":
             assert torch.equal(o2["g_images"], out["g_images"])
     return report
+
+
+def check_multi_rank(kind, dtype, dev, rank, world, n_side_global=256, S=100, captured=True, seed=4242):
+    """Correctness of the multi-rank step on hardware (NCCL): every rank runs the step on its shard of a side batch of
+    ``n_side_global`` images with draws from a per-rank seeded CPU generator; then
+      * ``targets_all`` and the all-reduced plan ``counts`` are BIT-IDENTICAL on all ranks (gathered and compared),
+      * the gathered rows are the ranks' own rows in rank order (a6: customized_all_gather E1:222-235),
+      * rank 0 recomputes the assignment with the oracle, simulating every rank's draws (``world_rand``, E3:1491-1535),
+        and the targets agree bit for bit, before and after the local slice (E3:2024-2025),
+      * the three-graph CapturedStep replay (NCCL between the graph replays) returns the same integers as the eager step.
+    Raises on any mismatch; returns a short report dict."""
+    import torch.distributed as dist
+    from fairguide import pipeline
+    from oracle import assign as oassign
+    cfg = pipeline.GuidanceConfig(kind=kind, num_samples_per_device=S)
+    widths = pipeline.KINDS[kind][0]
+    n_attr = len(widths)
+    n = n_side_global // world
+    head = pipeline.make_head_weights(cfg, dtype, dev)
+    batch = pipeline.synth_batch_device(n, cfg, dtype, dev, seed=seed + rank)
+    counts_local = batch["counts"].clone()
+    gathered = [torch.empty_like(counts_local) for _ in range(world)]
+    dist.all_gather(gathered, counts_local)
+    nv = int((torch.cat(gathered) > 0).sum().item())
+    draws = lambda r: tuple(torch.rand(S, nv, generator=torch.Generator().manual_seed(seed + 100 + 7 * r + a)).to(dtype) for a in range(n_attr))
+    rands = None if kind == "gender" else tuple(t.to(dev) for t in draws(rank))
+    path = pipeline.GuidancePath(cfg, head)
+    out = path.step(batch, rand_tensors=rands, num_valid=nv)
+    pipeline.validate_step(out)
+    torch.cuda.synchronize()
+
+    def same_on_all_ranks(t, what):
+        t = t.contiguous()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        for r, p in enumerate(parts):
+            assert torch.equal(p, t), f"{what} differs between rank {rank} and rank {r}"
+
+    for a in range(n_attr):
+        same_on_all_ranks(out["targets_all"][a], f"targets_all[{a}]")
+    if out["counts"] is not None:
+        same_on_all_ranks(out["counts"], "plan counts")
+    # gathered rows = every rank's own rows, in rank order
+    for a in range(n_attr):
+        parts = [torch.empty_like(out["probs"][a]) for _ in range(world)]
+        dist.all_gather(parts, out["probs"][a].contiguous())
+        assert torch.equal(torch.cat(parts), out["probs_all"][a]), "gathered probabilities are not the ranks' rows in rank order"
+    parts = [torch.empty_like(out["indicators"]) for _ in range(world)]
+    dist.all_gather(parts, out["indicators"].contiguous())
+    assert torch.equal(torch.cat(parts), out["indicators_all"])
+    # local slice (E3:2024-2025)
+    for a in range(n_attr):
+        assert torch.equal(out["targets"][a], out["targets_all"][a][n * rank:n * (rank + 1)])
+    report = {"rows": n * world, "faces": nv}
+    if rank == 0:
+        probs_all = [p.detach().cpu() for p in out["probs_all"]]
+        if kind == "gender":
+            res = oassign.generate_dynamic_targets(probs_all[0], cfg.target_ratio, True)
+        else:
+            wr = [draws(r) for r in range(world)]
+            fn = oassign.generate_dynamic_targets_gender_race if n_attr == 2 else oassign.generate_dynamic_targets_gender_race_age
+            res = fn(*probs_all, True, S, world_rand=wr, literal=False)
+        for a in range(n_attr):
+            t = res[2 * a].clone()
+            t[res[2 * a + 1] > cfg.uncertainty_threshold] = -1
+            got = out["targets_all"][a].cpu()
+            assert torch.equal(got, t), f"targets_all[{a}] differs from the oracle in {int((got != t).sum())} rows"
+        report["rows_with_target"] = [int((out["targets_all"][a] != -1).sum()) for a in range(n_attr)]
+    if captured:
+        cap = pipeline.CapturedStep(path, batch, nv, rand_tensors=rands)
+        o2 = cap.replay(validate=True)
+        torch.cuda.synchronize()
+        for a in range(n_attr):
+            assert torch.equal(o2["targets_all"][a], out["targets_all"][a]), "graph replay differs from the eager step"
+        if o2["counts"] is not None:
+            assert torch.equal(o2["counts"], out["counts"])
+        assert torch.equal(o2["g_images"], out["g_images"]) and torch.equal(o2["loss"], out["loss"])
+    dist.barrier()
+    return report
