@@ -209,10 +209,16 @@ __global__ void head_attr_bwd_kernel(const T* __restrict__ probs, AttrBwdPtrs gp
 
 #include "fg_head_tc.cuh"
 
-// tensor-core path: 16-bit operands, K and N multiples of 64, 16-byte aligned rows
+static bool env_flag(const char* name) {             // read once per process (tuning / A-B switches only)
+    return getenv(name) != nullptr;
+}
+static bool head_simt() { static const bool v = env_flag("FG_HEAD_SIMT"); return v; }
+
+// tensor-core path: K and N multiples of 64, 16-byte aligned rows; bf16 / fp16 operands as they are, fp32 operands as a
+// three-pass TF32 split (needs the TMA kernel, i.e. the driver's tensor-map encoder)
 static bool tc_ok(int dtype, int m, int d_in, int d_hid, int k_head, const void* a, const void* b) {
-    return (dtype == FG_BF16 || dtype == FG_F16) && m > 0 && d_in % 64 == 0 && d_hid % 64 == 0 && k_head <= 256 &&
-           ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && getenv("FG_HEAD_SIMT") == nullptr;
+    return m > 0 && d_in % 64 == 0 && d_hid % 64 == 0 && k_head <= 256 &&
+           ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && !head_simt();
 }
 
 // ---- 2-D tensor maps for the TMA kernel (row-major 16-bit matrix, 64-element x box_rows boxes, 128-byte swizzle)
@@ -227,45 +233,87 @@ static EncodeTiledFn tma_encoder() {
             f = nullptr;
         return (EncodeTiledFn)f;
     }();
-    return getenv("FG_HEAD_CPASYNC") ? nullptr : fn;       // FG_HEAD_CPASYNC=1: A/B runs against the cp.async kernel
+    static const bool off = env_flag("FG_HEAD_CPASYNC");    // FG_HEAD_CPASYNC=1: A/B runs against the cp.async kernel
+    return off ? nullptr : fn;
 }
+
+// Encoding a tensor map is pure host arithmetic on (base, shape, stride, box): a step encodes the same handful of maps every
+// time (frozen weights, reused activation buffers), so the last few are kept per thread.  Nothing here is observable state:
+// a hit returns byte-identical bytes to what the encoder would produce.
+struct MapKey { const void* base; int inner, rows, ld, box_inner, box_rows, esize; };
 template <typename T>
 static bool make_map(tc::TmaMap* out, const void* base, int inner, int rows, int ld, int box_rows) {
     EncodeTiledFn enc = tma_encoder();
     if (!enc) return false;
+    constexpr int NCACHE = 16;
+    thread_local MapKey keys[NCACHE];
+    thread_local tc::TmaMap vals[NCACHE];
+    thread_local int used = 0, next = 0;
+    const int box_inner = 128 / (int)sizeof(T);                 // one 128-byte swizzle span of K (or of N for an MN-major B)
+    const int esize = std::is_same<T, __half>::value ? -2 : (int)sizeof(T);      // fp16 and bf16 differ in the data type field
+    const MapKey k = {base, inner, rows, ld, box_inner, box_rows, esize};
+    for (int i = 0; i < used; i++)
+        if (memcmp(&keys[i], &k, sizeof(k)) == 0) { memcpy(out, &vals[i], sizeof(*out)); return true; }
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+        : (std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     if (enc(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     static_assert(sizeof(CUtensorMap) == sizeof(tc::TmaMap), "tensor map size");
     memcpy(out, &m, sizeof(m));
+    keys[next] = k; memcpy(&vals[next], &m, sizeof(m));
+    next = (next + 1) % NCACHE; if (used < NCACHE) used++;
     return true;
 }
 
+// A [M,K] and B as the kernel reads them; for fp32 also the low halves of the TF32 split (A_lo, B_lo; same shapes)
 template <typename T, int MODE>
-static int launch_head_gemm(const tc::Params& p, dim3 grid, cudaStream_t st) {
-    tc::TmaMap mapA, mapB;
-    // A [M,K]: boxes of 128 rows; B: forward [N,K] boxes of 64 rows (n), backward [K,N] boxes of 64 rows (k) x 64 n
-    const bool tma = make_map<T>(&mapA, p.A, p.K, p.M, p.lda, tc::BM) &&
-                     (MODE == 0 ? make_map<T>(&mapB, p.B, p.K, p.N, p.ldb, tc::BN) : make_map<T>(&mapB, p.B, p.N, p.K, p.ldb, tc::BK));
+static int launch_head_gemm(const tc::Params& p, const void* a_lo, const void* b_lo, dim3 grid, cudaStream_t st) {
+    constexpr bool F32 = sizeof(T) == 4;
+    tc::TmaMap mapA, mapB, mapAlo, mapBlo;
+    // A [M,K]: boxes of 128 rows; B: K-major [N,K] boxes of 64 rows (n); the 16-bit backward reads W1 as [K,N]: 64 k-rows x 64 n
+    auto map_b = [&](tc::TmaMap* o, const void* base) {
+        return (MODE == 0 || F32) ? make_map<T>(o, base, p.K, p.N, p.ldb, tc::BN) : make_map<T>(o, base, p.N, p.K, p.ldb, tc::BK);
+    };
+    bool tma = make_map<T>(&mapA, p.A, p.K, p.M, p.lda, tc::BM) && map_b(&mapB, p.B);
+    if (tma && F32) tma = make_map<T>(&mapAlo, a_lo, p.K, p.M, p.lda, tc::BM) && map_b(&mapBlo, b_lo);
+    if (!F32) { mapAlo = mapA; mapBlo = mapB; }
     cudaError_t e;
     if (tma) {
         const size_t smem = tc::smem_bytes_tma(MODE, p.k_head);
         e = cudaFuncSetAttribute(tc::head_gemm_tma_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        tc::head_gemm_tma_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p, mapA, mapB);
+        tc::head_gemm_tma_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p, mapA, mapB, mapAlo, mapBlo, F32 ? 3 : 1);
     } else {
-        const size_t smem = tc::smem_bytes(MODE, p.k_head);
-        e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        tc::head_gemm_tc_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p);
+        if constexpr (F32) {
+            return FG_ERR_INVALID_ARG;          // callers check tma_encoder() first and keep fp32 on the CUDA-core kernels without it
+        } else {
+            const size_t smem = tc::smem_bytes(MODE, p.k_head);
+            e = cudaFuncSetAttribute(tc::head_gemm_tc_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            tc::head_gemm_tc_kernel<T, MODE><<<grid, tc::THREADS, smem, st>>>(p);
+        }
     }
     return FG_OK;
+}
+
+// workspace carve for the fp32 (TF32 split) path
+struct F32Ws { float* part; float* a_hi; float* a_lo; float* b_hi; float* b_lo; size_t total; };
+static F32Ws f32_carve(void* base, int m, int d_in, int d_hid, int k_head) {
+    F32Ws w; size_t off = 0;
+    const size_t rows = (size_t)(m > 0 ? m : 1);
+    const size_t big = (size_t)(d_in > d_hid ? d_in : d_hid);
+    auto take = [&](size_t bytes) { size_t o = off; off += fg_align_up(bytes, 256); return (float*)((char*)base + o); };
+    w.part = take((size_t)((d_hid + 63) / 64) * rows * k_head * sizeof(float));
+    w.a_hi = take(rows * big * sizeof(float)); w.a_lo = take(rows * big * sizeof(float));
+    w.b_hi = take((size_t)d_in * d_hid * sizeof(float)); w.b_lo = take((size_t)d_in * d_hid * sizeof(float));
+    w.total = off;
+    return w;
 }
 
 template <typename T>
@@ -274,10 +322,28 @@ static int head_fwd_tc(const void* pooled, const void* w1, const void* b1, const
     tc::Params p;
     p.A = pooled; p.lda = d_in; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_hid; p.K = d_in;
     p.bias = b1; p.out = hidden_pre; p.ldo = d_hid; p.w2 = w2; p.k_head = k_head; p.part = part;
-    int rc = launch_head_gemm<T, 0>(p, dim3(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    int rc = launch_head_gemm<T, 0>(p, nullptr, nullptr, dim3(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM), st);
     if (rc) return rc;
     const int tot = m * k_head;
     tc::head_reduce_partials_kernel<T><<<(tot + 255) / 256, 256, 0, st>>>(part, (const T*)b2, d_hid / tc::BN, m, k_head, logits);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+// fp32: split pre-pass (pooled and W1 -> hi / lo), three-pass TF32 GEMM with the fused epilogue, partial reduction
+static int head_fwd_tf32(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2, int m, int d_in,
+                         int d_hid, int k_head, float* hidden_pre, float* logits, void* workspace, cudaStream_t st) {
+    F32Ws w = f32_carve(workspace, m, d_in, d_hid, k_head);
+    const size_t na = (size_t)m * d_in / 4, nb = (size_t)d_hid * d_in / 4;
+    tc::split_tf32_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(pooled, w.a_hi, w.a_lo, na);
+    tc::split_tf32_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(w1, w.b_hi, w.b_lo, nb);
+    tc::Params p;
+    p.A = w.a_hi; p.lda = d_in; p.B = w.b_hi; p.ldb = d_in; p.M = m; p.N = d_hid; p.K = d_in;
+    p.bias = b1; p.out = hidden_pre; p.ldo = d_hid; p.w2 = w2; p.k_head = k_head; p.part = w.part;
+    int rc = launch_head_gemm<float, 0>(p, w.a_lo, w.b_lo, dim3(d_hid / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    if (rc) return rc;
+    const int tot = m * k_head;
+    tc::head_reduce_partials_kernel<float><<<(tot + 255) / 256, 256, 0, st>>>(w.part, b2, d_hid / tc::BN, m, k_head, logits);
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
@@ -290,7 +356,24 @@ static int head_bwd_tc(const float* g_logits, const void* hidden_pre, const void
     tc::Params p;
     p.A = g_pre16; p.lda = d_hid; p.B = w1; p.ldb = d_in; p.M = m; p.N = d_in; p.K = d_hid;
     p.bias = nullptr; p.out = g_pooled; p.ldo = d_in; p.w2 = nullptr; p.k_head = 0; p.part = nullptr;
-    int rc = launch_head_gemm<T, 1>(p, dim3(d_in / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    int rc = launch_head_gemm<T, 1>(p, nullptr, nullptr, dim3(d_in / tc::BN, (m + tc::BM - 1) / tc::BM), st);
+    if (rc) return rc;
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+// fp32 backward: g_pre (fp32) -> hi / lo, W1 [d_hid, d_in] -> transposed hi / lo [d_in, d_hid] (K-major B), three-pass TF32 GEMM
+static int head_bwd_tf32(const float* g_logits, const float* hidden_pre, const float* w1, const float* w2, int m, int d_in, int d_hid,
+                         int k_head, float* g_pooled, void* workspace, cudaStream_t st) {
+    F32Ws w = f32_carve(workspace, m, d_in, d_hid, k_head);
+    head_bwd_hidden_kernel<float, float><<<m, 256, k_head * sizeof(float), st>>>(g_logits, hidden_pre, w2, w.a_hi, m, d_hid, k_head);
+    const size_t na = (size_t)m * d_hid / 4;
+    tc::split_tf32_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(w.a_hi, w.a_hi, w.a_lo, na);          // in place: hi overwrites g_pre
+    tc::split_transpose_tf32_kernel<<<dim3((d_in + 31) / 32, (d_hid + 31) / 32), 256, 0, st>>>(w1, w.b_hi, w.b_lo, d_hid, d_in);
+    tc::Params p;
+    p.A = w.a_hi; p.lda = d_hid; p.B = w.b_hi; p.ldb = d_hid; p.M = m; p.N = d_in; p.K = d_hid;
+    p.bias = nullptr; p.out = g_pooled; p.ldo = d_in; p.w2 = nullptr; p.k_head = 0; p.part = nullptr;
+    int rc = launch_head_gemm<float, 1>(p, w.a_lo, w.b_lo, dim3(d_in / tc::BN, (m + tc::BM - 1) / tc::BM), st);
     if (rc) return rc;
     FG_LAUNCH_CHECK();
     return FG_OK;
@@ -299,11 +382,16 @@ static int head_bwd_tc(const float* g_logits, const void* hidden_pre, const void
 }  // namespace
 
 extern "C" size_t fg_head_workspace_bytes(int m, int d_in, int d_hid, int k_head, int dtype) {
-    (void)d_in; (void)dtype;
-    // backward: g_pre [m, d_hid] (fp32, or 16-bit on the tensor-core path); forward: partial logits [d_hid/64, m, k_head]
+    // backward: g_pre [m, d_hid] (fp32, or 16-bit on the tensor-core path); forward: partial logits [d_hid/64, m, k_head];
+    // fp32 adds the hi / lo halves of the TF32 split of both operands
     size_t rows = (size_t)(m > 0 ? m : 1);
     size_t a = rows * d_hid * sizeof(float), b = (size_t)((d_hid + 63) / 64) * rows * k_head * sizeof(float);
-    return fg_align_up(a > b ? a : b, 256);
+    size_t base = fg_align_up(a > b ? a : b, 256);
+    if (dtype == FG_F32 && d_in > 0 && d_hid > 0 && k_head > 0) {
+        size_t f = f32_carve(nullptr, m, d_in, d_hid, k_head).total;
+        if (f > base) base = f;
+    }
+    return base;
 }
 
 extern "C" int fg_head_fwd(const void* pooled, const void* w1, const void* b1, const void* w2, const void* b2,
@@ -312,10 +400,13 @@ extern "C" int fg_head_fwd(const void* pooled, const void* w1, const void* b1, c
     if (m < 0 || d_in <= 0 || d_hid <= 0 || k_head <= 0) return FG_ERR_INVALID_ARG;
     if (!pooled || !w1 || !b1 || !w2 || !b2 || !hidden_pre || !logits) return FG_ERR_INVALID_ARG;
     if (m == 0) return FG_OK;
-    if (tc_ok(dtype, m, d_in, d_hid, k_head, pooled, w1)) {
+    if (tc_ok(dtype, m, d_in, d_hid, k_head, pooled, w1) && (dtype != FG_F32 || tma_encoder())) {
         if (!workspace || workspace_bytes < fg_head_workspace_bytes(m, d_in, d_hid, k_head, dtype)) return FG_ERR_WORKSPACE;
         if (dtype == FG_BF16) return head_fwd_tc<__nv_bfloat16>(pooled, w1, b1, w2, b2, m, d_in, d_hid, k_head, hidden_pre, logits, (float*)workspace, fg_stream(stream));
-        return head_fwd_tc<__half>(pooled, w1, b1, w2, b2, m, d_in, d_hid, k_head, hidden_pre, logits, (float*)workspace, fg_stream(stream));
+        if (dtype == FG_F16) return head_fwd_tc<__half>(pooled, w1, b1, w2, b2, m, d_in, d_hid, k_head, hidden_pre, logits, (float*)workspace, fg_stream(stream));
+        if (dtype == FG_F32) return head_fwd_tf32((const float*)pooled, (const float*)w1, (const float*)b1, (const float*)w2, (const float*)b2,
+                                                  m, d_in, d_hid, k_head, (float*)hidden_pre, logits, workspace, fg_stream(stream));
+        return FG_ERR_DTYPE;
     }
     dim3 grid((d_hid + 63) / 64, (m + 63) / 64);
     int groups = (k_head + 7) / 8;
@@ -336,9 +427,12 @@ extern "C" int fg_head_bwd(const float* g_logits, const void* hidden_pre, const 
     if (!g_logits || !hidden_pre || !w1 || !w2 || !g_pooled) return FG_ERR_INVALID_ARG;
     if (m == 0) return FG_OK;
     if (!workspace || workspace_bytes < fg_head_workspace_bytes(m, d_in, d_hid, k_head, dtype)) return FG_ERR_WORKSPACE;
-    if (tc_ok(dtype, m, d_in, d_hid, k_head, hidden_pre, w1)) {
+    if (tc_ok(dtype, m, d_in, d_hid, k_head, hidden_pre, w1) && (dtype != FG_F32 || tma_encoder())) {
         if (dtype == FG_BF16) return head_bwd_tc<__nv_bfloat16>(g_logits, hidden_pre, w1, w2, m, d_in, d_hid, k_head, g_pooled, workspace, fg_stream(stream));
-        return head_bwd_tc<__half>(g_logits, hidden_pre, w1, w2, m, d_in, d_hid, k_head, g_pooled, workspace, fg_stream(stream));
+        if (dtype == FG_F16) return head_bwd_tc<__half>(g_logits, hidden_pre, w1, w2, m, d_in, d_hid, k_head, g_pooled, workspace, fg_stream(stream));
+        if (dtype == FG_F32) return head_bwd_tf32(g_logits, (const float*)hidden_pre, (const float*)w1, (const float*)w2, m, d_in, d_hid, k_head,
+                                                  (float*)g_pooled, workspace, fg_stream(stream));
+        return FG_ERR_DTYPE;
     }
     float* g_pre = (float*)workspace;
     dim3 grid((d_in + 63) / 64, (m + 63) / 64);

@@ -80,6 +80,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 template <typename T> struct Fmt;
 template <> struct Fmt<__nv_bfloat16> { static constexpr int code = 1; };
 template <> struct Fmt<__half> { static constexpr int code = 0; };
+template <> struct Fmt<float> { static constexpr int code = 2; };          // TF32 operands (fp32 in shared memory)
+
+// fp32 inputs run on the tensor cores as TF32 with an error-compensating split: x = hi + lo with hi = cvt.rna.tf32(x) and
+// lo = x - hi (exact); the three passes  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  accumulate into the same TMEM tile, which keeps
+// the result at ~2^-21 relative (plain TF32: ~2^-11 per product, not enough for the 1e-3 bar on logits of magnitude ~10).
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 struct Params {
     const void* A; int lda;           // [M, K] row-major, 16-bit
@@ -117,7 +127,7 @@ __device__ __forceinline__ void epilogue(const Params& p, uint32_t tmem, const f
                 if (kb == 0 && row < p.M) {
                     int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(prs)[q];
+                    for (int q = 0; q < (int)(32 * sizeof(T) / 16); q++) dst[q] = reinterpret_cast<const int4*>(prs)[q];
                 }
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
@@ -144,7 +154,7 @@ __device__ __forceinline__ void epilogue(const Params& p, uint32_t tmem, const f
                 for (int i = 0; i < 32; i++) o16[i] = from_f32<T>(v[i]);
                 int4* dst = reinterpret_cast<int4*>(out + (size_t)row * p.ldo + n0 + ch * 32);
 #pragma unroll
-                for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const int4*>(o16)[q];
+                for (int q = 0; q < (int)(32 * sizeof(T) / 16); q++) dst[q] = reinterpret_cast<const int4*>(o16)[q];
             }
         }
     }
@@ -266,9 +276,17 @@ __device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 
 // dynamic smem (1024-byte aligned inside the kernel): STAGES x (A | B) | W2 tile | b1 tile | full[STAGES] empty[STAGES] done | tmem slot
+//
+// fp32 (T = float): a row of a tile is 32 elements (still 128 bytes, so stage sizes, swizzle and descriptors are unchanged),
+// one MMA covers K = 8, and B is K-major in BOTH modes (the backward gets W1 transposed by the split pre-pass).  The K loop
+// runs `passes` = 3 times over the operands with the (hi, hi), (hi, lo), (lo, hi) tensor maps.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(THREADS)
-head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const __grid_constant__ TmaMap mapB) {
+head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const __grid_constant__ TmaMap mapB,
+                     const __grid_constant__ TmaMap mapAlo, const __grid_constant__ TmaMap mapBlo, int passes) {
+    constexpr bool F32 = sizeof(T) == 4;
+    constexpr int BKE = 128 / (int)sizeof(T);                  // elements of K per stage
+    constexpr bool B_KMAJOR = MODE == 0 || F32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
     float* w2s = reinterpret_cast<float*>(smem + STAGES * (A_STAGE + B_STAGE));
@@ -280,20 +298,24 @@ head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const 
     const uint32_t ring = s32(smem);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int ksteps = p.K / BK;
+    const int kper = p.K / BKE, ksteps = kper * passes;
+    auto fetch = [&](int ks, int slot) {                      // thread 0: operands of K step ks -> ring slot
+        const int pass = ks / kper, k0 = (ks - pass * kper) * BKE;
+        const TmaMap* ma = pass == 2 ? &mapAlo : &mapA;
+        const TmaMap* mb = pass == 1 ? &mapBlo : &mapB;
+        const uint32_t a_dst = ring + slot * (A_STAGE + B_STAGE);
+        bar_expect_tx(&full[slot], A_STAGE + B_STAGE);
+        tma_load_2d(a_dst, ma, k0, m0, &full[slot]);
+        if (B_KMAJOR) tma_load_2d(a_dst + A_STAGE, mb, k0, n0, &full[slot]);
+        else          tma_load_2d(a_dst + A_STAGE, mb, n0, k0, &full[slot]);
+    };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
         bar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the whole ring is free: start streaming before anything else happens
-        for (int s = 0; s < STAGES && s < ksteps; s++) {
-            const uint32_t a_dst = ring + s * (A_STAGE + B_STAGE);
-            bar_expect_tx(&full[s], A_STAGE + B_STAGE);
-            tma_load_2d(a_dst, &mapA, s * BK, m0, &full[s]);
-            if (MODE == 0) tma_load_2d(a_dst + A_STAGE, &mapB, s * BK, n0, &full[s]);
-            else           tma_load_2d(a_dst + A_STAGE, &mapB, n0, s * BK, &full[s]);
-        }
+        for (int s = 0; s < STAGES && s < ksteps; s++) fetch(s, s);
     }
     if (warp == 0) {
         __syncwarp();
@@ -312,17 +334,18 @@ head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const 
     const uint32_t tmem = *tmem_slot;
 
     if (tid == 0) {
-        const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code, MODE == 1 ? 1 : 0);
+        const uint32_t idesc = instr_desc(Fmt<T>::code, Fmt<T>::code, B_KMAJOR ? 0 : 1);
         for (int ks = 0; ks < ksteps; ks++) {
             const int st = ks % STAGES;
             bar_wait(&full[st], (uint32_t)((ks / STAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = ring + st * (A_STAGE + B_STAGE), b0 = a0 + A_STAGE;
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; kk++) {
+            for (int kk = 0; kk < 4; kk++) {                  // 4 MMAs per 128-byte K slab: K = 16 (16-bit) or 8 (tf32) each
                 const uint64_t ad = smem_desc_sw128(a0 + kk * 32);
-                const uint64_t bd = smem_desc_sw128(MODE == 0 ? b0 + kk * 32 : b0 + kk * 2048);
-                mma_f16(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
+                const uint64_t bd = smem_desc_sw128(B_KMAJOR ? b0 + kk * 32 : b0 + kk * 2048);
+                if (F32) mma_tf32(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
+                else mma_f16(tmem, ad, bd, idesc, (ks | kk) ? 1u : 0u);
             }
             mma_commit(&empty[st]);
             if (ks == ksteps - 1) mma_commit(done);
@@ -331,11 +354,7 @@ head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const 
             if (prev >= 0 && nxt < ksteps) {
                 const int ps = prev % STAGES;
                 bar_wait(&empty[ps], (uint32_t)((prev / STAGES) & 1));
-                const uint32_t a_dst = ring + ps * (A_STAGE + B_STAGE);
-                bar_expect_tx(&full[ps], A_STAGE + B_STAGE);
-                tma_load_2d(a_dst, &mapA, nxt * BK, m0, &full[ps]);
-                if (MODE == 0) tma_load_2d(a_dst + A_STAGE, &mapB, nxt * BK, n0, &full[ps]);
-                else           tma_load_2d(a_dst + A_STAGE, &mapB, n0, nxt * BK, &full[ps]);
+                fetch(nxt, ps);
             }
         }
     }
@@ -346,6 +365,36 @@ head_gemm_tma_kernel(const Params p, const __grid_constant__ TmaMap mapA, const 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// ---- TF32 split pre-pass (fp32 inputs): hi = cvt.rna.tf32(x), lo = x - hi; optionally transposed ([rows, cols] -> [cols, rows])
+__device__ __forceinline__ float tf32_hi(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h; reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+// x [rows, cols] row-major -> hi, lo [cols, rows]; 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+split_transpose_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int rows, int cols) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) t[j][tx] = (r0 + j < rows && c0 + tx < cols) ? x[(size_t)(r0 + j) * cols + c0 + tx] : 0.f;
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;
+        if (c < cols && r < rows) {
+            const float v = t[tx][j], h = tf32_hi(v);
+            hi[(size_t)c * rows + r] = h; lo[(size_t)c * rows + r] = v - h;
+        }
+    }
 }
 
 inline size_t smem_bytes_tma(int mode, int k_head) {

@@ -200,6 +200,7 @@ __global__ void region_scale_kernel(const T* __restrict__ g_in, const int32_t* _
 
 #include "fg_sample_tiled.cuh"
 #include "fg_image_grad_staged.cuh"
+#include "fg_image_grad_quad.cuh"
 
 // ------------------------------------------------------------------------------ factors
 // python slice semantics: a negative stop counts from the end (E1:1594-1597 with a -1 box)
@@ -307,7 +308,8 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
     p.boxes = (const long long*)boxes; p.ind = indicators;
     p.chips = chips; p.ch = chip_h; p.cw = chip_w; p.small = small; p.sh = small_h; p.sw = small_w;
     p.fill = fill_value; p.total_tiles = (int)total;
-    p.pair_mode = getenv("FG_FWD_PAIR") ? 1 : 2;      // 1: tuning A/B, two columns per thread everywhere
+    static const bool fwd_pair = getenv("FG_FWD_PAIR") != nullptr;      // tuning A/B switch, read once
+    p.pair_mode = fwd_pair ? 1 : 2;                    // 1: two columns per thread everywhere
     const unsigned grid = (unsigned)(total < 2LL * FG_NUM_SMS ? total : 2LL * FG_NUM_SMS);   // persistent, 2 CTAs per SM
     switch (dtype) {
         case FG_F32: return launch_fwd_tiled_t<float, 2>(p, smem, grid, st);
@@ -321,15 +323,40 @@ template <typename T>
 static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 grid, cudaStream_t st) {
     const bool spec = p.H == 512 && p.W == 512 && (!p.g_small || (p.sh == 224 && p.sw == 224)) && (!p.g_chips || (p.ch == 224 && p.cw == 224));
     cudaError_t e;
-    if constexpr (sizeof(T) == 2) {
-        // 16-bit gradients at the BASELINE shape: rows staged through shared memory by bulk async copies
-        const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switch for kernel tuning runs
+    {
+        // the BASELINE shape: gradient rows staged through shared memory by bulk async copies
+        static const bool staged_off = getenv("FG_BWD_GATHER") != nullptr;      // A/B switches for kernel tuning runs (read once)
+        // 16-bit: the first-generation staged kernel stays the default (0.54 ms vs 0.56 ms for 1024 images on B200: at 2 bytes
+        // per element both are bound by instruction issue / latency, not by the L1 data pipe the second generation relieves);
+        // FG_BWD_QUAD=1 selects the second generation for A/B runs.  fp32 always takes the second generation (0.76 ms vs 1.43 ms).
+        static const bool v1 = getenv("FG_BWD_QUAD") == nullptr;
         const bool aligned = ((uintptr_t)p.g_small % 16 == 0) && ((uintptr_t)p.g_chips % 16 == 0);
         if (spec && aligned && !staged_off) {
             // rows per CTA: per-CTA set-up (tap tables) is amortised over NSUB * 8 rows, but the grid should still be
             // >= ~8 waves of 148 SMs x 3 resident CTAs; FG_BWD_NSUB overrides for tuning runs only
             const int nsub_env = getenv("FG_BWD_NSUB") ? atoi(getenv("FG_BWD_NSUB")) : 0;
             const int nsub = nsub_env ? nsub_env : (p.n >= 896 ? 16 : p.n >= 448 ? 8 : 4);
+            if (!v1 || sizeof(T) == 4) {
+                // second generation (fg_image_grad_quad.cuh): four columns per thread, packed shared loads, fp32 and 16-bit
+#define FG_LAUNCH_QUAD(NS)                                                                                                          \
+                do {                                                                                                                \
+                    using L = GqLayout<T, NS>;                                                                                      \
+                    if (p.g_small) {                                                                                                \
+                        e = cudaFuncSetAttribute(image_grad_quad_kernel<T, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total); \
+                        if (e != cudaSuccess) return (int)e;                                                                        \
+                        image_grad_quad_kernel<T, NS, true><<<dim3(512 / (NS * GQ_ROWS), p.n), 256, L::total, st>>>(p);             \
+                    } else {                                                                                                        \
+                        e = cudaFuncSetAttribute(image_grad_quad_kernel<T, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total); \
+                        if (e != cudaSuccess) return (int)e;                                                                        \
+                        image_grad_quad_kernel<T, NS, false><<<dim3(512 / (NS * GQ_ROWS), p.n), 256, L::total, st>>>(p);            \
+                    }                                                                                                               \
+                } while (0)
+                if (nsub == 16) FG_LAUNCH_QUAD(16); else if (nsub == 8) FG_LAUNCH_QUAD(8); else FG_LAUNCH_QUAD(4);
+#undef FG_LAUNCH_QUAD
+                FG_LAUNCH_CHECK();
+                return FG_OK;
+            }
+          if constexpr (sizeof(T) == 2) {
             if (nsub == 16) {
                 using L = GsLayout<16>;
                 e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
@@ -348,6 +375,7 @@ static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 gri
             }
             FG_LAUNCH_CHECK();
             return FG_OK;
+          }
         }
     }
     if (spec) {

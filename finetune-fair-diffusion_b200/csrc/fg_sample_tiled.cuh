@@ -371,7 +371,7 @@ struct Tab {
 
 // Outputs of an axis (out_size samples of an in_size-long virtual box) whose 2-tap footprint covers box
 // coordinate p:  exactly those with i0(o) in {p-1, p}; contiguous because i0 is monotone in o.
-__device__ __forceinline__ Tab make_tab(int p, float scale, int in_size, int out_size) {
+__device__ __noinline__ Tab make_tab(int p, float scale, int in_size, int out_size) {
     Tab t; t.lo = 0; t.n = 0;
 #pragma unroll
     for (int q = 0; q < TABW; q++) t.w[q] = 0.f;

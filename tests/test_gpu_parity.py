@@ -552,7 +552,10 @@ def test_assign_e1_half_golden(fg, dn):
         ratio = float(g[f"e1_{dn}_ratio_{c}"])
         t, u = fg.generate_dynamic_targets(p, target_ratio=ratio, w_uncertainty=True)
         assert np.array_equal(t.cpu().numpy(), g[f"e1_{dn}_targets_{c}"])
-        assert u.dtype == p.dtype and _ulp_diff(u, g[f"e1_{dn}_unc_{c}"]).max() <= 1       # lgamma-based CDF vs Boost's
+        # lgamma-based CDF vs Boost's: one unit in the last place, or 1e-7 absolute in the far tails (where 1 - cdf cancels)
+        ref_u = half_tensor(g[f"e1_{dn}_unc_{c}"], dn).float()
+        assert u.dtype == p.dtype
+        assert bool(((u.float().cpu() - ref_u).abs() <= torch.maximum(ref_u.abs() * (2.0 ** -7 if dn == "bf16" else 2.0 ** -10), torch.tensor(1e-7))).all())
         t2, _ = fg.generate_dynamic_targets(p, target_ratio=ratio, w_uncertainty=True, uncertainty_threshold=0.2)
         assert np.array_equal(t2.cpu().numpy(), g[f"e1_{dn}_thr_{c}"])
 
