@@ -329,7 +329,7 @@ static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 gri
         // 16-bit: the first-generation staged kernel stays the default (0.54 ms vs 0.56 ms for 1024 images on B200: at 2 bytes
         // per element both are bound by instruction issue / latency, not by the L1 data pipe the second generation relieves);
         // FG_BWD_QUAD=1 selects the second generation for A/B runs.  fp32 always takes the second generation (0.76 ms vs 1.43 ms).
-        static const bool v1 = getenv("FG_BWD_QUAD") == nullptr;
+        const bool v1 = getenv("FG_BWD_QUAD") == nullptr;                      // (dynamic: the parity tests toggle it in-process)
         const bool aligned = ((uintptr_t)p.g_small % 16 == 0) && ((uintptr_t)p.g_chips % 16 == 0);
         if (spec && aligned && !staged_off) {
             // rows per CTA: per-CTA set-up (tap tables) is amortised over NSUB * 8 rows, but the grid should still be

@@ -29,6 +29,32 @@ def _to(v, device):
     return v
 
 
+def tied_rows(probs_valid):
+    """Rows whose cost row holds two exactly equal class costs (e.g. two race probabilities that round to the same 16-bit
+    value).  Swapping such a row between the tied classes leaves the transport cost unchanged, so the optimal plan is not
+    unique there -- POT's own choice is arbitrary -- and an exact solver may legitimately differ from
+    another exact solver on THESE rows only.  ``probs_valid``: the probability tensors of the rows with a face."""
+    from oracle import assign as oassign
+    pa = probs_valid[2] if len(probs_valid) == 3 else None
+    M = oassign.cost_matrix(probs_valid[0], probs_valid[1], pa)
+    srt = np.sort(M, axis=1)
+    return torch.tensor((np.diff(srt, axis=1) == 0).any(axis=1)), M
+
+
+def assert_equal_up_to_ties(got, ref, probs_all, what):
+    """``got`` / ``ref``: per-row tensors over ALL rows.  Bit-exact on every row whose costs are tie-free; rows with tied
+    costs may differ (see tied_rows)."""
+    if torch.equal(got, ref):
+        return 0
+    valid = (probs_all[0] != -1).all(-1) & (probs_all[1] != -1).all(-1)
+    tied_v, _ = tied_rows([p[valid] for p in probs_all])
+    tied = torch.zeros(valid.shape[0], dtype=torch.bool)
+    tied[valid] = tied_v
+    diff = got != ref
+    assert not bool((diff & ~tied).any()), (what, "differs on", int((diff & ~tied).sum()), "rows with tie-free costs")
+    return int(diff.sum())
+
+
 def check_small_steps(device="cuda:0"):
     from fairguide import pipeline
     from oracle import pipeline as opipe
@@ -126,8 +152,11 @@ def check_step_vs_oracle(kind="gender_race_age", n=1024, dtype=torch.bfloat16, n
     for a in range(n_attr):
         t = res[2 * a].clone()
         t[res[2 * a + 1] > cfg.uncertainty_threshold] = -1                                   # E3:2022-2023
-        targets.append(t)
-        assert torch.equal(cpu(out["targets"][a]), t), ("targets", a, int((cpu(out["targets"][a]) != t).sum()))
+        if kind == "gender":
+            assert torch.equal(cpu(out["targets"][a]), t), ("targets", a, int((cpu(out["targets"][a]) != t).sum()))
+        else:
+            report[f"rows_differing_by_cost_ties_{a}"] = assert_equal_up_to_ties(cpu(out["targets"][a]), t, probs_dev, f"targets[{a}]")
+        targets.append(cpu(out["targets"][a]))          # the losses / gradients below are checked against the device's own targets
     report["rows_with_target"] = [int((t != -1).sum()) for t in targets]
 
     # ---- losses
@@ -238,7 +267,10 @@ def check_multi_rank(kind, dtype, dev, rank, world, n_side_global=256, S=100, ca
             t = res[2 * a].clone()
             t[res[2 * a + 1] > cfg.uncertainty_threshold] = -1
             got = out["targets_all"][a].cpu()
-            assert torch.equal(got, t), f"targets_all[{a}] differs from the oracle in {int((got != t).sum())} rows"
+            if kind == "gender":
+                assert torch.equal(got, t), f"targets_all[{a}] differs from the oracle in {int((got != t).sum())} rows"
+            else:
+                assert_equal_up_to_ties(got, t, probs_all, f"targets_all[{a}]")
         report["rows_with_target"] = [int((out["targets_all"][a] != -1).sum()) for a in range(n_attr)]
     if captured:
         cap = pipeline.CapturedStep(path, batch, nv, rand_tensors=rands)

@@ -608,13 +608,26 @@ def test_assign_mc_half_large_vs_oracle(fg, dtype, N, kind, S):
     ref = fn(*probs, True, S, rand_tensors=rands, literal=False)
     api_fn = fg.generate_dynamic_targets_gender_race if n_attr == 2 else fg.generate_dynamic_targets_gender_race_age
     out = api_fn(*[p.to(DEV) for p in probs], True, S, rand_tensors=tuple(r.to(DEV) for r in rands), num_valid=nv)
+    # 16-bit probabilities often hold two exactly equal class probabilities in a row: equal costs, a non-unique optimum
+    # (the device plan of the one such case here was checked to have the oracle's objective to the last bit, tools/diag_assign.py).
+    # Rows with tie-free costs must agree bit for bit; tied rows may differ.
+    from tests.stepcheck import assert_equal_up_to_ties
     for a in range(2 * n_attr):
-        assert torch.equal(out[a].cpu(), ref[a]), (kind, N, a)
+        assert_equal_up_to_ties(out[a].cpu(), ref[a], probs, (kind, N, a))
     thr = api_fn(*[p.to(DEV) for p in probs], True, S, rand_tensors=tuple(r.to(DEV) for r in rands), num_valid=nv,
                  uncertainty_threshold=0.2)
     for a in range(n_attr):
         t_ref, _ = oassign.threshold_and_slice(ref[2 * a], ref[2 * a + 1], 0.2, N, 0)
-        assert torch.equal(thr[2 * a].cpu(), t_ref), (kind, N, a)
+        assert_equal_up_to_ties(thr[2 * a].cpu(), t_ref, probs, (kind, N, a, "thresholded"))
+    # ... and the summed plan is optimal: same transport cost as the oracle's, same column sums
+    _, counts, ws = fg.api._mc_targets(tuple(p.to(DEV) for p in probs), True, S, tuple(r.to(DEV) for r in rands), nv, None, None,
+                                       return_counts=True)
+    valid = ~miss
+    M = oassign.cost_matrix(probs[0][valid], probs[1][valid], probs[2][valid] if n_attr == 3 else None)
+    ref_counts = oassign.plan_counts(M, oassign.draw_histograms(*rands))
+    dev_counts = counts.cpu().numpy().astype(np.float64)
+    assert np.array_equal(dev_counts.sum(0), ref_counts.sum(0)) and (dev_counts.sum(1) == S).all()
+    assert abs((dev_counts * M).sum() - (ref_counts * M).sum()) <= 1e-9 * (ref_counts * M).sum()
 
 
 # ----------------------------------------------------------------------------- whole path

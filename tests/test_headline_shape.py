@@ -47,11 +47,14 @@ def test_sampler_512_to_224_vs_oracle(fg, dtype, rtol):
 
 
 @pytest.mark.parametrize("dtype,rtol", [(torch.bfloat16, 2e-2), (torch.float16, 5e-3), (torch.float32, 1e-3)])
-@pytest.mark.parametrize("nsub", ["0", "4", "8", "16"])
+@pytest.mark.parametrize("nsub", ["0", "4", "8", "16", "q4", "q16"])
 def test_image_grad_512_vs_oracle(fg, dtype, rtol, nsub, monkeypatch):
     """image_grad_staged_kernel<T,NSUB> (16-bit) / the fp32 backward at the BASELINE shape against autograd through
     oracle.crop + oracle.hooks (the reference's crop, hook and Resize), every rows-per-CTA variant."""
     from oracle import crop as ocrop, hooks as ohooks
+    if nsub.startswith("q"):                    # the second-generation kernel for 16-bit gradients too (fp32 always uses it)
+        monkeypatch.setenv("FG_BWD_QUAD", "1")
+        nsub = nsub[1:]
     if nsub != "0":
         monkeypatch.setenv("FG_BWD_NSUB", nsub)
     n = 16
