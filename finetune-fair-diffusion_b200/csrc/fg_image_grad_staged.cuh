@@ -109,6 +109,10 @@ struct GsCols {             // per-thread constants of its two image columns
 template <typename T, bool DO_S, int CHIP>
 __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_t sbuf, char* out) {
     constexpr unsigned oplb = 512u * 512u * 2u, orowb = 512u * 2u;
+    // A resized row feeds TWO adjacent image rows (i0 and i0 + 1): the second of them finds the same record offsets and
+    // reuses the six values the first one loaded (7 of the 14 tapped rows of every 16 skip their shared loads).
+    uint32_t prev_x = 0xffffffffu, prev_w = 0xffffffffu;
+    float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < GS_ROWS; r++) {
         float o0[3] = {0.f, 0.f, 0.f}, o1[3] = {0.f, 0.f, 0.f};
@@ -116,12 +120,17 @@ __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_
             const uint4 h = lds_v4(rec + r * 16);             // off, wy, wr      (warp-uniform)
             const float wy = __uint_as_float(h.y), wr = __uint_as_float(h.z);
             const float f0 = fmaf(wr, k.wd0, wy * k.ws0), f1 = fmaf(wr, k.wd1, wy * k.ws1);
-            const uint32_t a0 = sbuf + k.s0 + (k.m0 ? h.x : h.w), a1 = sbuf + k.s1 + (k.m1 ? h.x : h.w);
-            uint32_t v0[3], v1[3];
+            if (h.x != prev_x || h.w != prev_w) {             // warp-uniform
+                const uint32_t a0 = sbuf + k.s0 + (k.m0 ? h.x : h.w), a1 = sbuf + k.s1 + (k.m1 ? h.x : h.w);
+                uint32_t v0[3], v1[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { v0[c] = lds_u16(a0 + c * GS_S_CH); v1[c] = lds_u16(a1 + c * GS_S_CH); }
+                for (int c = 0; c < 3; c++) { v0[c] = lds_u16(a0 + c * GS_S_CH); v1[c] = lds_u16(a1 + c * GS_S_CH); }
 #pragma unroll
-            for (int c = 0; c < 3; c++) { o0[c] = f0 * bits16_to_f32<T>(v0[c]); o1[c] = f1 * bits16_to_f32<T>(v1[c]); }
+                for (int c = 0; c < 3; c++) { g0[c] = bits16_to_f32<T>(v0[c]); g1[c] = bits16_to_f32<T>(v1[c]); }
+                prev_x = h.x; prev_w = h.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { o0[c] = f0 * g0[c]; o1[c] = f1 * g1[c]; }
         }
         if (CHIP == 1) {
             // downscaled box: <= 2 taps per column and the two columns' taps start 0 or 1 apart -> 3 words cover both
