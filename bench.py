@@ -147,6 +147,29 @@ def peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def pin_to_gpu_numa(torch, local_rank):
+    """Bind this rank (and therefore the pinned host buffers it allocates next: first touch) to the CPU cores of the NUMA
+    node its GPU hangs off.  With every rank on node 0 the end-to-end number stopped scaling at 4 GPUs (all H2D copies
+    crossed one memory controller / one socket link).  Best effort: returns a short description or the reason it was skipped."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {dev}: no NUMA affinity reported"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"gpu {dev}: node {node} has no allowed cpu"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {dev} -> numa node {node} ({len(allowed)} cpus)"
+    except Exception as ex:                                            # noqa: BLE001
+        return f"skipped: {type(ex).__name__}: {str(ex)[:80]}"
+
+
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_reference_step(kind, n_images, solver, seed=5991):
     """One step of the oracle's CPU restatement of the reference path on `n_images` images of the workload (fp32)."""
@@ -223,6 +246,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a step from Python instead of replaying a CUDA graph")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's image count per GPU (default); strong: that count in total, sharded")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="for ncu: time only the eager (launch by launch) steps between cudaProfilerStart/Stop, print a short line, exit")
     ap.add_argument("--surface", default="step", choices=["step", "closures"],
                     help="closures: `value` is measured through the fairguide.bind() closure surface too (eager, no graph)")
     a = ap.parse_args()
@@ -260,6 +285,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = pin_to_gpu_numa(torch, local_rank) if world > 1 else "single rank: not pinned"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == a.gpus or world == 1, (world, a.gpus)
@@ -321,7 +347,7 @@ def main():
         nv = global_faces(batch)
         res = {}
         captured, note = None, "off (--no-graph)"
-        if not a.no_graph:
+        if not a.no_graph and not a.profile_only:
             try:
                 captured = pipeline.CapturedStep(path, batch, nv)
                 note = "on"
@@ -332,6 +358,13 @@ def main():
         ms_eager, calls = timed(lambda: res.__setitem__("out", path.step(batch, num_valid=nv, probe=probe)), max(3, steps // 2), warmup)
         launches_per_step = sum(_lib.KERNELS_PER_CALL.get(k, 1) * v for k, v in calls.items()) // max(3, steps // 2)
         stage_ms = {k: probe.mean_ms(k) for k in ("sample_fwd", "assign", "image_grad")}
+        if a.profile_only:
+            if rank == 0:
+                print(json.dumps({"profile_only": True, "workload": a.workload, "ms_per_step_eager": ms_eager, "stage_ms": stage_ms,
+                                  "gpu_launches_per_step": launches_per_step}))
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(0)
         ms_step, _ = timed(lambda: res.__setitem__("out", captured.replay() if captured is not None else path.step(batch, num_valid=nv)),
                            steps, warmup)
         pipeline.validate_step(res["out"])                            # status words of the assignment kernels (frozen face count, exact plans)
@@ -527,7 +560,7 @@ def main():
             "dtype": {"bfloat16": "bf16", "float32": "f32", "float16": "f16"}[dtype_name], "data": "synthetic",
             "config": {"workload": f"{a.workload}: {desc}", "kind": kind, "global_batch": n_global, "images_per_gpu": n_local,
                        "image": "3x512x512", "chip": "3x224x224", "mc_draws_per_rank": cfg.num_samples_per_device,
-                       "faces_in_batch": num_valid, "parallelism": f"dp{world}",
+                       "faces_in_batch": num_valid, "parallelism": f"dp{world}", "numa": numa_note,
                        "backbone": "excluded (stand-in pooled features and chip gradient; SURVEY.md 8d)",
                        "l2": f"inputs larger than L2 ({(fwd_b + bwd_b) * n_local / 1e6:.0f} MB touched per step per GPU vs 126 MB)"},
             "stage_ms": stage_ms, "ms_per_step_eager": ms_eager, "cuda_graph": m["graph"], "gpu_launches": launches_per_step * a.steps,

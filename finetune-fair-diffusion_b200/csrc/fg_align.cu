@@ -130,21 +130,24 @@ aligned_warp_fwd_kernel(const T* __restrict__ images, const float* __restrict__ 
     }
 }
 
-// backward: persistent CTAs of 8 warps; a CTA walks the images round-robin and, inside an image, the 32x8-pixel tiles of
-// the bounding box of the taps only (the whole image when it has to write the zeros as well) -- a grid over all tiles
-// of all images spent its time launching ~1M empty CTAs.  thread = one source pixel, all channels.  Measured slower and
-// dropped: staging the tile's output-gradient footprint in shared memory (two block barriers per tile, 2.75 ms vs 1.71 ms) and
-// four pixels per thread with their accumulate targets loaded up front (2.27 ms).
+// backward: grid (AW_SLICES, n): the CTAs of an image share the 32x8-pixel tiles of the bounding box of its taps (the whole
+// image when the zeros have to be written as well) round-robin.  thread = one source pixel, all channels.  History: a grid
+// over all tiles of all images spent its time launching ~1M empty CTAs (2.4 ms for 1024 images); one persistent CTA per
+// image (round-robin over the images) left a CTA alone with the ~175 tiles of a face, i.e. with a long dependent chain of
+// L2 gathers, and the last images of the launch had the GPU to themselves (1.7 ms).  Measured slower and dropped: staging
+// the tile's output-gradient footprint in shared memory (two block barriers per tile) and four pixels per thread.
+constexpr int AW_SLICES = 48;
 template <typename T>
 __global__ void __launch_bounds__(256)
 aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ params, const uint8_t* __restrict__ indicators,
                         int n, int C, int Hs, int Ws, int Hd, int Wd, int accumulate, T* __restrict__ g_images) {
     const int tx_ = threadIdx.x & 31, ty_ = threadIdx.x >> 5;
-    for (int img = blockIdx.x; img < n; img += gridDim.x) {
+    {
+        const int img = blockIdx.y;
         const float* P = params + (size_t)img * ALIGN_PARAMS;
         const bool face = !indicators || indicators[img];
         const int bx0 = (int)P[12], by0 = (int)P[13], bx1 = (int)P[14], by1 = (int)P[15];
-        if (accumulate && (!face || bx1 < bx0 || by1 < by0)) continue;
+        if (accumulate && (!face || bx1 < bx0 || by1 < by0)) return;
         // tile range: the bounding box (accumulate) or the whole image (overwrite)
         const int X0 = accumulate ? (bx0 & ~31) : 0, Y0 = accumulate ? (by0 & ~7) : 0;
         const int X1 = accumulate ? bx1 : Ws - 1, Y1 = accumulate ? by1 : Hs - 1;
@@ -153,7 +156,7 @@ aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ p
         const float c00 = P[0], c01 = P[1], c02 = P[2], c10 = P[3], c11 = P[4], c12 = P[5];
         const float hx = fabsf(d00) + fabsf(d01), hy = fabsf(d10) + fabsf(d11);
         const T* go = g_out + (size_t)img * C * Hd * Wd;
-        for (int tile = 0; tile < tiles_x * tiles_y; tile++) {
+        for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
             const int x = X0 + (tile % tiles_x) * 32 + tx_, y = Y0 + (tile / tiles_x) * 8 + ty_;
             if (x >= Ws || y >= Hs) continue;
             T* g = g_images + (size_t)img * C * Hs * Ws + (size_t)y * Ws + x;
@@ -169,7 +172,15 @@ aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ p
             const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int i = i0; i <= i1; i++) {
+                // Output pixel (j,i) taps this pixel iff its source position lies in [x-1, x+1) x [y-1, y+1); relative to the
+                // pixel that position is the affine image C (j - qx, i - qy), so most of the window is rejected by two FMAs
+                // (with a margin for the fp32 rounding of q); survivors are decided by the forward's own expressions below.
+                const float ri = (float)i - qy;
+                const float ex = c01 * ri, ey = c11 * ri;
                 for (int j = j0; j <= j1; j++) {
+                    const float rj = (float)j - qx;
+                    const float dxs = fmaf(c00, rj, ex), dys = fmaf(c10, rj, ey);
+                    if (fabsf(dxs) > 1.02f || fabsf(dys) > 1.02f) continue;
                     // the same fp32 expressions as the forward, so the tap weights are bit-identical
                     const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
                     const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
@@ -401,7 +412,8 @@ extern "C" int fg_aligned_warp_bwd(const void* g_out, int n, int C, int Hd, int 
     if (n < 0 || C < 1 || C > 4 || Hs < 2 || Ws < 2 || Hd < 1 || Wd < 1) return FG_ERR_INVALID_ARG;
     if (n == 0) return FG_OK;
     if (!g_out || !params || !g_images) return FG_ERR_INVALID_ARG;
-    const int grid = n < 8 * FG_NUM_SMS ? n : 8 * FG_NUM_SMS;       // persistent: up to 8 CTAs of 256 threads per SM
+    if (n > 65535) return FG_ERR_LIMIT;
+    const dim3 grid(AW_SLICES, n);
     FG_DISPATCH_DTYPE(dtype, T,
         aligned_warp_bwd_kernel<T><<<grid, 256, 0, fg_stream(stream)>>>((const T*)g_out, params, indicators, n, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
     FG_LAUNCH_CHECK();
