@@ -248,6 +248,19 @@ struct SolverSmem {
     unsigned whist[2][SOLVER_WARPS][KP / 2];   // price search: per-warp class counts (packed), by iteration parity
     __align__(16) float wprice[SOLVER_WARPS][KP];   // price search: the warp's copy of the K prices of this round
     int status;
+#ifdef FG_OT_PROFILE
+    int prof_pivots, prof_pivot_last, prof_rounds;
+#endif
+    int rcnt[3][KP];           // price search: class counts of the round (atomic adds of the warp sums), three buffers in rotation
+    int n_active;              // trust-region price search: rows in the active list, and whether the list overflowed
+    int tr_overflow;
+    // first scan of the large modes (sweep_assign_scan): per (class k, target l) the fp32 minimum of M[i,l] - M[i,k] over the
+    // rows of k as an order-preserving key, the number of rows within SCREEN_EPS of it and the lowest such row.  Rows of 17
+    // words: the 32 lanes of an access hold different k and the same l, so a stride of 16 would put them on two banks.
+    unsigned smin[KP][KP + 1];
+    int scnt[KP][KP + 1];
+    int sidx[KP][KP + 1];
+    unsigned sexact[KP];       // targets of class k left to the exact scan (near-ties)
 };
 
 // dynamic shared memory behind the control block
@@ -270,9 +283,63 @@ __device__ __forceinline__ float funkey(unsigned k) { return __uint_as_float((k 
 // differences): 7.2e-7.  Two candidates further apart than twice that in fp32 are ordered the same way in fp64.
 constexpr float SCREEN_EPS = 4e-6f;
 
+// One screening pass over the members of class k for NT target classes: fp32 minimum, runner-up and argmin per target
+// and lane.  The loads of U members per lane are issued together: for the large problems the member lists and the cost
+// copy sit in L2 / global memory and a pass is a chain of dependent round trips (member id -> its costs), so the number
+// of loads in flight, not the arithmetic, sets its duration (one member at a time: 181 k cycles for the first scan of
+// all classes at N = 7720).
+template <int NT, int U>
+__device__ __forceinline__ void screen_pass(const SolverViews& v, int N, int k, int cnt, const int (&ls)[NT],
+                                            float (&b1)[NT], float (&b2)[NT], int (&bi)[NT]) {
+    const int lane = threadIdx.x & 31;
+    const uint16_t* mem = v.members + (size_t)k * N;
+    const float* Mk = v.Mf + (size_t)k * N;
+    int off[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) { off[j] = ls[j] * N; b1[j] = INFINITY; b2[j] = INFINITY; bi[j] = 0x7fffffff; }
+    for (int t0 = 0; t0 < cnt; t0 += 32 * U) {
+        int id[U]; bool ok[U]; float mk[U], x[U][NT];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int t = t0 + 32 * u + lane; ok[u] = t < cnt; id[u] = ok[u] ? (int)mem[t] : 0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            mk[u] = ok[u] ? Mk[id[u]] : 0.f;
+#pragma unroll
+            for (int j = 0; j < NT; j++) x[u][j] = ok[u] ? v.Mf[off[j] + id[u]] : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                const float d = x[u][j] - mk[u];
+                if (d < b1[j]) { b2[j] = b1[j]; b1[j] = d; bi[j] = id[u]; } else if (d < b2[j]) b2[j] = d;
+            }
+    }
+}
+
+// the warp-wide verdict of a screening pass for one target l: a unique fp32 winner clear of every runner-up is the fp64
+// winner (its row goes to wi[k][l], the exact difference follows), anything closer is left to the exact scan
+__device__ __forceinline__ unsigned screen_resolve(SolverSmem& sm, int k, int l, float b1, float b2, int bi) {
+    const int lane = threadIdx.x & 31;
+    const float m1 = funkey(__reduce_min_sync(0xffffffffu, fkey(b1)));
+    const float thr = m1 + SCREEN_EPS;
+    const unsigned cand = __ballot_sync(0xffffffffu, b1 <= thr);
+    const unsigned close2 = __ballot_sync(0xffffffffu, b2 <= thr);
+    if (cand == 0u) {                     // class k is empty
+        if (lane == 0) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
+        return 0u;
+    }
+    if ((cand & (cand - 1)) == 0u && close2 == 0u) {
+        const int win = __shfl_sync(0xffffffffu, bi, __ffs(cand) - 1);
+        if (lane == 0) sm.wi[k][l] = win;          // w[k][l] follows in warp_rescan
+        return 0u;
+    }
+    return 1u << l;
+}
+
 // One warp recomputes w[k][l], wi[k][l] for the classes l in `mask` from the member list of class k.
 // FP64 issues at a small fraction of the FP32 rate on this part and the fp64 matrix lives in global memory, so with the
-// fp32 copy in shared memory (`screen`) a pass over the members finds the fp32 minimum and runner-up of every target:
+// fp32 copy (`screen`) a pass over the members finds the fp32 minimum and runner-up of every target:
 // when the runner-up is more than SCREEN_EPS away the fp32 winner is the fp64 winner, and its exact fp64 difference is
 // computed afterwards by lane l for all targets at once (one round trip to global memory per class).  Only targets
 // with a near-tie take the exact scan over all members.
@@ -281,44 +348,33 @@ __device__ void warp_rescan(SolverSmem& sm, const SolverViews& v, const double* 
     const int lane = threadIdx.x & 31;
     const int cnt = sm.cnt[k];
     const uint16_t* mem = v.members + (size_t)k * N;
-    const float* Mk = v.Mf + (size_t)k * N;
     mask &= ~(1u << k);
     unsigned exact_mask = screen ? 0u : mask;        // targets that need the exact scan
     if (screen) {
         unsigned todo = mask;
-        while (todo) {                               // warp-uniform; 4 target classes per pass over the members
-            int ls[4]; int nl = 0;
+        while (todo) {                               // warp-uniform
+            if (__popc(todo) > 4) {                  // 8 targets per pass, two members per lane in flight
+                int ls[8]; int nl = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (todo) { ls[j] = __ffs(todo) - 1; todo &= todo - 1; nl = j + 1; } else ls[j] = ls[0];
-            }
-            float b1[4], b2[4]; int bi[4];
+                for (int j = 0; j < 8; j++) {
+                    if (todo) { ls[j] = __ffs(todo) - 1; todo &= todo - 1; nl = j + 1; } else ls[j] = ls[0];
+                }
+                float b1[8], b2[8]; int bi[8];
+                screen_pass<8, 2>(v, N, k, cnt, ls, b1, b2, bi);
 #pragma unroll
-            for (int j = 0; j < 4; j++) { b1[j] = INFINITY; b2[j] = INFINITY; bi[j] = 0x7fffffff; }
-            for (int t = lane; t < cnt; t += 32) {
-                const int i = mem[t];
-                const float mk = Mk[i];
+                for (int j = 0; j < 8; j++)
+                    if (j < nl) exact_mask |= screen_resolve(sm, k, ls[j], b1[j], b2[j], bi[j]);      // warp-uniform
+            } else {                                 // up to 4 targets, four members per lane in flight
+                int ls[4]; int nl = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float x = v.Mf[(size_t)ls[j] * N + i] - mk;
-                    if (x < b1[j]) { b2[j] = b1[j]; b1[j] = x; bi[j] = i; } else if (x < b2[j]) b2[j] = x;
+                    if (todo) { ls[j] = __ffs(todo) - 1; todo &= todo - 1; nl = j + 1; } else ls[j] = ls[0];
                 }
-            }
+                float b1[4], b2[4]; int bi[4];
+                screen_pass<4, 4>(v, N, k, cnt, ls, b1, b2, bi);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j >= nl) break;                   // warp-uniform
-                const float m1 = funkey(__reduce_min_sync(0xffffffffu, fkey(b1[j])));
-                const float thr = m1 + SCREEN_EPS;
-                const unsigned cand = __ballot_sync(0xffffffffu, b1[j] <= thr);
-                const unsigned close2 = __ballot_sync(0xffffffffu, b2[j] <= thr);
-                if (cand == 0u) {                     // class k is empty
-                    if (lane == 0) { sm.w[k][ls[j]] = INFINITY; sm.wi[k][ls[j]] = -1; }
-                } else if ((cand & (cand - 1)) == 0u && close2 == 0u) {
-                    const int win = __shfl_sync(0xffffffffu, bi[j], __ffs(cand) - 1);
-                    if (lane == 0) sm.wi[k][ls[j]] = win;          // w[k][l] follows below
-                } else {
-                    exact_mask |= 1u << ls[j];
-                }
+                for (int j = 0; j < 4; j++)
+                    if (j < nl) exact_mask |= screen_resolve(sm, k, ls[j], b1[j], b2[j], bi[j]);      // warp-uniform
             }
         }
         __syncwarp();
@@ -520,6 +576,8 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
         for (int l = 0; l < KK; l++) x[r][l] = have[r] ? cost_key(Mf[l * N + i], l) : 0;
     }
     int* wp = reinterpret_cast<int*>(sm.wprice[warp]);
+    const int rword = ((lane >> 3) << 1) | (lane & 1), rsh = ((lane & 7) >> 1) * 8;      // where lane l finds class l in acc[]
+    int rb = 0;                                                                          // counter buffer of this round
     for (int it = 0; it <= dual_iters; it++) {
         const int my_pk = price_key(my_price);
         if (lane < KK) wp[lane] = my_pk;
@@ -549,17 +607,19 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
             acc[2] = __reduce_add_sync(0xffffffffu, hi & 0x0F0F0F0Fu);        // classes 8,10,12,14
             acc[3] = __reduce_add_sync(0xffffffffu, (hi >> 4) & 0x0F0F0F0Fu); // classes 9,11,13,15
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int w = 0; w < KK / 4; w++) sm.whist[it & 1][warp][w] = acc[w];
+        // lane l adds the warp's count of class l to the round's counter (one shared-memory atomic per warp; every lane then
+        // reads ONE word -- summing the 16 per-warp histograms in every lane of every warp was 40 % of the round's instructions)
+        if (lane < KK) {
+            unsigned a = acc[0];
+            a = rword == 1 ? acc[1] : a;
+            if (KK > 8) { a = rword == 2 ? acc[2] : a; a = rword == 3 ? acc[3] : a; }
+            const int mine = (int)((a >> rsh) & 0xFFu);
+            if (mine) atomicAdd(&sm.rcnt[rb][lane], mine);
         }
         __syncthreads();
-        int cnt = 0;
-        if (lane < KK) {
-            const int word = ((lane >> 3) << 1) | (lane & 1), sh = ((lane & 7) >> 1) * 8;
-#pragma unroll
-            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][word] >> sh) & 0xFFu);
-        }
+        const int cnt = lane < KK ? sm.rcnt[rb][lane] : 0;
+        { const int rz = rb == 0 ? 2 : rb - 1; if (warp == 0 && lane < KP) sm.rcnt[rz][lane] = 0; }     // the buffer of round it + 2
+        rb = rb == 2 ? 0 : rb + 1;
         const int err = lane < KK ? my_b - cnt : 0;
         const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
         if (resid < best_resid) { best_resid = resid; my_best = price_of_key(my_pk); }      // the price the rows actually saw
@@ -576,21 +636,35 @@ __device__ __forceinline__ void price_search_reg(SolverSmem& sm, const float* __
 }
 
 // Price search for problems whose fp32 cost copy does not fit in shared memory (modes 1 / 2 of ot_solve_kernel).  Streaming
-// the whole copy from L2 every round made the search L2-bound (~30 B/clk per SM with 100 CTAs doing the same), so the
-// rows are split three ways and only the remainder is streamed: the first 4 x 512 rows stay in registers for all rounds
-// (as in price_search_reg), the next `slice_rows` rows sit in the shared memory the member lists leave free (class-major
-// slice), the rest is read from global memory.  Histogram and price update as in price_search.
+// the whole copy from L2 every round made the search L2-bound (100 CTAs read the same 0.5 MB per round: ~6 TB/s of L2 hits),
+// so the rows are split three ways: the first 4 x 512 rows stay in registers for all rounds (as in price_search_reg), the
+// next `slice_rows` rows sit in the shared memory the member lists leave free (class-major slice), the rest is read from
+// global memory.  Histogram and price update as in price_search.
+//
+// Trust region (rounds >= pivot_round).  Once the steps are small, the prices stay inside a box  |p_l - p0_l| <= R_l  around
+// their current value p0 (R_l = trust * step_l) for many rounds.  A row whose cheapest class s under the box's most
+// adverse corner still beats every other class,  key_s - (p0_s - R_s) < key_l - (p0_l + R_l)  for all l != s, takes class s
+// under EVERY price vector of the box: it is counted once (`frozen`) and skipped.  One classification sweep over the rows
+// outside the registers separates those rows from the ACTIVE ones, whose keys are packed into the shared-memory slice; the
+// following rounds sweep the registers and the active list only -- everything on chip, no L2 traffic -- and yield exactly the
+// counts a full sweep would.  A price that leaves its box triggers a new classification around the current prices.  If
+// the active rows do not fit the slice (nearly tied costs everywhere), the search falls back to full sweeps from L2.
+// The search is a heuristic either way: the assignment is made exact by the repair steps that follow it.
 template <int KK>
 __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* __restrict__ Mk,
-                                                    int* __restrict__ slice, int slice_rows, int N, int dual_iters, float step0) {
+                                                    int* __restrict__ slice, int slice_rows, int N, int dual_iters, float step0,
+                                                    int pivot_arg) {
     constexpr int RPT = 4;
+    const int pivot_round = pivot_arg & 0xff;            // first round of the trust region
+    const float trust = (float)((pivot_arg >> 8) & 0xff);    // R_l = trust * step_l
+    const int sample_rounds = min((pivot_arg >> 16) & 0xff, pivot_round);   // first rounds that sweep the on-chip rows only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
     int my_prev = 0, best_resid = 0x7fffffff;
     const int my_b = lane < KK ? sm.b[lane] : 0;
     const int reg_rows = min(N, RPT * SOLVER_THREADS);
-    slice_rows = min(slice_rows, N - reg_rows);
-    const int glob_begin = reg_rows + slice_rows;
+    const int cap = slice_rows;                          // rows the slice can hold (static prefix, later the active list)
+    int static_rows = min(slice_rows, N - reg_rows);     // rows of the static prefix currently in the slice
     auto key_at = [&](int l, int i) { return __ldg(Mk + (size_t)l * N + i); };      // (a float fallback in these loops cost 25 %: code size)
     int x[RPT][KK];
     bool have[RPT];
@@ -601,13 +675,112 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
 #pragma unroll
         for (int l = 0; l < KK; l++) x[r][l] = have[r] ? key_at(l, i) : 0;
     }
-    for (int e = tid; e < KK * slice_rows; e += SOLVER_THREADS) {
-        const int l = e / slice_rows, j = e - l * slice_rows;
-        slice[e] = key_at(l, reg_rows + j);
-    }
+    auto fill_static = [&]() {                           // the rows behind the registers, as many as the slice holds
+        static_rows = min(slice_rows, N - reg_rows);
+        for (int e = tid; e < KK * static_rows; e += SOLVER_THREADS) {
+            const int l = e / static_rows, j = e - l * static_rows;
+            slice[l * cap + j] = key_at(l, reg_rows + j);
+        }
+    };
+    fill_static();
+    if (tid == 0) { sm.n_active = 0; sm.tr_overflow = 0; }
     __syncthreads();
+    // The first rounds only steer the prices towards the right region: they sweep the on-chip rows alone (registers + slice, 2/3
+    // of the rows at N = 7720) against the demand scaled to that share -- no L2 traffic, half the time of a full sweep.  Only
+    // the exact rounds that follow can set the best prices.  (Sampling all rounds up to the pivot shrinks the steps on the
+    // sample's sign flips and costs more repair steps than it saves: 2.0 instead of 0.5 per draw.)
+    const bool sample_start = sample_rounds + 8 <= dual_iters && reg_rows + static_rows < N;
+    const float sample_share = (float)(reg_rows + static_rows) / (float)N;
+    int next_pivot = pivot_round;    // the next round that may classify (moved back after an overflow)
+    // trust-region state, identical in every thread (lane l < KK holds class l's pivot key, radius and frozen count)
+    int tr_mode = 0;                 // 0: full / sampled sweeps, 1: inside a trust region (registers + active list)
+    int n_active = 0, my_pk0 = 0, my_rk = 0, my_frozen = 0;
+    int rb = 0;                      // counter buffer of this round (sm.rcnt)
     for (int it = 0; it <= dual_iters; it++) {
         const int my_pk = price_key(my_price);
+        // ---- classification sweep (no price update): pivot = the current prices
+        if (it >= next_pivot && (tr_mode == 0 || __any_sync(0xffffffffu, lane < KK && abs(my_pk - my_pk0) > my_rk))) {
+            my_pk0 = my_pk;
+            my_rk = max(price_key(trust * my_step), 16);
+#ifdef FG_OT_PROFILE
+            if (tid == 0) { sm.prof_pivots++; sm.prof_pivot_last = it; }
+#endif
+            int pkz[KK];
+#pragma unroll
+            for (int l = 0; l < KK; l++) pkz[l] = __shfl_sync(0xffffffffu, my_pk0 + my_rk, l);
+            if (tid == 0) { sm.n_active = 0; sm.tr_overflow = 0; }
+            __syncthreads();
+            unsigned acc[KP / 2];
+#pragma unroll
+            for (int w = 0; w < KP / 2; w++) acc[w] = 0u;
+            unsigned long long h = 0ull; int pending = 0;
+            const int rest = N - reg_rows;
+            for (int j0 = 0; j0 < rest; j0 += SOLVER_THREADS) {          // uniform trip count: the loop body shuffles
+                const int j = j0 + tid;
+                const bool valid = j < rest;
+                const int i = reg_rows + (valid ? j : 0);
+                int y[KK];
+#pragma unroll
+                for (int l = 0; l < KK; l++) y[l] = key_at(l, i) - pkz[l];
+                const int m1 = min_key<KK>(y);
+                const int sc = m1 & 15;
+#pragma unroll
+                for (int l = 0; l < KK; l++) y[l] = l == sc ? 0x7f000000 : y[l];
+                const int m2 = min_key<KK>(y);
+                const int rs = __shfl_sync(0xffffffffu, my_rk, sc);
+                const bool frozen = valid && m2 > m1 + 2 * rs + 16;
+                const bool active = valid && !frozen;
+                if (frozen) {
+                    h += 1ull << (sc << 2);
+                    if (++pending == 15) {
+#pragma unroll
+                        for (int w = 0; w < KP / 2; w++) acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+                        h = 0ull; pending = 0;
+                    }
+                }
+                const unsigned am = __ballot_sync(0xffffffffu, active);
+                int base = 0;
+                if (lane == 0 && am) base = atomicAdd(&sm.n_active, __popc(am));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (active) {
+                    const int slot = base + __popc(am & ((1u << lane) - 1u));
+                    if (slot < cap) {
+#pragma unroll
+                        for (int l = 0; l < KK; l++) slice[l * cap + slot] = key_at(l, i);
+                    } else sm.tr_overflow = 1;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < KK / 2; w++) {
+                acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
+                acc[w] = __reduce_add_sync(0xffffffffu, acc[w]);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int w = 0; w < KK / 2; w++) sm.whist[it & 1][warp][w] = acc[w];
+            }
+            __syncthreads();
+            my_frozen = 0;
+            if (lane < KK) {
+#pragma unroll
+                for (int w = 0; w < SOLVER_WARPS; w++) my_frozen += (int)((sm.whist[it & 1][w][lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu);
+            }
+            n_active = sm.n_active;
+            tr_mode = sm.tr_overflow ? 0 : 1;
+#ifdef FG_OT_PROFILE
+            if (tid == 0) sm.prof_rounds = tr_mode == 0 ? -n_active : n_active;
+#endif
+            static_rows = 0;                                  // the slice no longer holds the static prefix
+            __syncthreads();                                  // every thread has read n_active / tr_overflow; whist is free again
+            if (tr_mode == 0) {
+                // the active rows do not fit (the steps, hence the radii, are still large, or the costs are nearly tied): back to
+                // full sweeps with the static prefix restored, and a new attempt two rounds later
+                fill_static();
+                next_pivot = it + 2;
+                __syncthreads();
+            }
+        }
+        const bool sampled = sample_start && it < sample_rounds;   // block-uniform
         int pk[KK];
 #pragma unroll
         for (int l = 0; l < KK; l++) pk[l] = __shfl_sync(0xffffffffu, my_pk, l);
@@ -635,40 +808,53 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
                 count_row(y);
             }
         }
-        for (int j = tid; j < slice_rows; j += SOLVER_THREADS) {
+        // shared-memory rows: the static prefix (full sweeps) or the active list (trust region)
+        const int smem_rows = tr_mode == 1 ? n_active : static_rows;
+        for (int j = tid; j < smem_rows; j += SOLVER_THREADS) {
             int y[KK];
 #pragma unroll
-            for (int l = 0; l < KK; l++) y[l] = slice[l * slice_rows + j];
+            for (int l = 0; l < KK; l++) y[l] = slice[l * cap + j];
             count_row(y);
         }
+        if (tr_mode != 1 && !sampled) {
 #pragma unroll 2
-        for (int i = glob_begin + tid; i < N; i += SOLVER_THREADS) {
-            int y[KK];
+            for (int i = reg_rows + static_rows + tid; i < N; i += SOLVER_THREADS) {
+                int y[KK];
 #pragma unroll
-            for (int l = 0; l < KK; l++) y[l] = key_at(l, i);
-            count_row(y);
+                for (int l = 0; l < KK; l++) y[l] = key_at(l, i);
+                count_row(y);
+            }
         }
 #pragma unroll
         for (int w = 0; w < KK / 2; w++) {
             acc[w] += (unsigned)((h >> (8 * w)) & 0xF) | ((unsigned)((h >> (8 * w + 4)) & 0xF) << 16);
             acc[w] = __reduce_add_sync(0xffffffffu, acc[w]);           // N <= 65535: a 16-bit field cannot overflow
         }
-        if (lane == 0) {
+        // lane l adds the warp's count of class l to the round's counter (see price_search_reg)
+        if (lane < KK) {
+            unsigned a = acc[0];
 #pragma unroll
-            for (int w = 0; w < KK / 2; w++) sm.whist[it & 1][warp][w] = acc[w];
+            for (int w = 1; w < KK / 2; w++) a = (lane >> 1) == w ? acc[w] : a;
+            const int mine = (int)((a >> ((lane & 1) * 16)) & 0xFFFFu);
+            if (mine) atomicAdd(&sm.rcnt[rb][lane], mine);
         }
         __syncthreads();
-        int cnt = 0;
-        if (lane < KK) {
-#pragma unroll
-            for (int w = 0; w < SOLVER_WARPS; w++) cnt += (int)((sm.whist[it & 1][w][lane >> 1] >> ((lane & 1) * 16)) & 0xFFFFu);
+        int cnt = tr_mode == 1 ? my_frozen : 0;
+        if (lane < KK) cnt += sm.rcnt[rb][lane];
+        { const int rz = rb == 0 ? 2 : rb - 1; if (warp == 0 && lane < KP) sm.rcnt[rz][lane] = 0; }     // the buffer of round it + 2
+        rb = rb == 2 ? 0 : rb + 1;
+        int sg;
+        if (sampled) {
+            const float errf = (float)my_b * sample_share - (float)cnt;                      // against the scaled demand; half a row of slack
+            sg = errf > 0.5f ? 1 : (errf < -0.5f ? -1 : 0);
+        } else {
+            const int err = lane < KK ? my_b - cnt : 0;
+            const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
+            if (resid < best_resid) { best_resid = resid; my_best = price_of_key(my_pk); }      // the price the rows actually saw
+            if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
+            sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
         }
-        const int err = lane < KK ? my_b - cnt : 0;
-        const int resid = (int)(__reduce_add_sync(0xffffffffu, (unsigned)(err < 0 ? -err : err)) >> 1);
-        if (resid < best_resid) { best_resid = resid; my_best = price_of_key(my_pk); }      // the price the rows actually saw
-        if (resid == 0 || it == dual_iters) break;                     // same decision in every thread
         if (lane < KK) {
-            const int sg = err > 0 ? 1 : (err < 0 ? -1 : 0);
             if (sg * my_prev < 0) my_step *= 0.5f; else if (sg * my_prev > 0) my_step *= 1.2f;
             my_prev = sg;
             my_price += my_step * (float)sg;                           // too few rows -> cheaper class
@@ -676,6 +862,136 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
     }
     if (warp == 0 && lane < KP) sm.best_pricef[lane] = my_best;
     __syncthreads();
+}
+
+// Final assignment under the best prices + first scan of the class graph for the large modes (cost copy in global memory).
+// warp_rescan walks a class's member list and gathers that row's costs: every 4-byte gather pulls its own 32-byte sector
+// from L2, and with 100 CTAs doing the same the first scan of all classes took ~115-180 k cycles at N = 7720.  The same
+// minima come out of ONE coalesced sweep over the rows (lane = row, like the price search) plus a pass over a short list:
+//   sweep:  class s of the row (the assignment), then for every target l the difference d = M[i,l] - M[i,s] is compared with
+//           the running minimum smin[s][l]; a row within SCREEN_EPS of the minimum it reads updates it (atomicMin) and is a
+//           CANDIDATE: its costs are appended to a list in the shared memory the price search no longer needs.  The running
+//           minimum only decreases, so every row within SCREEN_EPS of the FINAL minimum is in the list (~N/6 rows: the
+//           first 512 and O(log) record-breakers per pair);
+//   list:   rows of the list within SCREEN_EPS of the final smin[s][l] are counted and the lowest of them kept.
+// A pair with exactly one such row has its fp64 winner (same rule as screen_resolve); the others (near-ties) go to the exact
+// member-list scan of warp_rescan, and so does everything when the list overflows.
+template <int KK>
+__device__ __forceinline__ void sweep_assign_scan(SolverSmem& sm, const SolverViews& v, const double* __restrict__ M, int N,
+                                                  float* __restrict__ cand, int cand_cap) {
+    constexpr int CW = KK + 1;                       // list entry: KK costs + the row index; odd stride = conflict-free
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < KP * (KP + 1); e += SOLVER_THREADS) {
+        (&sm.smin[0][0])[e] = 0xffffffffu; (&sm.scnt[0][0])[e] = 0; (&sm.sidx[0][0])[e] = 0x7fffffff;
+    }
+    if (tid < KP) sm.sexact[tid] = 0u;
+    if (tid == 0) { sm.n_active = 0; sm.tr_overflow = 0; }
+    __syncthreads();
+#ifdef FG_OT_PROFILE
+    long long tq[5]; tq[0] = clock64();
+#define FG_SWEEP_MARK(q) do { __syncthreads(); tq[q] = clock64(); } while (0)
+#else
+#define FG_SWEEP_MARK(q) do {} while (0)
+#endif
+    float pf[KK];
+#pragma unroll
+    for (int l = 0; l < KK; l++) pf[l] = sm.best_pricef[l];
+    for (int i0 = 0; i0 < N; i0 += SOLVER_THREADS) {           // uniform trip count: the body uses warp votes
+        const int i = i0 + tid;
+        const bool valid = i < N;
+        const int il = valid ? i : 0;
+        float xv[KK];
+#pragma unroll
+        for (int l = 0; l < KK; l++) xv[l] = __ldg(v.Mf + (size_t)l * N + il);
+        // fp32 screen: the prices are fp32 values, so |fp32 reduced cost - fp64 reduced cost| <= 2 ulp(M) ~ 5e-7;
+        // when the runner-up is further away than that the fp64 argmin is the fp32 argmin
+        float b1 = INFINITY, b2 = INFINITY; int s = 0;
+#pragma unroll
+        for (int l = 0; l < KK; l++) {
+            const float x = xv[l] - pf[l];
+            if (x < b1) { b2 = b1; b1 = x; s = l; } else if (x < b2) b2 = x;
+        }
+        if (valid && !(b2 - b1 > 8e-6f)) {
+            const double* row = M + (size_t)i * KK;
+            double bv = INFINITY; s = 0;
+            for (int l = 0; l < KK; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+        }
+        bool att = false;
+        if (valid) {
+            v.sigma[i] = (uint8_t)s;
+            const int slot = atomicAdd(&sm.cnt[s], 1);
+            v.members[(size_t)s * N + slot] = (uint16_t)i;
+            v.pos[i] = (uint16_t)slot;
+            float xs = xv[0];
+#pragma unroll
+            for (int l = 1; l < KK; l++) xs = l == s ? xv[l] : xs;
+#pragma unroll
+            for (int l = 0; l < KK; l++) {
+                // one flat predicate per target (a short-circuit `l != s && ...` made the compiler nest 16 divergent regions
+                // that never reconverged: 7x the instructions); 0xffffffff reads as NaN, so the first rows always enter
+                const float d = xv[l] - xs;
+                const float cur = funkey(sm.smin[s][l]);
+                const bool hit = (l != s) & !(d > cur + SCREEN_EPS);
+                att |= hit;
+                if (hit) atomicMin(&sm.smin[s][l], fkey(d));
+            }
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, att);
+        if (am) {                                     // warp-uniform
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sm.n_active, __popc(am));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (att) {
+                const int slot = base + __popc(am & ((1u << lane) - 1u));
+                if (slot < cand_cap) {
+#pragma unroll
+                    for (int l = 0; l < KK; l++) cand[slot * CW + l] = xv[l];
+                    cand[slot * CW + KK] = __int_as_float(i);
+                } else sm.tr_overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+    FG_SWEEP_MARK(1);
+    const bool overflow = sm.tr_overflow != 0;            // block-uniform
+    const int n_cand = overflow ? 0 : sm.n_active;
+    for (int j = tid; j < n_cand; j += SOLVER_THREADS) {
+        const float* e = cand + j * CW;
+        const int i = __float_as_int(e[KK]);
+        const int s = v.sigma[i];
+        const float xs = e[s];
+#pragma unroll
+        for (int l = 0; l < KK; l++) {
+            const float cur = funkey(sm.smin[s][l]);
+            const bool hit = (l != s) & (e[l] - xs <= cur + SCREEN_EPS);
+            if (hit) { atomicAdd(&sm.scnt[s][l], 1); atomicMin(&sm.sidx[s][l], i); }
+        }
+    }
+    __syncthreads();
+    FG_SWEEP_MARK(2);
+    if (tid < KP * KP) {
+        const int k = tid >> 4, l = tid & 15;
+        if (k < KK && l < KK && k != l) {
+            if (sm.cnt[k] == 0) { sm.w[k][l] = INFINITY; sm.wi[k][l] = -1; }
+            else if (!overflow && sm.scnt[k][l] == 1) {
+                const int i = sm.sidx[k][l];
+                sm.wi[k][l] = i;
+                sm.w[k][l] = __dsub_rn(M[(size_t)i * KK + l], M[(size_t)i * KK + k]);
+            } else atomicOr(&sm.sexact[k], 1u << l);
+        }
+    }
+    __syncthreads();
+    FG_SWEEP_MARK(3);
+    const int warp = tid >> 5;
+    for (int k = warp; k < KK; k += SOLVER_WARPS)
+        if (sm.sexact[k]) warp_rescan(sm, v, M, N, KK, k, sm.sexact[k], !overflow ? false : true);       // warp-uniform
+#ifdef FG_OT_PROFILE
+    FG_SWEEP_MARK(4);
+    if (tid == 0 && ((blockIdx.x % 50) == 0 || tq[4] - tq[0] > 120000)) {
+        int ne = 0; for (int k = 0; k < KK; k++) ne += __popc(sm.sexact[k]);
+        printf("sweepprof blk %d: sweep %lld list(%d rows) %lld resolve %lld exact(%d pairs) %lld cycles\n", blockIdx.x, tq[1] - tq[0], n_cand, tq[2] - tq[1], tq[3] - tq[2], ne, tq[4] - tq[3]);
+    }
+#endif
 }
 
 // One CTA solves one transport problem exactly.
@@ -705,7 +1021,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
                 Demand demand_by_value, const int* __restrict__ hist,
                 int32_t* __restrict__ assign_out, int32_t* __restrict__ counts,
                 int* __restrict__ status, int status_slot, int m_in_smem, uint16_t* __restrict__ members_global, int slice_rows,
-                const int* __restrict__ Mk_global) {
+                const int* __restrict__ Mk_global, int pivot_round) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     SolverSmem& sm = *reinterpret_cast<SolverSmem*>(dyn_smem);
     SolverViews v;
@@ -749,6 +1065,10 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
         sm.prev_sign[tid] = 0;
     }
     if (tid == 0) { sm.status = 0; sm.path_len = 0; sm.best_resid = 0x7fffffff; sm.stop = 0; }
+    if (tid < 3 * KP) (&sm.rcnt[0][0])[tid] = 0;
+#ifdef FG_OT_PROFILE
+    if (tid == 0) { sm.prof_pivots = 0; sm.prof_pivot_last = -1; sm.prof_rounds = 0; }
+#endif
     for (int e = tid; e < KP * KP; e += SOLVER_THREADS) { sm.w[e / KP][e % KP] = INFINITY; sm.wi[e / KP][e % KP] = -1; }
     __syncthreads();
     if (tid == 0) {
@@ -768,46 +1088,58 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
     } else if (MODE != 0 && m_in_smem && Mk_global) {
         // the shared memory behind the last view holds a slice of the cost copy during the search
         int* slice = reinterpret_cast<int*>(dyn_smem + (MODE == 1 ? solver_off_M(N, K) : solver_off_members(N)));
-        if (K == 16) price_search_hybrid<16>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0);
-        else price_search_hybrid<8>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0);
+        if (K == 16) price_search_hybrid<16>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0, pivot_round);
+        else price_search_hybrid<8>(sm, Mk_global, slice, slice_rows, N, dual_iters, (float)step0, pivot_round);
     } else if (K == 16) price_search<16>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     else price_search<8>(sm, v.Mf, M_global, N, dual_iters, (float)step0, m_in_smem != 0);
     if (tid < KP) sm.price[tid] = (double)sm.best_pricef[tid];
     __syncthreads();
     FG_MARK();
     // final assignment under the best prices + member lists (list order is arbitrary; no result depends on it)
-    for (int i = tid; i < N; i += SOLVER_THREADS) {
-        int s = 0;
-        bool exact = true;
-        if (m_in_smem) {
-            // fp32 screen: the prices are fp32 values, so |fp32 reduced cost - fp64 reduced cost| <= 2 ulp(M) ~ 5e-7;
-            // when the runner-up is further away than that the fp64 argmin is the fp32 argmin
-            float b1 = INFINITY, b2 = INFINITY;
-            for (int l = 0; l < K; l++) {
-                const float x = v.Mf[l * N + i] - sm.best_pricef[l];
-                if (x < b1) { b2 = b1; b1 = x; s = l; } else if (x < b2) b2 = x;
+    const bool coalesced_scan = MODE != 0 && m_in_smem && !(sm.status & ST_BAD_DEMAND);       // block-uniform
+    if (coalesced_scan) {
+        // candidate list: the shared memory behind the last view, which held the slice of the cost copy during the search
+        float* cand = reinterpret_cast<float*>(dyn_smem + (MODE == 1 ? solver_off_M(N, K) : solver_off_members(N)));
+        const int cand_cap = (slice_rows * K) / (K + 1);
+        if (K == 16) sweep_assign_scan<16>(sm, v, M, N, cand, cand_cap); else sweep_assign_scan<8>(sm, v, M, N, cand, cand_cap);
+    } else {
+        for (int i = tid; i < N; i += SOLVER_THREADS) {
+            int s = 0;
+            bool exact = true;
+            if (m_in_smem) {
+                // fp32 screen: the prices are fp32 values, so |fp32 reduced cost - fp64 reduced cost| <= 2 ulp(M) ~ 5e-7;
+                // when the runner-up is further away than that the fp64 argmin is the fp32 argmin
+                float b1 = INFINITY, b2 = INFINITY;
+                for (int l = 0; l < K; l++) {
+                    const float x = v.Mf[l * N + i] - sm.best_pricef[l];
+                    if (x < b1) { b2 = b1; b1 = x; s = l; } else if (x < b2) b2 = x;
+                }
+                exact = !(b2 - b1 > 8e-6f);
             }
-            exact = !(b2 - b1 > 8e-6f);
+            if (exact) {
+                const double* row = M + (size_t)i * K;
+                double bv = INFINITY; s = 0;
+                for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
+            }
+            sigma[i] = (uint8_t)s;
+            const int slot = atomicAdd(&sm.cnt[s], 1);
+            v.members[(size_t)s * N + slot] = (uint16_t)i;
+            v.pos[i] = (uint16_t)slot;
         }
-        if (exact) {
-            const double* row = M + (size_t)i * K;
-            double bv = INFINITY; s = 0;
-            for (int l = 0; l < K; l++) { const double x = __dsub_rn(row[l], sm.price[l]); if (x < bv) { bv = x; s = l; } }
-        }
-        sigma[i] = (uint8_t)s;
-        const int slot = atomicAdd(&sm.cnt[s], 1);
-        v.members[(size_t)s * N + slot] = (uint16_t)i;
-        v.pos[i] = (uint16_t)slot;
     }
     __syncthreads();
     FG_MARK();
     const unsigned all_mask = (1u << K) - 1u;
     int iters = 0;
     if (!(sm.status & ST_BAD_DEMAND)) {
-        for (int k = warp; k < K; k += SOLVER_WARPS) warp_rescan(sm, v, M, N, K, k, all_mask, m_in_smem != 0);
+        if (!coalesced_scan)
+            for (int k = warp; k < K; k += SOLVER_WARPS) warp_rescan(sm, v, M, N, K, k, all_mask, m_in_smem != 0);
         __syncthreads();
         FG_MARK();
         const int max_iters = N + KP;
+        // One repair step = shortest path + row moves (warp 0), barrier, re-scan of the classes that lost a row (ONE WARP PER
+        // PATH CLASS, in parallel: the scans are independent and each is a chain of L2 round trips in the large modes),
+        // barrier, fold of the arrivals (warp 0).
         for (;; iters++) {
             if (warp == 0) {
                 const int lane = tid;
@@ -835,27 +1167,31 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
                             sm.cnt[to] = q + 1;
                             sigma[item] = (uint8_t)to;
                         }
+                        if (MODE == 2) __threadfence_block();      // the member lists live in global memory: publish them to the CTA
                     }
-                    __syncwarp();
-                    for (int e = 0; e + 1 < len; e++) warp_rescan(sm, v, M, N, K, sm.path[e], sm.need[e], m_in_smem != 0);
-                    // rows that arrived in path[e+1]: fold their outgoing differences into the minima
-                    if (lane < K) {
-                        const int l = lane;
-                        for (int e = 0; e + 1 < len; e++) {
-                            const int to = sm.path[e + 1], item = sm.moved[e];
-                            if (l == to) continue;
-                            const double* row = M + (size_t)item * K;
-                            const double d = __dsub_rn(row[l], row[to]);
-                            const double cur = sm.w[to][l];
-                            if (sm.wi[to][l] < 0 || d < cur || (d == cur && item < sm.wi[to][l])) { sm.w[to][l] = d; sm.wi[to][l] = item; }
-                        }
-                    }
-                    __syncwarp();
                 }
-                if (lane == 0) sm.cont[iters & 1] = len > 0 ? 1 : 0;
             }
             __syncthreads();
-            if (sm.cont[iters & 1] == 0) break;
+            const int len = sm.path_len;                   // block-uniform
+            if (len == 0) break;
+            if (warp < len - 1) warp_rescan(sm, v, M, N, K, sm.path[warp], sm.need[warp], m_in_smem != 0);     // len - 1 <= K - 1 < SOLVER_WARPS
+            __syncthreads();
+            if (warp == 0) {
+                const int lane = tid;
+                // rows that arrived in path[e+1]: fold their outgoing differences into the minima
+                if (lane < K) {
+                    const int l = lane;
+                    for (int e = 0; e + 1 < len; e++) {
+                        const int to = sm.path[e + 1], item = sm.moved[e];
+                        if (l == to) continue;
+                        const double* row = M + (size_t)item * K;
+                        const double d = __dsub_rn(row[l], row[to]);
+                        const double cur = sm.w[to][l];
+                        if (sm.wi[to][l] < 0 || d < cur || (d == cur && item < sm.wi[to][l])) { sm.w[to][l] = d; sm.wi[to][l] = item; }
+                    }
+                }
+                __syncwarp();
+            }
         }
         if (tid == 0 && status) atomicAdd(&status[status_slot], iters);
     }
@@ -888,7 +1224,7 @@ ot_solve_kernel(const double* __restrict__ M_global, const float* __restrict__ M
 #ifdef FG_OT_PROFILE
     FG_MARK();
     if (tid == 0)
-        printf("otprof blk %d N %d K %d grid %d: copy %lld search %lld assign %lld rescan %lld ssp(%d) %lld out %lld total %lld cycles\n", blockIdx.x, N, K, gridDim.x,
+        printf("otprof blk %d N %d K %d grid %d pivots %d (last at %d) active %d: copy %lld search %lld assign %lld rescan %lld ssp(%d) %lld out %lld total %lld cycles\n", blockIdx.x, N, K, gridDim.x, sm.prof_pivots, sm.prof_pivot_last, sm.prof_rounds,
                tprof[1] - tprof[0], tprof[2] - tprof[1], tprof[3] - tprof[2], tprof[4] - tprof[3], iters, tprof[5] - tprof[4], tprof[6] - tprof[5], tprof[6] - tprof[0]);
 #endif
 }
@@ -1101,14 +1437,20 @@ __global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict
     if (e < N * K) { const int i = e / K, l = e - i * K; const float c = (float)M[e]; Mf[(size_t)l * N + i] = c; Mk[(size_t)l * N + i] = cost_key(c, l); }
 }
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
+// round of the price search at which the trust region starts (price_search_hybrid); a tuning knob, results do not depend on it
+#define SEARCH_PIVOT_ROUND (env_int("FG_OT_PIVOT", 12) | (env_int("FG_OT_TRUST", 6) << 8) | (env_int("FG_OT_SAMPLE", 6) << 16))
+
 #define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, MK_, ...)                                                                     \
     do {                                                                                                              \
         const int mode_ = solver_mode(N_, K_);                                                                        \
         const int smem_ = solver_smem_bytes(N_, K_);                                                                  \
         const int slice_ = solver_slice_rows(N_, K_);                                                                 \
-        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);           \
-        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);      \
-        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_);                      \
+        const int pivot_ = SEARCH_PIVOT_ROUND;                                                                        \
+        if (mode_ == 0) ot_solve_kernel<0><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_, pivot_);   \
+        else if (mode_ == 1) ot_solve_kernel<1><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_, pivot_); \
+        else ot_solve_kernel<2><<<GRID_, SOLVER_THREADS, smem_, ST_>>>(__VA_ARGS__, slice_, MK_, pivot_);              \
     } while (0)
 
 // expected demand for n rows: largest-remainder rounding of n*q
@@ -1126,8 +1468,6 @@ static void expected_demand(int n, int K, Demand* d) {
 }
 
 // price-search schedule (rounds, first step) of a solve that starts from zero prices, i.e. from the greedy assignment
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
 // defaults; the FG_OT_* environment variables exist for tuning runs only (results do not depend on them)
 #define BASE_DUAL_ITERS env_int("FG_OT_BASE_ITERS", 40)
 #define BASE_STEP0 env_dbl("FG_OT_BASE_STEP", 0.03)

@@ -25,10 +25,16 @@
 //   ~115 px, or more than 4 taps per pixel) take the direct 2-D gather per pixel (correct, slow, rare).
 #pragma once
 
-constexpr int GS_ROWS = 8;        // image rows per sub-tile
-constexpr int GS_SROWS = 6;       // resized rows a sub-tile can touch (<= 5 at 512 -> 224)
-constexpr int GS_SZERO = 3;       // zero rows after them (rows 6, 7, 8 of every bufS channel)
-constexpr int GS_CROWS = 16;      // chip rows staged per sub-tile
+#ifndef FG_GS_ROWS
+#define FG_GS_ROWS 8
+#define FG_GS_SROWS 6
+#define FG_GS_CROWS 16
+#define FG_GS_MINB 3
+#endif
+constexpr int GS_ROWS = FG_GS_ROWS;     // image rows per sub-tile
+constexpr int GS_SROWS = FG_GS_SROWS;   // resized rows a sub-tile can touch (<= 5 per 8 image rows at 512 -> 224, <= 3 per 4)
+constexpr int GS_SZERO = 3;             // zero rows after them (rows GS_SROWS .. GS_SROWS + 2 of every bufS channel)
+constexpr int GS_CROWS = FG_GS_CROWS;   // chip rows staged per sub-tile
 constexpr int GS_OW = 224;        // width (and height) of both gradient grids
 constexpr int GS_TBW = GS_OW + TPAD;
 constexpr int GS_S_CH = (GS_SROWS + GS_SZERO) * GS_OW * 2;   // bufS channel stride, bytes
@@ -161,7 +167,7 @@ __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_
 }
 
 template <typename T, int NSUB>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, FG_GS_MINB)
 image_grad_staged_kernel(const BwdParams p) {
     static_assert(sizeof(T) == 2, "16-bit gradients only");
     using L = GsLayout<NSUB>;

@@ -294,8 +294,8 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
                             float fill_value, int dtype, cudaStream_t st) {
     const size_t esz = dtype == FG_F32 ? 4 : 2;
     const size_t row_bytes = (size_t)W * esz;
-    const int stages = dtype == FG_F32 ? 2 : 3;
-    const int rmax = dtype == FG_F32 ? 2 * TOH : 12;             // ring rows per channel (RMAX in the kernel)
+    const int stages = dtype == FG_F32 ? 2 : FG_FWD_STAGES16;
+    const int rmax = dtype == FG_F32 ? 2 * TOH : FG_FWD_RMAX16;             // ring rows per channel (RMAX in the kernel)
     const size_t meta = ((size_t)stages * sizeof(FwdMeta) + 127) / 128 * 128;
     const size_t smem = 128 + meta + (size_t)stages * rmax * 3 * row_bytes;
     FwdParams p;
@@ -310,11 +310,15 @@ static int launch_fwd_tiled(const void* images, int n, int C, int H, int W, cons
     p.fill = fill_value; p.total_tiles = (int)total;
     static const bool fwd_pair = getenv("FG_FWD_PAIR") != nullptr;      // tuning A/B switch, read once
     p.pair_mode = fwd_pair ? 1 : 2;                    // 1: two columns per thread everywhere
-    const unsigned grid = (unsigned)(total < 2LL * FG_NUM_SMS ? total : 2LL * FG_NUM_SMS);   // persistent, 2 CTAs per SM
+    #ifndef FG_FWD_CTAS_PER_SM
+#define FG_FWD_CTAS_PER_SM 4
+#endif
+    const long long resident = (long long)(dtype == FG_F32 ? 2 : FG_FWD_CTAS_PER_SM) * FG_NUM_SMS;     // persistent CTAs
+    const unsigned grid = (unsigned)(total < resident ? total : resident);
     switch (dtype) {
         case FG_F32: return launch_fwd_tiled_t<float, 2>(p, smem, grid, st);
-        case FG_BF16: return launch_fwd_tiled_t<__nv_bfloat16, 3>(p, smem, grid, st);
-        case FG_F16: return launch_fwd_tiled_t<__half, 3>(p, smem, grid, st);
+        case FG_BF16: return launch_fwd_tiled_t<__nv_bfloat16, FG_FWD_STAGES16>(p, smem, grid, st);
+        case FG_F16: return launch_fwd_tiled_t<__half, FG_FWD_STAGES16>(p, smem, grid, st);
         default: return FG_ERR_DTYPE;
     }
 }
@@ -357,22 +361,16 @@ static int launch_bwd_tiled_t(const BwdParams& p, int owp, size_t smem, dim3 gri
                 return FG_OK;
             }
           if constexpr (sizeof(T) == 2) {
-            if (nsub == 16) {
-                using L = GsLayout<16>;
-                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
-                if (e != cudaSuccess) return (int)e;
-                image_grad_staged_kernel<T, 16><<<dim3(512 / (16 * GS_ROWS), p.n), 256, L::total, st>>>(p);
-            } else if (nsub == 8) {
-                using L = GsLayout<8>;
-                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
-                if (e != cudaSuccess) return (int)e;
-                image_grad_staged_kernel<T, 8><<<dim3(512 / (8 * GS_ROWS), p.n), 256, L::total, st>>>(p);
-            } else {
-                using L = GsLayout<4>;
-                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total);
-                if (e != cudaSuccess) return (int)e;
-                image_grad_staged_kernel<T, 4><<<dim3(512 / (4 * GS_ROWS), p.n), 256, L::total, st>>>(p);
-            }
+            constexpr int F = 8 / GS_ROWS;          // sub-tiles of GS_ROWS rows: the CTA keeps its 128 / 64 / 32 image rows
+#define FG_LAUNCH_STAGED(NS)                                                                                                        \
+            do {                                                                                                                    \
+                using L = GsLayout<NS>;                                                                                             \
+                e = cudaFuncSetAttribute(image_grad_staged_kernel<T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total); \
+                if (e != cudaSuccess) return (int)e;                                                                                \
+                image_grad_staged_kernel<T, NS><<<dim3(512 / (NS * GS_ROWS), p.n), 256, L::total, st>>>(p);                         \
+            } while (0)
+            if (nsub == 16) FG_LAUNCH_STAGED(16 * F); else if (nsub == 8) FG_LAUNCH_STAGED(8 * F); else FG_LAUNCH_STAGED(4 * F);
+#undef FG_LAUNCH_STAGED
             FG_LAUNCH_CHECK();
             return FG_OK;
           }

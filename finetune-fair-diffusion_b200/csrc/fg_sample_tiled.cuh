@@ -27,6 +27,14 @@
 #pragma once
 
 constexpr int TOH = 4;                      // output rows per forward tile
+#ifndef FG_FWD_RMAX16
+#define FG_FWD_RMAX16 9                     // ring rows per channel and stage of the 16-bit forward (>= 9: the 512 -> 224 resize spans 8-9 rows)
+#endif
+#ifndef FG_FWD_STAGES16
+#define FG_FWD_STAGES16 2                   // ring depth of the 16-bit forward: 2 x 27 KB per CTA leaves room for FOUR resident CTAs per SM
+                                            // (measured on B200, 1024 bf16 images: 3 stages x 12 rows x 2 CTAs 0.472 ms, 2 x 12 x 3 CTAs 0.454 ms,
+                                            //  2 x 9 x 4 CTAs 0.432 ms -- the kernel is latency / issue bound, so resident warps beat ring depth)
+#endif
 constexpr int FWD_CONSUMER_WARPS = 7;       // 224 threads = one 224-wide output row per pass
 constexpr int FWD_CONSUMERS = FWD_CONSUMER_WARPS * 32;
 constexpr int FWD_THREADS = FWD_CONSUMERS + 32;
@@ -114,7 +122,7 @@ sample_fwd_tiled_kernel(const FwdParams p) {
     // contiguous in the image, so ONE bulk copy per channel brings rows [first, last] at full width (3 copies per tile
     // instead of 24 -- the copy engine, not HBM, was the limit with one copy per row).  Tiles whose row span exceeds
     // RMAX (boxes taller than ~2.5x the chip) and fp32 tiles (rows are already 2 KB) use one copy per needed row.
-    constexpr int RMAX = sizeof(T) == 2 ? 12 : 2 * TOH;
+    constexpr int RMAX = sizeof(T) == 2 ? FG_FWD_RMAX16 : 2 * TOH;
     const int W = p.W;
     const int stage_elems = C * RMAX * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,8 +144,11 @@ sample_fwd_tiled_kernel(const FwdParams p) {
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k++) {
             const int s = k % STAGES;
             const uint32_t ph = (uint32_t)((k / STAGES) & 1);
+#ifdef FG_FWD_EARLY_WAIT
             if (k >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
-            // decode (all lanes, uniform)
+#endif
+            // decode (all lanes, uniform).  The wait for the ring slot comes AFTER the decode: the box load (a global-memory
+            // round trip) and the tap arithmetic of tile k overlap the consumers' work on tile k - STAGES.
             const int img = t / per_image;
             const int rt = t - img * per_image;
             const bool is_small = rt < p.tiles_small;
@@ -181,6 +192,9 @@ sample_fwd_tiled_kernel(const FwdParams p) {
                     }
                 }
             }
+#ifndef FG_FWD_EARLY_WAIT
+            if (k >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
+#endif
             // metadata: lanes 0..3 hold the row taps of rows 0..3
             FwdMeta& m = meta[s];
             if (lane < TOH) {
