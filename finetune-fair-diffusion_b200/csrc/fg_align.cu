@@ -23,6 +23,7 @@
 // down-scale), so the image gradient is written once, without atomics, deterministic; it either overwrites the whole
 // image gradient (zeros outside the box) or accumulates into the one fg_image_grad produced.
 #include "fg_common.cuh"
+#include <cstdlib>
 #include <math.h>
 
 namespace {
@@ -198,6 +199,206 @@ aligned_warp_bwd_kernel(const T* __restrict__ g_out, const float* __restrict__ p
             }
         }
     }
+}
+
+// backward, second generation: CELL MAP.  The gather above tests a window of chip pixels per image pixel (4-9 candidates for
+// ~1.2 real taps: ~200 instructions per pixel, 1.36 ms for 1024 images).  When the chip grid is coarser than the image grid
+// (the usual case: a 112-pixel chip of a 150-300 pixel face), no two chip pixels fall into the same unit cell of the image,
+// so the map  cell (floor xs, floor ys) -> chip pixel  is injective and can be built without atomics or ordering:
+//   phase 1  every chip pixel whose source position falls into the tile's cells writes its (row, column) into the map
+//            (shared memory; entries carry the tile's tag, so the map is never cleared);
+//   phase 2  an image pixel (x, y) looks up the four cells (x - dx, y - dy): a hit is a chip pixel for which this pixel is
+//            tap (dx, dy), with the forward's own fp32 expressions for the weight -- fixed summation order, deterministic.
+// Tiles are 64 x 16 pixels (four rows per thread), the map is double-buffered: one block barrier per tile.  A second chip pixel
+// arriving in an occupied cell (up-sampled faces) flags the tile, whose pixels then take the candidate scan of the first
+// generation; images whose matrix cannot be injective skip phase 1 altogether.
+constexpr int AT_W = 64, AT_H = 16;
+constexpr int AM_W = AT_W + 1, AM_H = AT_H + 1, AM_STRIDE = AM_W + 1;
+
+// the first generation's per-pixel candidate scan (see aligned_warp_bwd_kernel)
+template <typename T>
+__device__ __forceinline__ void aligned_scan_pixel(const T* __restrict__ go, const float* __restrict__ P, int x, int y, int C, int Hd, int Wd, float* acc) {
+    const float d00 = P[6], d01 = P[7], d10 = P[8], d11 = P[9], d02 = P[10], d12 = P[11];
+    const float c00 = P[0], c01 = P[1], c02 = P[2], c10 = P[3], c11 = P[4], c12 = P[5];
+    const float hx = fabsf(d00) + fabsf(d01), hy = fabsf(d10) + fabsf(d11);
+    const float qx = fmaf(d00, (float)x, fmaf(d01, (float)y, d02));
+    const float qy = fmaf(d10, (float)x, fmaf(d11, (float)y, d12));
+    const int j0 = max((int)ceilf(qx - hx - 1e-3f), 0), j1 = min((int)floorf(qx + hx + 1e-3f), Wd - 1);
+    const int i0 = max((int)ceilf(qy - hy - 1e-3f), 0), i1 = min((int)floorf(qy + hy + 1e-3f), Hd - 1);
+    for (int i = i0; i <= i1; i++) {
+        const float ri = (float)i - qy;
+        const float ex = c01 * ri, ey = c11 * ri;
+        for (int j = j0; j <= j1; j++) {
+            const float rj = (float)j - qx;
+            const float dxs = fmaf(c00, rj, ex), dys = fmaf(c10, rj, ey);
+            if (fabsf(dxs) > 1.02f || fabsf(dys) > 1.02f) continue;
+            const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
+            const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
+            const float fx0 = floorf(xs), fy0 = floorf(ys);
+            const int tx = x - (int)fx0, ty = y - (int)fy0;
+            if ((unsigned)tx > 1u || (unsigned)ty > 1u) continue;
+            const float wx1 = xs - fx0, wy1 = ys - fy0;
+            const float w = (tx ? wx1 : 1.f - wx1) * (ty ? wy1 : 1.f - wy1);
+            for (int c = 0; c < C && c < 4; c++) acc[c] = fmaf(w, to_f32(__ldg(go + (size_t)c * Hd * Wd + (size_t)i * Wd + j)), acc[c]);
+        }
+    }
+}
+
+constexpr int AM_CELLS = AM_H * AM_STRIDE;                  // words per map plane
+constexpr int AM_PLANES = 6;                                // tag | wx1 | wy1 | three channel values
+constexpr size_t AM_SMEM = (size_t)2 * AM_PLANES * AM_CELLS * sizeof(int);
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+aligned_warp_bwd_cell_kernel(const T* __restrict__ g_out, const float* __restrict__ params, const uint8_t* __restrict__ indicators,
+                             int n, int C, int Hs, int Ws, int Hd, int Wd, int accumulate, T* __restrict__ g_images) {
+    // per buffer: the cell map (tagged chip pixel) and, next to it, what that chip pixel contributes: its two fractional
+    // weights and its three gradient values (fp32) -- written once by the chip pixel in phase 1, so that an image pixel's
+    // phase 2 is shared-memory reads only
+    extern __shared__ __align__(16) int am_smem[];
+    __shared__ int conflict[2];
+    const int tid = threadIdx.x, tx = tid & (AT_W - 1), ty = tid >> 6;        // 64 columns x 4 row groups
+    for (int e = tid; e < 2 * AM_PLANES * AM_CELLS; e += 256) am_smem[e] = 0;     // tag 0 = never valid; stale values stay finite
+    if (tid < 2) conflict[tid] = 0;
+    __syncthreads();
+    const size_t gplane = (size_t)Hd * Wd, iplane = (size_t)Hs * Ws;
+    int it = 0;                                                                // tiles this CTA has processed (tag source)
+    // persistent over the images: the shared-memory set-up above is paid once per CTA, not once per (image, slice)
+    for (int img = blockIdx.y; img < n; img += gridDim.y) {
+    const float* P = params + (size_t)img * ALIGN_PARAMS;
+    const bool face = !indicators || indicators[img];
+    const int bx0 = (int)P[12], by0 = (int)P[13], bx1 = (int)P[14], by1 = (int)P[15];
+    const bool has_taps = face && bx1 >= bx0 && by1 >= by0;
+    if (accumulate && !has_taps) continue;
+    const int X0 = accumulate ? (bx0 & ~(AT_W - 1)) : 0, Y0 = accumulate ? (by0 & ~(AT_H - 1)) : 0;
+    const int X1 = accumulate ? bx1 : Ws - 1, Y1 = accumulate ? by1 : Hs - 1;
+    const int tiles_x = (X1 - X0) / AT_W + 1, tiles_y = (Y1 - Y0) / AT_H + 1;
+    const float c00 = P[0], c01 = P[1], c02 = P[2], c10 = P[3], c11 = P[4], c12 = P[5];
+    const float d00 = P[6], d01 = P[7], d10 = P[8], d11 = P[9], d02 = P[10], d12 = P[11];
+    // injective cell map <=> every non-zero integer step of the chip grid moves the source position by >= 1 in x or y;
+    // the four shortest steps decide (longer ones move further)
+    bool unique = has_taps && C == 3;
+    {
+        const float sj[4] = {1.f, 0.f, 1.f, 1.f}, si[4] = {0.f, 1.f, 1.f, -1.f};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            unique = unique && fmaxf(fabsf(c00 * sj[q] + c01 * si[q]), fabsf(c10 * sj[q] + c11 * si[q])) >= 1.002f;
+    }
+    const T* go = g_out + (size_t)img * C * Hd * Wd;
+    const unsigned inv_tiles_x = 0xFFFFFFFFu / (unsigned)tiles_x + 1u;       // exact quotient by __umulhi for tile < 2^16
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x, it++) {
+        const int b = it & 1;
+        const int tag = it + 1;                                  // < 2^17: at most a few hundred tiles per CTA
+        int* map = am_smem + b * AM_PLANES * AM_CELLS;
+        float* fw = reinterpret_cast<float*>(map + AM_CELLS);   // [2][AM_CELLS] wx1, wy1; then [3][AM_CELLS] values
+        const int tyi = (int)__umulhi((unsigned)tile, inv_tiles_x), txi = tile - tyi * tiles_x;     // tile / tiles_x without the divide
+        const int X = X0 + txi * AT_W, Y = Y0 + tyi * AT_H;
+        const bool touches = has_taps && X <= bx1 && X + AT_W > bx0 && Y <= by1 && Y + AT_H > by0;      // block-uniform
+        const bool mapped = touches && unique;
+        if (mapped) {
+            // phase 1: chip pixels with xs in [X-1, X+AT_W), ys in [Y-1, Y+AT_H): bounding box of that rectangle in chip space
+            float jlo = INFINITY, jhi = -INFINITY, ilo = INFINITY, ihi = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float px = (q & 1) ? (float)(X + AT_W) : (float)(X - 1), py = (q & 2) ? (float)(Y + AT_H) : (float)(Y - 1);
+                const float qj = fmaf(d00, px, fmaf(d01, py, d02)), qi = fmaf(d10, px, fmaf(d11, py, d12));
+                jlo = fminf(jlo, qj); jhi = fmaxf(jhi, qj); ilo = fminf(ilo, qi); ihi = fmaxf(ihi, qi);
+            }
+            const int j0 = max((int)floorf(jlo) - 1, 0), j1 = min((int)ceilf(jhi) + 1, Wd - 1);
+            const int i0 = max((int)floorf(ilo) - 1, 0), i1 = min((int)ceilf(ihi) + 1, Hd - 1);
+            const int jw = j1 - j0 + 1, cand = jw > 0 && i1 >= i0 ? jw * (i1 - i0 + 1) : 0;
+            const unsigned inv_jw = 0xFFFFFFFFu / (unsigned)(jw > 0 ? jw : 1) + 1u;
+#pragma unroll 2
+            for (int e = tid; e < cand; e += 256) {
+                const int ei = (int)__umulhi((unsigned)e, inv_jw);
+                const int i = i0 + ei, j = j0 + e - ei * jw;
+                const float xs = fmaf(c00, (float)j, fmaf(c01, (float)i, c02));
+                const float ys = fmaf(c10, (float)j, fmaf(c11, (float)i, c12));
+                const float fx0 = floorf(xs), fy0 = floorf(ys);
+                const int cx = (int)fx0 - (X - 1), cy = (int)fy0 - (Y - 1);
+                if (fabsf(xs) < 1e8f && fabsf(ys) < 1e8f && (unsigned)cx < (unsigned)AM_W && (unsigned)cy < (unsigned)AM_H) {
+                    const int cell = cy * AM_STRIDE + cx;
+                    const T* gp = go + (size_t)i * Wd + j;
+                    const float v0 = to_f32(__ldg(gp)), v1 = to_f32(__ldg(gp + gplane)), v2 = to_f32(__ldg(gp + 2 * gplane));
+                    const int old = atomicExch(&map[cell], tag);
+                    if (old == tag) conflict[b] = tag;                         // a second chip pixel in this cell
+                    fw[cell] = xs - fx0; fw[AM_CELLS + cell] = ys - fy0;
+                    fw[2 * AM_CELLS + cell] = v0; fw[3 * AM_CELLS + cell] = v1; fw[4 * AM_CELLS + cell] = v2;
+                }
+            }
+        }
+        __syncthreads();
+        const bool use_map = mapped && conflict[b] != tag;
+        const int x = X + tx;
+        constexpr int RPT = AT_H / 4;                        // rows per thread
+        T* gbase = g_images + (size_t)img * C * iplane + x;
+        if (use_map) {
+            // Branch-free phase 2: the read-modify-write operands of the four rows are requested first, every cell is a few
+            // shared-memory reads, a miss contributes with weight zero.
+            bool ok[RPT], any[RPT]; T praw[RPT][3]; float acc[RPT][3]; bool mv[RPT][4];
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const int y = Y + ty + 4 * r;
+                ok[r] = x < Ws && y < Hs && x >= bx0 && x <= bx1 && y >= by0 && y <= by1;
+                bool hit = false;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    mv[r][q] = ok[r] && map[(ty + 4 * r + 1 - (q >> 1)) * AM_STRIDE + tx + 1 - (q & 1)] == tag;
+                    hit = hit || mv[r][q];
+                }
+                any[r] = hit;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { acc[r][c] = 0.f; praw[r][c] = from_f32<T>(0.f); }
+                if (accumulate && any[r]) {                       // raw bits only: the conversion (first use) waits until after the cells
+#pragma unroll
+                    for (int c = 0; c < 3; c++) praw[r][c] = gbase[(size_t)c * iplane + (size_t)y * Ws];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int dx = q & 1, dy = q >> 1;
+                    const int cell = (ty + 4 * r + 1 - dy) * AM_STRIDE + tx + 1 - dx;
+                    const float wx1 = fw[cell], wy1 = fw[AM_CELLS + cell];
+                    const float w = mv[r][q] ? (dx ? wx1 : 1.f - wx1) * (dy ? wy1 : 1.f - wy1) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[r][c] = fmaf(w, fw[(2 + c) * AM_CELLS + cell], acc[r][c]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const int y = Y + ty + 4 * r;
+                if (x >= Ws || y >= Hs) continue;
+                T* g = gbase + (size_t)y * Ws;
+                if (accumulate) {
+                    if (any[r]) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) g[(size_t)c * iplane] = from_f32<T>(to_f32(praw[r][c]) + acc[r][c]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) g[(size_t)c * iplane] = from_f32<T>(acc[r][c]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < RPT; r++) {
+                const int y = Y + ty + 4 * r;
+                if (x >= Ws || y >= Hs) continue;
+                T* g = gbase + (size_t)y * Ws;
+                const bool inside = touches && x >= bx0 && x <= bx1 && y >= by0 && y <= by1;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (inside) aligned_scan_pixel<T>(go, P, x, y, C, Hd, Wd, acc);
+                if (accumulate) {
+                    if (inside) for (int c = 0; c < C && c < 4; c++) { T* gc = g + (size_t)c * iplane; *gc = from_f32<T>(to_f32(*gc) + acc[c]); }
+                } else {
+                    for (int c = 0; c < C && c < 4; c++) g[(size_t)c * iplane] = from_f32<T>(acc[c]);
+                }
+            }
+        }
+    }
+    }   // images
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -413,9 +614,26 @@ extern "C" int fg_aligned_warp_bwd(const void* g_out, int n, int C, int Hd, int 
     if (n == 0) return FG_OK;
     if (!g_out || !params || !g_images) return FG_ERR_INVALID_ARG;
     if (n > 65535) return FG_ERR_LIMIT;
-    const dim3 grid(AW_SLICES, n);
-    FG_DISPATCH_DTYPE(dtype, T,
-        aligned_warp_bwd_kernel<T><<<grid, 256, 0, fg_stream(stream)>>>((const T*)g_out, params, indicators, n, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
+    // cell-map kernel for chips up to 128 x 128 (7-bit row / column in a map entry); FG_AW_GEN1 / FG_AW_SLICES: A/B switches, read once
+    static const bool gen1 = getenv("FG_AW_GEN1") != nullptr;
+    static const int slices = getenv("FG_AW_SLICES") ? atoi(getenv("FG_AW_SLICES")) : 12;
+    if (!gen1 && Hd <= 128 && Wd <= 128) {
+        // `slices` CTAs share an image's tiles.  (A persistent grid looping over the images measured SLOWER, 0.82-0.93 ms vs
+        // 0.77 ms: faces differ 4x in area and the hardware scheduler balances (image, slice) CTAs better than a static
+        // round-robin; FG_AW_GROUPS caps the image groups for such experiments.)
+        const int sl = slices > 0 ? slices : 12;
+        static const int groups_env = getenv("FG_AW_GROUPS") ? atoi(getenv("FG_AW_GROUPS")) : 0;
+        int groups = groups_env > 0 && groups_env < n ? groups_env : n;
+        const dim3 grid(sl, groups);
+        FG_DISPATCH_DTYPE(dtype, T,
+            cudaError_t e = cudaFuncSetAttribute(aligned_warp_bwd_cell_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            aligned_warp_bwd_cell_kernel<T><<<grid, 256, AM_SMEM, fg_stream(stream)>>>((const T*)g_out, params, indicators, n, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
+    } else {
+        const dim3 grid(AW_SLICES, n);
+        FG_DISPATCH_DTYPE(dtype, T,
+            aligned_warp_bwd_kernel<T><<<grid, 256, 0, fg_stream(stream)>>>((const T*)g_out, params, indicators, n, C, Hs, Ws, Hd, Wd, accumulate, (T*)g_images));
+    }
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
