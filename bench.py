@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch of a step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"],
+                    help="N > 1: auto = one-shot NVLink stores between symmetric buffers (dist.PeerExchange) when the GPUs can map each "
+                         "other's memory, nccl = one NCCL call per exchange between three graph replays")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's image count per GPU (default); strong: that count in total, sharded")
     ap.add_argument("--profile-only", action="store_true",
@@ -343,7 +346,7 @@ def main():
     def measure(n_loc, steps, warmup, want_stages=True):
         """Device-resident timing of one configuration -> dict (ms_per_step = graph replay, eager stages, launches)."""
         batch = pipeline.synth_batch_device(n_loc, cfg, dtype, dev, seed=5991 + rank, max_faces=max_faces)
-        path = pipeline.GuidancePath(cfg, head)
+        path = pipeline.GuidancePath(cfg, head, peer_exchange=("auto" if a.exchange == "auto" else False))
         nv = global_faces(batch)
         res = {}
         captured, note = None, "off (--no-graph)"
@@ -568,6 +571,9 @@ def main():
             "clocks": clocks, "roofline": roofline, "fairness_only": fairness_only, "e2e": e2e, "closures": closures, "cpu_baseline": cpu}
     if surface:
         line["surface"] = surface
+    if world > 1:
+        line["exchange"] = ("peer: one-shot NVLink stores / loads between symmetric buffers with epoch flags (csrc/fg_peer.cu), the step is ONE CUDA graph"
+                            if path.peer else "nccl: all_gather_into_tensor + all_reduce between three graph replays")
     if multi_gpu_parity:
         line["multi_gpu_parity"] = multi_gpu_parity["status"]
         line["multi_gpu_parity_detail"] = multi_gpu_parity

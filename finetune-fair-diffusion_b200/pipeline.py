@@ -175,8 +175,32 @@ class _NullProbe:
 class GuidancePath:
     """Holds the frozen head and the configuration; ``step`` runs stages 1-10 on this rank's images."""
 
-    def __init__(self, cfg: GuidanceConfig, head_weights, backbone=None, group=None):
+    def __init__(self, cfg: GuidanceConfig, head_weights, backbone=None, group=None, peer_exchange="auto"):
+        """``peer_exchange``: "auto" = the one-shot NVLink transport (dist.PeerExchange) when several NCCL ranks can map each
+        other's memory, else one NCCL call per exchange; False = NCCL / gloo always."""
         self.cfg, self.head, self.backbone, self.group = cfg, head_weights, backbone, group
+        self.peer_mode, self.peer = peer_exchange, None
+
+    def _peer_for(self, packed, n_all, K):
+        """The PeerExchange for this batch shape: created collectively on the first multi-rank step; None = use NCCL (transport
+        switched off or unavailable, rows not a multiple of 16 bytes, or a batch larger than the one it was sized for)."""
+        if self.peer_mode in (False, "off") or self.peer is False:
+            return None
+        slot = packed.numel() * packed.element_size()
+        counts_bytes = ((n_all * K * 4 + 15) // 16) * 16
+        if self.peer is None:
+            if slot % 16 or not fdist.PeerExchange.available(packed.device):
+                return None
+            try:
+                self.peer = fdist.PeerExchange(slot, counts_bytes, packed.device, self.group)
+            except Exception as e:      # no peer mapping on this machine: say so once, stay on NCCL
+                import sys
+                print(f"fairguide: PeerExchange unavailable ({type(e).__name__}: {e}); the exchanges use NCCL", file=sys.stderr)
+                self.peer = False
+                return None
+        if self.peer.slot_bytes != slot or self.peer.counts_bytes < counts_bytes:
+            return None
+        return self.peer
 
     # The step is written as three local phases around the two exchanges of the path (DESIGN.md section 6), so that the
     # phases can be recorded into CUDA graphs while the collectives stay ordinary NCCL calls between them.
@@ -201,11 +225,18 @@ class GuidancePath:
         if world > 1:
             st["packed"] = fdist.pack_probs(ind, probs)
             st["gathered"] = torch.empty((world * n, st["packed"].shape[1]), dtype=st["packed"].dtype, device=images.device)
+            st["peer"] = self._peer_for(st["packed"], world * n, K) if images.is_cuda else None
+            if st["peer"] is not None:
+                # one-shot NVLink transport: the rows leave for every peer as soon as they exist
+                st["peer"].begin_step()
+                st["peer"].push_rows(st["packed"])
         return st
 
     def exchange_1(self, st):
         """Stage 5: the all-gather (no-op with one rank)."""
-        if "packed" in st:
+        if st.get("peer") is not None:
+            st["peer"].wait_rows(st["gathered"])
+        elif "packed" in st:
             fdist.all_gather_packed(st["gathered"], st["packed"], self.group)
 
     @torch.no_grad()
@@ -237,7 +268,10 @@ class GuidancePath:
     def exchange_2(self, st):
         """The all-reduce of the plan counts (E3:1535; no-op with one rank or for the E1 rule)."""
         if st.get("counts") is not None and st["nv"] > 0:
-            fdist.all_reduce_counts(st["counts"], self.group)
+            if st.get("peer") is not None and st["counts"].numel() * 4 <= st["peer"].counts_bytes:
+                st["peer"].sum_counts(st["counts"])
+            else:
+                fdist.all_reduce_counts(st["counts"], self.group)
 
     @torch.no_grad()
     def phase_c(self, st, batch, probe=None, close_assign=False):
@@ -275,7 +309,7 @@ class GuidancePath:
                     g_pooled=g_pooled, region=region, scale=scale, dyn_weights=dyn_w, loss=loss, loss_mean=loss.mean(),
                     g_images=g_images, bbox_ori=bbox_ori,
                     ot_status=st["ws"].status_tensor() if st.get("counts") is not None else None, num_valid=st.get("nv"),
-                    indicators_all=st["ind_all"], probs_all=probs_all)
+                    indicators_all=st["ind_all"], probs_all=probs_all, peer=st.get("peer"))
 
     @torch.no_grad()
     def step(self, batch, rand_tensors=None, num_valid: Optional[int] = None, probe=None):
@@ -295,6 +329,8 @@ def validate_step(out):
     that does not match the faces actually present (one 16-byte device-to-host read; synchronises)."""
     if out.get("ot_status") is not None:
         ops.check_ot_status(out["ot_status"].tolist(), out.get("num_valid"))
+    if out.get("peer"):
+        out["peer"].check()
 
 
 class CapturedStep:
@@ -322,7 +358,8 @@ class CapturedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
-        if world == 1:
+        if world == 1 or path.peer:
+            # one rank, or the exchanges are kernels of ours (dist.PeerExchange): the whole step is ONE graph
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.out = path.step(batch, rand_tensors=rand_tensors, num_valid=num_valid)

@@ -295,6 +295,31 @@ int fg_grad_bucket_pack(const uint64_t* grad_ptrs, const int64_t* offsets, int n
 int fg_grad_bucket_unpack(const uint64_t* grad_ptrs, const int64_t* offsets, int n_tensors, int64_t total,
                           const float* bucket, double divisor_a, double divisor_b, int dtype, void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU exchanges -
+ * The two exchanges of the path as one-shot NVLink transfers between peer-mapped ("symmetric") buffers, replacing
+ *   customized_all_gather (E1:222-235; call sites E3:1978-1986)   ->  fg_peer_push + fg_peer_wait_copy
+ *   dist.all_reduce(plan counts, SUM) (E3:1535, E4:1569)            ->  fg_peer_push(self_only) + fg_peer_wait_sum
+ * Every rank owns one allocation of the same layout; peer_base_dev is a DEVICE array of the `world` base addresses (rank
+ * order).  Offsets are bytes from a base: flags at flags_off ([2][64] uint32, flag_index 0 = rows, 1 = counts), a region at
+ * region_off + parity * parity_stride where parity = *epoch_dev & 1.  epoch_dev (uint32, device) is bumped once per step by
+ * fg_peer_epoch_advance; flags carry the epoch.  All sizes / offsets are multiples of 16 bytes.  Plain stream launches: no
+ * host synchronisation, capturable in a CUDA graph.  A wait that sees no flag within ~1 s ORs 0x100 into status[0]
+ * (int32, device; may be NULL) and returns control to the stream instead of hanging.
+ *   fg_peer_push       copies src[bytes] to slot_off inside the region of every peer (self_only = 0) or of this rank only
+ *                      (self_only = 1), then raises this rank's flag `flag_index` on every peer.  done_counter: one zeroed
+ *                      uint32 of device scratch, shared by consecutive pushes on a stream.
+ *   fg_peer_wait_copy  waits for the `world` flags, then copies bytes from this rank's region to dst.
+ *   fg_peer_wait_sum   waits for the `world` flags, then out[i] = sum over ranks (rank order) of the int32 slabs at the
+ *                      region of every peer (n_elems a multiple of 4). */
+int fg_peer_epoch_advance(uint32_t* epoch_dev, void* stream);
+int fg_peer_push(const void* src, size_t bytes, const void* peer_base_dev, size_t region_off, size_t parity_stride,
+                 size_t slot_off, int self_only, size_t flags_off, int flag_index, int rank, int world,
+                 const uint32_t* epoch_dev, uint32_t* done_counter, void* stream);
+int fg_peer_wait_copy(const void* peer_base_dev, int rank, int world, size_t flags_off, int flag_index, size_t region_off,
+                      size_t parity_stride, const uint32_t* epoch_dev, void* dst, size_t bytes, int32_t* status, void* stream);
+int fg_peer_wait_sum(const void* peer_base_dev, int rank, int world, size_t flags_off, int flag_index, size_t region_off,
+                     size_t parity_stride, const uint32_t* epoch_dev, int32_t* out, size_t n_elems, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

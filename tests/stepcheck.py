@@ -281,5 +281,19 @@ def check_multi_rank(kind, dtype, dev, rank, world, n_side_global=256, S=100, ca
         if o2["counts"] is not None:
             assert torch.equal(o2["counts"], out["counts"])
         assert torch.equal(o2["g_images"], out["g_images"]) and torch.equal(o2["loss"], out["loss"])
+        report["graphs_per_step"] = len(cap.graphs)
+    # which transport carried the two exchanges; when it was the one-shot NVLink one (dist.PeerExchange), the same step over
+    # NCCL must return the same integers
+    report["transport"] = "peer" if path.peer else "nccl"
+    if path.peer:
+        path.peer.check()
+        path_nccl = pipeline.GuidancePath(cfg, head, peer_exchange=False)
+        o3 = path_nccl.step(batch, rand_tensors=rands, num_valid=nv)
+        torch.cuda.synchronize()
+        for a in range(n_attr):
+            assert torch.equal(o3["targets_all"][a], out["targets_all"][a]), "PeerExchange and NCCL disagree on targets_all"
+            assert torch.equal(o3["probs_all"][a], out["probs_all"][a]), "PeerExchange and NCCL disagree on the gathered rows"
+        if o3["counts"] is not None:
+            assert torch.equal(o3["counts"], out["counts"]), "PeerExchange and NCCL disagree on the plan counts"
     dist.barrier()
     return report
