@@ -58,6 +58,8 @@ SIGNATURES = {
     "fg_feats_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "fg_face_search_workspace_bytes": (_z, [_i]),
     "fg_face_search_top1": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _z, _p]),
+    "fg_face_search_tc_workspace_bytes": (_z, [_i, _i]),
+    "fg_face_search_top1_tc": (_i, [_p, _p, _i, _p, _i, _i, _f, _p, _p, _p, _z, _p]),
     "fg_face_loss_workspace_bytes": (_z, [_i, _i]),
     "fg_face_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _f, _i, _f, _p, _p, _z, _i, _p]),
     "fg_face_loss_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _z, _i, _p]),
@@ -110,7 +112,7 @@ KERNELS_PER_CALL = {
     "fg_fair_ce_bwd": 1, "fg_fair_loss_fused": 1, "fg_assign_rank_binom": 2, "fg_ot_plan_counts": 3, "fg_ot_targets": 1,
     "fg_ot_solve_single": 2, "fg_ot_cost_matrix": 2, "fg_stage_detector_input": 1, "fg_bias_metrics": 1,
     "fg_assign_race_enumerated": 4, "fg_race_cost_matrix": 2, "fg_align_matrices": 1, "fg_aligned_warp_fwd": 1,
-    "fg_aligned_warp_bwd": 1, "fg_feats_normalize_fwd": 1, "fg_feats_normalize_bwd": 1, "fg_face_search_top1": 2,
+    "fg_aligned_warp_bwd": 1, "fg_feats_normalize_fwd": 1, "fg_feats_normalize_bwd": 1, "fg_face_search_top1": 2, "fg_face_search_top1_tc": 6,
     "fg_face_loss_fwd": 4, "fg_face_loss_bwd": 1, "fg_face_loss_target_rows": 0,
     "fg_grad_bucket_pack": 2, "fg_grad_bucket_unpack": 1,
     "fg_peer_epoch_advance": 1, "fg_peer_push": 1, "fg_peer_wait_copy": 1, "fg_peer_wait_sum": 1,

@@ -340,6 +340,8 @@ class FaceFeatsModel(torch.nn.Module):
         # normalised on the device by the same kernel as the queries (a host tensor is moved first; no CPU arithmetic here)
         feats = face_feats if face_feats.is_cuda else face_feats.cuda()
         self.face_feats = torch.nn.Parameter(ops.feats_normalize_fwd(feats)[0], requires_grad=False)
+        # rows are unit vectors up to fp32 rounding: the bound the tensor-core search scales its TF32 error margin with
+        self.db_norm_bound = 1.0 + 1e-5
 
     def forward(self, x):
         return None
@@ -347,7 +349,7 @@ class FaceFeatsModel(torch.nn.Module):
     @torch.no_grad()
     def semantic_search(self, query_embeddings, selector=None, return_similarity=False):
         q = query_embeddings
-        best, sim = ops.face_search_top1(q, selector, self.face_feats.data)
+        best, sim = ops.face_search_top1(q, selector, self.face_feats.data, db_norm_bound=self.db_norm_bound)
         hit = best >= 0
         target = torch.ones_like(q) * (-1)
         target[hit] = self.face_feats.data[best[hit]].to(q.dtype)

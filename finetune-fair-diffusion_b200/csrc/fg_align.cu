@@ -477,7 +477,9 @@ constexpr int SEARCH_Q = 32;      // queries per group
 constexpr int SEARCH_D = 512;     // feature width handled in registers (4 x float4 per lane)
 __global__ void __launch_bounds__(256)
 face_search_kernel(const float* __restrict__ queries, const uint8_t* __restrict__ selector, uint8_t want, int m,
-                   const float* __restrict__ db, int D, int d, unsigned long long* __restrict__ keys) {
+                   const float* __restrict__ db, int D, int d, unsigned long long* __restrict__ keys,
+                   const unsigned* __restrict__ only_if) {
+    if (only_if && *only_if == 0u) return;                             // fallback of the tensor-core search: runs only when flagged
     extern __shared__ __align__(16) float q_s[];                       // [SEARCH_Q][d]
     __shared__ unsigned long long best_s[SEARCH_Q];
     const int group = blockIdx.y, q0 = group * SEARCH_Q;
@@ -661,7 +663,7 @@ extern "C" int fg_feats_normalize_bwd(const float* g_f, const float* f, const fl
 }
 
 static int launch_search(const float* queries, const uint8_t* selector, uint8_t want, int m, const float* db, int D, int d,
-                         unsigned long long* keys, cudaStream_t st) {
+                         unsigned long long* keys, cudaStream_t st, const unsigned* only_if = nullptr) {
     const size_t smem = (size_t)(m < SEARCH_Q ? m : SEARCH_Q) * d * sizeof(float);      // few queries -> more CTAs per SM
     if (smem > 200 * 1024) return FG_ERR_LIMIT;
     cudaError_t e = cudaFuncSetAttribute(face_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -670,9 +672,15 @@ static int launch_search(const float* queries, const uint8_t* selector, uint8_t 
     int slabs = (D + 63) / 64;                                          // >= 64 database rows per CTA
     if (slabs > 4 * FG_NUM_SMS) slabs = 4 * FG_NUM_SMS;
     if (slabs < 1) slabs = 1;
-    face_search_kernel<<<dim3(slabs, groups), 256, smem, st>>>(queries, selector, want, m, db, D, d, keys);
+    face_search_kernel<<<dim3(slabs, groups), 256, smem, st>>>(queries, selector, want, m, db, D, d, keys, only_if);
     FG_LAUNCH_CHECK();
     return FG_OK;
+}
+
+// the exact streaming search as the overflow fallback of the tensor-core search (fg_head.cu): a no-op launch unless *only_if != 0
+int fg_internal_search_exact_if(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
+                                unsigned long long* keys, const unsigned* only_if, cudaStream_t st) {
+    return launch_search(queries, selector, 1, m, db, D, d, keys, st, only_if);
 }
 
 extern "C" size_t fg_face_search_workspace_bytes(int m) { return (size_t)(m > 0 ? m : 1) * sizeof(unsigned long long); }

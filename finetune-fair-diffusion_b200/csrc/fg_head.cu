@@ -490,3 +490,244 @@ extern "C" int fg_head_attributes_bwd(const void* probs, const void* const* g_pr
     FG_LAUNCH_CHECK();
     return FG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// f1: FaceFeatsModel.semantic_search (E1:96-117) for query BATCHES on the tensor cores.
+// top-1 of Q [m,d] against db [D,d] is a GEMM with an arg-max epilogue.  The streaming kernel of fg_align.cu is HBM-bound
+// for the reference's micro-batches of 3-4 rows and loses to cuBLAS from ~16 queries on (warp-shuffle bound).  Here:
+//   1. ONE TF32 pass on tcgen05 (M = 128 queries on the TMEM lanes, N = 128 database rows per CTA, K in 128-byte slabs
+//      through the same TMA / mbarrier ring as the head GEMM) gives approximate scores t = <q, row> +- eps, with
+//      eps <= 2^-9 |q| max|row| (the tensor core truncates both operands to 10 mantissa bits; db_norm_bound = max|row|);
+//   2. the epilogue -- thread = query, reading its 128 TMEM columns -- stores the approximate scores [D, m] (12-50 MB, a
+//      fraction of the database) and publishes the tile's maximum per query; a second small kernel then keeps every row
+//      with t >= (final best t of that query) - 2 eps: the exact arg-max, every row tied with it and whatever else the
+//      TF32 resolution cannot separate -- a handful of rows per query.  (Selecting inside the epilogue against the best t
+//      published SO FAR kept ~5 rows per query and tile, 100 k pairs: 782 tiles start at once and none has seen the others.)
+//   3. one warp per kept (query, row) recomputes the score with the streaming kernel's own fp32 expression and merges it
+//      with the same 64-bit atomicMax key: results are IDENTICAL to the exact search, database untouched, no copy of it.
+// A list that overflows flags the exact streaming search to run instead (a no-op launch otherwise).
+int fg_internal_search_exact_if(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
+                                unsigned long long* keys, const unsigned* only_if, cudaStream_t st);
+
+namespace {
+namespace tc {
+constexpr int SN = 128;                                   // database rows per tile
+constexpr int S_STAGE = (BM + SN) * 128;                  // one K slab of 32 floats for 128 query rows + 128 database rows
+constexpr int S_STAGES = 3;                               // 96 KB: two CTAs per SM, one's epilogue under the other's loads
+constexpr int S_TMEM_COLS = 128;
+
+struct SearchParams {
+    const uint8_t* selector; int m, D, K;
+    const float* qnorm; float eps_scale;                  // eps = eps_scale * qnorm[q]
+    unsigned* best_seen;                                  // [m] order-preserving key of the best approximate score
+    float* scores;                                        // [D, m] approximate scores (query-minor: coalesced both ways)
+};
+__device__ __forceinline__ unsigned skey(float f) { const unsigned b = __float_as_uint(f); return (b >> 31) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float sunkey(unsigned k) { return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k); }
+
+__global__ void __launch_bounds__(THREADS)
+face_search_tc_kernel(const SearchParams p, const __grid_constant__ TmaMap mapQ, const __grid_constant__ TmaMap mapD) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_STAGES * S_STAGE);
+    uint64_t* empty = full + S_STAGES;
+    uint64_t* done = empty + S_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const uint32_t ring = s32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * SN;
+    const int ksteps = p.K / 32;
+    auto fetch = [&](int ks, int slot) {
+        const uint32_t a_dst = ring + slot * S_STAGE;
+        bar_expect_tx(&full[slot], S_STAGE);
+        tma_load_2d(a_dst, &mapQ, ks * 32, m0, &full[slot]);
+        tma_load_2d(a_dst + BM * 128, &mapD, ks * 32, n0, &full[slot]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < S_STAGES; s++) { bar_init(&full[s], 1); bar_init(&empty[s], 1); }
+        bar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < S_STAGES && s < ksteps; s++) fetch(s, s);
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s32(tmem_slot)), "n"(S_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) {
+        // c_format F32 | a, b format TF32 | both K-major | N = 128 | M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int ks = 0; ks < ksteps; ks++) {
+            const int st = ks % S_STAGES;
+            bar_wait(&full[st], (uint32_t)((ks / S_STAGES) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = ring + st * S_STAGE, b0 = a0 + BM * 128;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) mma_tf32(tmem, smem_desc_sw128(a0 + kk * 32), smem_desc_sw128(b0 + kk * 32), idesc, (ks | kk) ? 1u : 0u);
+            mma_commit(&empty[st]);
+            if (ks == ksteps - 1) mma_commit(done);
+            const int prev = ks - 1, nxt = prev + S_STAGES;
+            if (prev >= 0 && nxt < ksteps) {
+                const int ps = prev % S_STAGES;
+                bar_wait(&empty[ps], (uint32_t)((prev / S_STAGES) & 1));
+                fetch(nxt, ps);
+            }
+        }
+    }
+    __syncwarp();
+    bar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int q = m0 + tid;
+        const bool sel = q < p.m && (!p.selector || p.selector[q] == 1);
+        float best = -INFINITY;
+        float* out = p.scores + (size_t)n0 * p.m + (sel ? q : 0);        // [D, m]: the 32 lanes of a store are 32 adjacent queries
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < SN / 32; ch++) {
+            float v[32];
+            tmem_ld32(lane_base + ch * 32, v);                         // warp-collective: every thread takes part
+            if (sel) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const bool in = n0 + ch * 32 + i < p.D;
+                    if (in) out[(size_t)(ch * 32 + i) * p.m] = v[i];
+                    best = in ? fmaxf(best, v[i]) : best;
+                }
+            }
+        }
+        if (sel && best > -INFINITY) atomicMax(&p.best_seen[q], skey(best));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(S_TMEM_COLS) : "memory");
+}
+
+// norms of the queries, cleared keys / counters
+__global__ void search_prep_kernel(const float* __restrict__ queries, int m, int d, float* __restrict__ qnorm,
+                                   unsigned long long* __restrict__ keys, unsigned* __restrict__ best_seen, unsigned* __restrict__ counters) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0u;
+    if (row >= m) return;
+    float ss = 0.f;
+    for (int k = lane; k < d; k += 32) { const float v = queries[(size_t)row * d + k]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) { qnorm[row] = sqrtf(ss); keys[row] = 0ull; best_seen[row] = 0u; }
+}
+
+// rows within 2 eps of the query's best approximate score -> the list of (query, row) pairs to re-score exactly
+__global__ void __launch_bounds__(256)
+search_select_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ selector, int m, int D, const float* __restrict__ qnorm,
+                     float eps_scale, const unsigned* __restrict__ best_seen, unsigned* __restrict__ counters, uint2* __restrict__ cand,
+                     unsigned cand_cap) {
+    const size_t total = (size_t)m * D;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / m), q = (int)(e - (size_t)r * m);
+        if (selector && selector[q] != 1) continue;
+        const unsigned seen = best_seen[q];
+        if (!seen) continue;
+        if (scores[e] >= sunkey(seen) - 2.f * eps_scale * qnorm[q]) {
+            const unsigned slot = atomicAdd(&counters[0], 1u);
+            if (slot < cand_cap) cand[slot] = make_uint2((unsigned)q, (unsigned)r); else counters[1] = 1u;
+        }
+    }
+}
+
+// exact score of every kept pair: the streaming kernel's expression (fg_align.cu face_search_kernel, d = 512 path and the
+// generic one), merged with its key (score key << 32 | ~row: the lowest row wins ties)
+__global__ void __launch_bounds__(256)
+search_rescore_kernel(const float* __restrict__ queries, const float* __restrict__ db, int d, const unsigned* __restrict__ counters,
+                      const uint2* __restrict__ cand, unsigned cand_cap, unsigned long long* __restrict__ keys) {
+    if (counters[1]) return;                                           // overflow: the exact search runs instead
+    const unsigned n = min(counters[0], cand_cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned c = blockIdx.x * 8 + (threadIdx.x >> 5); c < n; c += gridDim.x * 8) {
+        const uint2 pr = cand[c];
+        const float* qv = queries + (size_t)pr.x * d;
+        const float* row = db + (size_t)pr.y * d;
+        float acc = 0.f;
+        if (d == 512) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row) + lane + 32 * k);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(qv) + lane + 32 * k);
+                acc = fmaf(v.x, w.x, acc); acc = fmaf(v.y, w.y, acc); acc = fmaf(v.z, w.z, acc); acc = fmaf(v.w, w.w, acc);
+            }
+        } else {
+            for (int k = lane; k < d; k += 32) acc = fmaf(__ldg(row + k), qv[k], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) atomicMax(&keys[pr.x], ((unsigned long long)skey(acc) << 32) | (unsigned)(~pr.y));
+    }
+}
+
+__global__ void search_decode_kernel(const unsigned long long* __restrict__ keys, int m, long long* __restrict__ best_row, float* __restrict__ similarity) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const unsigned long long k = keys[q];
+    best_row[q] = k ? (long long)(unsigned)(~(unsigned)(k & 0xFFFFFFFFull)) : -1;
+    if (similarity) similarity[q] = k ? sunkey((unsigned)(k >> 32)) : -1.f;
+}
+}  // namespace tc
+}  // namespace
+
+struct SearchWs { unsigned long long* keys; unsigned* best_seen; float* qnorm; unsigned* counters; uint2* cand; unsigned cap; float* scores; size_t total; };
+static SearchWs search_carve(void* base, int m, int D) {
+    SearchWs w; size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off += (bytes + 255) / 256 * 256; return p; };
+    w.keys = (unsigned long long*)take((size_t)m * 8);
+    w.best_seen = (unsigned*)take((size_t)m * 4);
+    w.qnorm = (float*)take((size_t)m * 4);
+    w.counters = (unsigned*)take(16);
+    w.cap = (unsigned)m * 256u + 4096u;
+    w.cand = (uint2*)take((size_t)w.cap * 8);
+    w.scores = (float*)take((size_t)m * D * 4);
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t fg_face_search_tc_workspace_bytes(int m, int D) { return search_carve(nullptr, m > 0 ? m : 1, D > 0 ? D : 1).total; }
+
+extern "C" int fg_face_search_top1_tc(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
+                                      float db_norm_bound, int64_t* best_row, float* similarity, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    if (m < 0 || D < 1 || d < 32 || (d % 32) || !(db_norm_bound > 0.f) || !(db_norm_bound < 1e30f)) return FG_ERR_INVALID_ARG;
+    if (m == 0) return FG_OK;
+    if (!queries || !db || !best_row || ((uintptr_t)queries % 16) || ((uintptr_t)db % 16)) return FG_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < fg_face_search_tc_workspace_bytes(m, D)) return FG_ERR_WORKSPACE;
+    cudaStream_t st = fg_stream(stream);
+    SearchWs w = search_carve(workspace, m, D);
+    tc::TmaMap mq, md;
+    if (!make_map<float>(&mq, queries, d, m, d, tc::BM) || !make_map<float>(&md, db, d, D, d, tc::SN)) return FG_ERR_LIMIT;
+    tc::search_prep_kernel<<<(m + 7) / 8, 256, 0, st>>>(queries, m, d, w.qnorm, w.keys, w.best_seen, w.counters);
+    FG_LAUNCH_CHECK();
+    tc::SearchParams p;
+    p.selector = selector; p.m = m; p.D = D; p.K = d; p.qnorm = w.qnorm;
+    p.eps_scale = 2.2e-3f * db_norm_bound;            // 2^-9 = 1.95e-3 (two truncations to 10 mantissa bits) + the fp32 accumulation
+    p.best_seen = w.best_seen; p.scores = w.scores;
+    const size_t smem = (size_t)tc::S_STAGES * tc::S_STAGE + 1024 + 256;
+    cudaError_t e = cudaFuncSetAttribute(tc::face_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tc::face_search_tc_kernel<<<dim3((D + tc::SN - 1) / tc::SN, (m + tc::BM - 1) / tc::BM), tc::THREADS, smem, st>>>(p, mq, md);
+    FG_LAUNCH_CHECK();
+    {
+        size_t bx = ((size_t)m * D + 256 * 8 - 1) / (256 * 8);
+        if (bx > (size_t)8 * FG_NUM_SMS) bx = (size_t)8 * FG_NUM_SMS;
+        tc::search_select_kernel<<<(unsigned)bx, 256, 0, st>>>(w.scores, selector, m, D, w.qnorm, p.eps_scale, w.best_seen, w.counters, w.cand, w.cap);
+        FG_LAUNCH_CHECK();
+    }
+    tc::search_rescore_kernel<<<2 * FG_NUM_SMS, 256, 0, st>>>(queries, db, d, w.counters, w.cand, w.cap, w.keys);
+    FG_LAUNCH_CHECK();
+    int rc = fg_internal_search_exact_if(queries, selector, m, db, D, d, w.keys, w.counters + 1, st);
+    if (rc) return rc;
+    tc::search_decode_kernel<<<(m + 127) / 128, 128, 0, st>>>(w.keys, m, (long long*)best_row, similarity);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}

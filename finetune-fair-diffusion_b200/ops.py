@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and the
 current CUDA stream, raise on a non-zero return code.  No arithmetic happens here."""
 import ctypes
+import os
 
 import torch
 
@@ -480,14 +481,25 @@ def feats_normalize_bwd(g_f, f, inv, dtype):
     return g_raw
 
 
-def face_search_top1(queries, selector, db):
-    """-> (best_row int64 [m] (-1 where not selected), similarity float32 [m])."""
+SEARCH_TC_MIN_QUERIES = 16     # below this the streaming search is HBM-bound on the database and as fast as anything can be
+
+
+def face_search_top1(queries, selector, db, db_norm_bound=None):
+    """-> (best_row int64 [m] (-1 where not selected), similarity float32 [m]).
+    ``db_norm_bound`` (>= the largest L2 norm of a database row; computed once per database by the caller) enables the
+    tensor-core search for batches of >= SEARCH_TC_MIN_QUERIES queries; the results are identical either way."""
     _cuda(queries, selector, db)
     q = queries.to(torch.float32).contiguous()
     m, d = q.shape
     assert db.dtype == torch.float32 and db.is_contiguous() and db.shape[1] == d
     best = torch.empty((m,), dtype=torch.int64, device=q.device)
     sim = torch.empty((m,), dtype=torch.float32, device=q.device)
+    if db_norm_bound is not None and m >= SEARCH_TC_MIN_QUERIES and d % 32 == 0 and db.shape[0] >= 128 and os.environ.get("FG_SEARCH_EXACT") is None:
+        nbytes = _lib.lib().fg_face_search_tc_workspace_bytes(m, db.shape[0])
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
+        check(_lib.lib().fg_face_search_top1_tc(_p(q), _p(_u8(selector)), m, _p(db), db.shape[0], d, float(db_norm_bound), _p(best), _p(sim),
+                                                _p(ws), nbytes, _stream()), "fg_face_search_top1_tc")
+        return best, sim
     nbytes = _lib.lib().fg_face_search_workspace_bytes(m)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
     check(_lib.lib().fg_face_search_top1(_p(q), _p(_u8(selector)), m, _p(db), db.shape[0], d, _p(best), _p(sim), _p(ws), nbytes,

@@ -270,6 +270,15 @@ int fg_feats_normalize_bwd(const float* g_f, const float* f, const float* inv_no
 size_t fg_face_search_workspace_bytes(int m);
 int fg_face_search_top1(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
                         int64_t* best_row, float* similarity, void* workspace, size_t workspace_bytes, void* stream);
+/* The same search for query BATCHES (m >= ~16) on the tensor cores: one TF32 tcgen05 pass keeps, per query, the rows whose
+ * approximate score is within the TF32 error bound of the query's best one; those (a handful per query) are re-scored with the
+ * exact fp32 expression of fg_face_search_top1, so best_row / similarity are identical to it.  db_norm_bound >= the largest
+ * L2 norm of a database row (1 for the reference's normalised features; the caller computes it once per database);
+ * d a multiple of 32, queries / db 16-byte aligned. */
+size_t fg_face_search_tc_workspace_bytes(int m, int D);
+int fg_face_search_top1_tc(const float* queries, const uint8_t* selector, int m, const float* db, int D, int d,
+                           float db_norm_bound, int64_t* best_row, float* similarity, void* workspace,
+                           size_t workspace_bytes, void* stream);
 size_t fg_face_loss_workspace_bytes(int n, int d);
 int fg_face_loss_fwd(const void* raw_feats, const float* feats_ori, const float* db, int n, int d, int D,
                      const uint8_t* face_indicators, const int64_t* const* targets, const int64_t* const* preds_ori,

@@ -190,6 +190,31 @@ def test_gpu_semantic_search_vs_oracle(n, d, D):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("m,d,D", [(16, 512, 128), (33, 512, 1000), (128, 512, 20000), (200, 256, 4099), (64, 512, 100000)])
+def test_gpu_tensor_core_search_equals_exact_search(m, d, D):
+    """fg_face_search_top1_tc (one TF32 tcgen05 pass + exact re-score of the rows within the TF32 error bound) returns the
+    SAME rows and the SAME fp32 scores as the streaming search -- with a selector, ragged last tiles, duplicated database
+    rows (exact ties: the lowest row wins) and near-duplicates closer together than the TF32 resolution."""
+    import fairguide as fg
+    g = torch.Generator().manual_seed(m * 7 + D)
+    db = torch.nn.functional.normalize(torch.randn(D, d, generator=g), dim=-1)
+    q = torch.nn.functional.normalize(torch.randn(m, d, generator=g), dim=-1)
+    q[1] = db[D // 2]                                    # an exact hit ...
+    db[D // 3] = db[D // 2]                              # ... that exists twice (tie -> row D // 3)
+    db[D - 1] = torch.nn.functional.normalize(db[D // 2] + 1e-5 * torch.randn(d, generator=g), dim=-1)   # and a near-duplicate
+    sel = torch.rand(m, generator=g) > 0.2
+    sel[1] = True
+    db, q, sel = db.to(DEV).contiguous(), q.to(DEV), sel.to(DEV)
+    b0, s0 = fg.ops.face_search_top1(q, sel, db)
+    b1, s1 = fg.ops.face_search_top1(q, sel, db, db_norm_bound=float(db.norm(dim=1).max()))
+    assert torch.equal(b0, b1) and torch.equal(s0, s1)
+    # the duplicated row: the lower index wins the tie (the near-duplicate may round to the same fp32 score or above)
+    assert int(b1[1]) in (D // 3, D - 1) and (b1[~sel] == -1).all()
+    ref = (q.double() @ db.double().T).max(1).values
+    assert (ref[sel] - s1[sel].double()).abs().max() < 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("n_attr", [1, 2, 3])
 def test_gpu_face_realism_loss_fwd_bwd_vs_oracle(n_attr, dtype, tol):

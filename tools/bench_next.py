@@ -52,11 +52,17 @@ res["align_matrices_ms"] = round(timeit(lambda: fg.ops.align_matrices(lms, ind, 
 
 D, d = 100_000, 512
 db = torch.nn.functional.normalize(torch.randn(D, d, generator=g, device=dev), dim=-1)
+dbound = float(db.norm(dim=1).max())        # once per database
 for m in (4, 32, 128):
     q = torch.nn.functional.normalize(torch.randn(m, d, generator=g, device=dev), dim=-1)
-    t = timeit(lambda: fg.ops.face_search_top1(q, None, db))
+    t = timeit(lambda: fg.ops.face_search_top1(q, None, db, db_norm_bound=dbound))
+    t_exact = timeit(lambda: fg.ops.face_search_top1(q, None, db))
+    b1, s1 = fg.ops.face_search_top1(q, None, db, db_norm_bound=dbound)
+    b0, s0 = fg.ops.face_search_top1(q, None, db)
+    assert torch.equal(b1, b0) and torch.equal(s1, s0), "tensor-core search differs from the exact search"
     t_torch = timeit(lambda: (q @ db.T).max(dim=1))
-    res[f"face_search_m{m}"] = {"ms": round(t, 4), "db_GBps": round(D * d * 4 / t / 1e6, 1), "torch_matmul_max_ms": round(t_torch, 4)}
+    res[f"face_search_m{m}"] = {"ms": round(t, 4), "db_GBps": round(D * d * 4 / t / 1e6, 1), "torch_matmul_max_ms": round(t_torch, 4), "streaming_kernel_ms": round(t_exact, 4),
+                                "path": "tcgen05 TF32 + exact re-score" if m >= fg.ops.SEARCH_TC_MIN_QUERIES else "streaming (HBM-bound)"}
 m = 32
 raw = torch.randn(m, d, generator=g, device=dev)
 fo = torch.nn.functional.normalize(torch.randn(m, d, generator=g, device=dev), dim=-1)
