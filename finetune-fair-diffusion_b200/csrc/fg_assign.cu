@@ -696,12 +696,17 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
     int tr_mode = 0;                 // 0: full / sampled sweeps, 1: inside a trust region (registers + active list)
     int n_active = 0, my_pk0 = 0, my_rk = 0, my_frozen = 0;
     int rb = 0;                      // counter buffer of this round (sm.rcnt)
+    int n_pivots = 0;                // classifications so far
     for (int it = 0; it <= dual_iters; it++) {
         const int my_pk = price_key(my_price);
         // ---- classification sweep (no price update): pivot = the current prices
         if (it >= next_pivot && (tr_mode == 0 || __any_sync(0xffffffffu, lane < KK && abs(my_pk - my_pk0) > my_rk))) {
             my_pk0 = my_pk;
-            my_rk = max(price_key(trust * my_step), 16);
+            // every re-classification doubles the radius factor (up to 8x): a draw whose prices keep drifting out of their boxes
+            // (8 classifications at a fixed factor, 20-25 k cycles each, on the draws that set the kernel's duration) settles
+            // for a larger active list instead
+            my_rk = max(price_key(trust * (float)(1 << min(n_pivots, 3)) * my_step), 16);
+            n_pivots++;
 #ifdef FG_OT_PROFILE
             if (tid == 0) { sm.prof_pivots++; sm.prof_pivot_last = it; }
 #endif
