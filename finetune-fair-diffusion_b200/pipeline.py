@@ -318,15 +318,16 @@ class GuidancePath:
         P = probe if probe is not None else _NullProbe
         st = self.phase_a(batch, probe)
         P.begin("assign")
-        P.begin("exchange_rows")
+        Q = P if "packed" in st else _NullProbe          # the parts of the assignment stage are of interest with several ranks only
+        Q.begin("exchange_rows")
         self.exchange_1(st)
-        P.end("exchange_rows")
-        P.begin("plan_counts")
+        Q.end("exchange_rows")
+        Q.begin("plan_counts")
         self.phase_b(st, batch, rand_tensors, num_valid)
-        P.end("plan_counts")
-        P.begin("exchange_counts")
+        Q.end("plan_counts")
+        Q.begin("exchange_counts")
         self.exchange_2(st)
-        P.end("exchange_counts")
+        Q.end("exchange_counts")
         return self.phase_c(st, batch, probe, close_assign=True)
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence of the Blackwell-native instructions per kernel of libfairguide.so (B200_PROFILING.md: tcgen05.mma -> UTC*MMA,
 tcgen05.ld -> LDTM, TMA -> UTMALDG / UBLKCP, mbarrier -> SYNCS, warp reductions -> REDUX, 3-input integer min -> VIMNMX3).
-usage: sass_evidence.py ROUND_TAG   ->  profiles/<tag>_sass_{head,sample,image_grad,solver}.txt  (runs without a GPU)"""
+usage: sass_evidence.py ROUND_TAG   ->  profiles/<tag>_sass_{head,sample,image_grad,solver,peer}.txt  (runs without a GPU)"""
 import collections, os, re, subprocess, sys
 tag = sys.argv[1]
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,8 +16,9 @@ for line in sass.splitlines():
     elif cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         funcs[cur].append(line)
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip() or n
-PAT = re.compile(r"\b(UTC\w*MMA\w*|UTCBAR\w*|UTCATOM\w*|LDTM\w*|STTM\w*|UTMALDG\w*|UTMASTG\w*|UBLKCP\w*|SYNCS\w*|REDUX\w*|VIMNMX3\w*|HMMA\w*|LDGSTS\w*|UTMAPF\w*)")
-groups = {"head": ["head_gemm", "head_", "split_tf32"], "sample": ["sample_fwd"], "image_grad": ["image_grad"], "solver": ["ot_solve", "cost_hist", "ot_targets", "compact"]}
+PAT = re.compile(r"\b(STG\.E\.STRONG\.SYS|LDG\.E\.STRONG\.SYS|MEMBAR\.ALL\.SYS|UTC\w*MMA\w*|UTCBAR\w*|UTCATOM\w*|LDTM\w*|STTM\w*|UTMALDG\w*|UTMASTG\w*|UBLKCP\w*|SYNCS\w*|REDUX\w*|VIMNMX3\w*|HMMA\w*|LDGSTS\w*|UTMAPF\w*)")
+groups = {"head": ["head_gemm", "head_", "split_tf32", "face_search_tc"], "sample": ["sample_fwd"], "image_grad": ["image_grad"],
+          "solver": ["ot_solve", "cost_hist", "ot_targets", "compact"], "peer": ["peer_"]}
 for g, keys in groups.items():
     out = [f"# cuobjdump -sass libfairguide.so (architectures in the library: {', '.join(arch)}), kernels matching {keys}",
            "# per kernel: instruction count, then every Blackwell-specific / async / tensor mnemonic with its count and one example line"]
