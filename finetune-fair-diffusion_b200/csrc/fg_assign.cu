@@ -657,7 +657,8 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
     constexpr int RPT = 4;
     const int pivot_round = pivot_arg & 0xff;            // first round of the trust region
     const float trust = (float)((pivot_arg >> 8) & 0xff);    // R_l = trust * step_l
-    const int sample_rounds = min((pivot_arg >> 16) & 0xff, pivot_round);   // first rounds that sweep the on-chip rows only
+    const int sample_rounds = min((pivot_arg >> 16) & 0x7f, pivot_round);   // first rounds that sweep the on-chip rows only
+    const bool asym = ((pivot_arg >> 23) & 1) != 0;                         // asymmetric boxes (A/B runs only)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float my_price = lane < KP ? sm.pricef[lane] : 0.f, my_best = my_price, my_step = step0;
     int my_prev = 0, best_resid = 0x7fffffff;
@@ -694,25 +695,31 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
     int next_pivot = pivot_round;    // the next round that may classify (moved back after an overflow)
     // trust-region state, identical in every thread (lane l < KK holds class l's pivot key, radius and frozen count)
     int tr_mode = 0;                 // 0: full / sampled sweeps, 1: inside a trust region (registers + active list)
-    int n_active = 0, my_pk0 = 0, my_rk = 0, my_frozen = 0;
+    int n_active = 0, my_pk0 = 0, my_rp = 0, my_rm = 0, my_frozen = 0;     // box of class l: [pk0 - rm, pk0 + rp]
     int rb = 0;                      // counter buffer of this round (sm.rcnt)
     int n_pivots = 0;                // classifications so far
     for (int it = 0; it <= dual_iters; it++) {
         const int my_pk = price_key(my_price);
         // ---- classification sweep (no price update): pivot = the current prices
-        if (it >= next_pivot && (tr_mode == 0 || __any_sync(0xffffffffu, lane < KK && abs(my_pk - my_pk0) > my_rk))) {
+        if (it >= next_pivot && (tr_mode == 0 || __any_sync(0xffffffffu, lane < KK && (my_pk - my_pk0 > my_rp || my_pk0 - my_pk > my_rm)))) {
             my_pk0 = my_pk;
-            // every re-classification doubles the radius factor (up to 8x): a draw whose prices keep drifting out of their boxes
-            // (8 classifications at a fixed factor, 20-25 k cycles each, on the draws that set the kernel's duration) settles
-            // for a larger active list instead
-            my_rk = max(price_key(trust * (float)(1 << min(n_pivots, 3)) * my_step), 16);
+            // Tried and kept as A/B knobs only (FG_OT_ASYM=1): a box that reaches 4x further in the direction a class's price is
+            // drifting, and a radius that doubles on every re-classification.  Both cut the number of classifications (5-8 per draw
+            // on peaked, class-biased probabilities) but push the active list over the slice's capacity: 0.42 -> 0.53 ms at
+            // N = 7720 on the bench step's probabilities, 0.43 -> 0.57 ms inside the 8-GPU step.
+            {
+                const int base = max(price_key(trust * my_step), 16);
+                const int ahead = asym ? 4 * base : base, behind = asym ? max(base / 2, 16) : base;
+                my_rp = my_prev > 0 ? ahead : (my_prev < 0 ? behind : base);
+                my_rm = my_prev < 0 ? ahead : (my_prev > 0 ? behind : base);
+            }
             n_pivots++;
 #ifdef FG_OT_PROFILE
             if (tid == 0) { sm.prof_pivots++; sm.prof_pivot_last = it; }
 #endif
             int pkz[KK];
 #pragma unroll
-            for (int l = 0; l < KK; l++) pkz[l] = __shfl_sync(0xffffffffu, my_pk0 + my_rk, l);
+            for (int l = 0; l < KK; l++) pkz[l] = __shfl_sync(0xffffffffu, my_pk0 + my_rp, l);
             if (tid == 0) { sm.n_active = 0; sm.tr_overflow = 0; }
             __syncthreads();
             unsigned acc[KP / 2];
@@ -732,8 +739,8 @@ __device__ __forceinline__ void price_search_hybrid(SolverSmem& sm, const int* _
 #pragma unroll
                 for (int l = 0; l < KK; l++) y[l] = l == sc ? 0x7f000000 : y[l];
                 const int m2 = min_key<KK>(y);
-                const int rs = __shfl_sync(0xffffffffu, my_rk, sc);
-                const bool frozen = valid && m2 > m1 + 2 * rs + 16;
+                const int rs = __shfl_sync(0xffffffffu, my_rp + my_rm, sc);          // width of the winner's box
+                const bool frozen = valid && m2 > m1 + rs + 16;
                 const bool active = valid && !frozen;
                 if (frozen) {
                     h += 1ull << (sc << 2);
@@ -1445,7 +1452,7 @@ __global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
 // round of the price search at which the trust region starts (price_search_hybrid); a tuning knob, results do not depend on it
-#define SEARCH_PIVOT_ROUND (env_int("FG_OT_PIVOT", 12) | (env_int("FG_OT_TRUST", 6) << 8) | (env_int("FG_OT_SAMPLE", 6) << 16))
+#define SEARCH_PIVOT_ROUND (env_int("FG_OT_PIVOT", 12) | (env_int("FG_OT_TRUST", 6) << 8) | (env_int("FG_OT_SAMPLE", 6) << 16) | (env_int("FG_OT_ASYM", 0) << 23))
 
 #define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, MK_, ...)                                                                     \
     do {                                                                                                              \
