@@ -1452,7 +1452,7 @@ __global__ void mf_from_m_kernel(const double* __restrict__ M, float* __restrict
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static double env_dbl(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
 // round of the price search at which the trust region starts (price_search_hybrid); a tuning knob, results do not depend on it
-#define SEARCH_PIVOT_ROUND (env_int("FG_OT_PIVOT", 12) | (env_int("FG_OT_TRUST", 6) << 8) | (env_int("FG_OT_SAMPLE", 6) << 16) | (env_int("FG_OT_ASYM", 0) << 23))
+#define SEARCH_PIVOT_ROUND (env_int("FG_OT_PIVOT", 18) | (env_int("FG_OT_TRUST", 6) << 8) | (env_int("FG_OT_SAMPLE", 6) << 16) | (env_int("FG_OT_ASYM", 0) << 23))
 
 #define FG_SOLVE_LAUNCH(N_, K_, GRID_, ST_, MK_, ...)                                                                     \
     do {                                                                                                              \
