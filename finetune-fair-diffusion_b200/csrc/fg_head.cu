@@ -128,9 +128,13 @@ head_bwd_hidden_kernel(const float* __restrict__ g_logits, const T* __restrict__
     for (int k = threadIdx.x; k < k_head; k += blockDim.x) gl[k] = g_logits[(size_t)row * k_head + k];
     __syncthreads();
     for (int j = threadIdx.x; j < d_hid; j += blockDim.x) {
+        // same summation order as before; unrolled so that the loads of 8 rows of W2 are in flight together (k_head = 80 for the
+        // E1 head: 400 dependent L2 round trips per thread made this 61 us for 122 rows)
+        const float pv = to_f32(pre[(size_t)row * d_hid + j]);
         float s = 0.f;
-        for (int k = 0; k < k_head; k++) s = fmaf(gl[k], to_f32(w2[(size_t)k * d_hid + j]), s);
-        g_pre[(size_t)row * d_hid + j] = from_f32<TO>(s * hardswish_grad(to_f32(pre[(size_t)row * d_hid + j])));
+#pragma unroll 8
+        for (int k = 0; k < k_head; k++) s = fmaf(gl[k], to_f32(__ldg(w2 + (size_t)k * d_hid + j)), s);
+        g_pre[(size_t)row * d_hid + j] = from_f32<TO>(s * hardswish_grad(pv));
     }
 }
 
