@@ -166,6 +166,23 @@ __device__ __forceinline__ void gs_stage2(const GsCols& k, uint32_t rec, uint32_
     }
 }
 
+// Tap table of image index p for the 512 -> 224 resize without make_tab's search: the ratio is 16 : 7, so within every block
+// of 16 image indices the pairs (0,1) (2,3) (5,6) (7,8) (9,10) (12,13) (14,15) are the two taps of resized indices 7g .. 7g+6 and
+// indices 4 and 11 receive nothing (fg_image_grad_quad.cuh).  The weight is still the fp32 value of ATen's formula, and the
+// formula's own i0 is checked: a disagreement (never observed; the distance of the source coordinate from an integer is
+// >= 1/14) falls back to the search.  Cuts the per-CTA set-up, which was 16 % of the kernel's instructions.
+__device__ __forceinline__ Tab small_tab_512_224(int p, float ss) {
+    Tab t; t.lo = 0; t.n = 0; t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+    const int q = p & 15;
+    // o_local = (7 q + 3) >> 4 maps 0,1->0  2,3->1  5,6->2  7,8->3  9,10->4  12,13->5  14,15->6  (4 and 11 are excluded first)
+    if (q == 4 || q == 11) return t;
+    const int o = 7 * (p >> 4) + ((7 * q + 3) >> 4);
+    const Axis a = axis_index(o, ss, 512);
+    if (a.i0 == p) { t.lo = o; t.n = 1; t.w[0] = a.l0; return t; }
+    if (a.i1 == p && a.i1 != a.i0) { t.lo = o; t.n = 1; t.w[0] = a.l1; return t; }
+    return make_tab(p, ss, 512, GS_OW);
+}
+
 template <typename T, int NSUB>
 __global__ void __launch_bounds__(256, FG_GS_MINB)
 image_grad_staged_kernel(const BwdParams p) {
@@ -216,7 +233,7 @@ image_grad_staged_kernel(const BwdParams p) {
         const int y = ybase + r;
         if (g == 0) {
             Tab t; t.lo = 0; t.n = 0; t.w[0] = 0.f;
-            if (has_s) t = make_tab(y, ss, H, OH);
+            if (has_s) t = small_tab_512_224(y, ss);
             GsRowS a; a.off = t.n ? t.lo : -1;                // absolute row for now
             a.wy = t.n ? t.w[0] : 0.f; a.wr = (y >= ry0 && y < ry1) ? a.wy : 0.f; a.offz = 0;
             rowS[r] = a;
@@ -238,7 +255,7 @@ image_grad_staged_kernel(const BwdParams p) {
     for (int v = 0; v < 2; v++) {
         const int x = x_a + v;
         Tab t; t.lo = 0; t.n = 0; t.w[0] = 0.f;
-        if (has_s) t = make_tab(x, ss, W, OW);
+        if (has_s) t = small_tab_512_224(x, ss);
         const bool keep = t.n != 0;
         const float ws = keep ? t.w[0] : 0.f;
         const float wd = (x >= rx0 && x < rx1) ? ws * rs - ws : 0.f;
