@@ -70,6 +70,8 @@ SIGNATURES = {
     "fg_peer_push": (_i, [_p, _z, _p, _z, _z, _z, _i, _z, _i, _i, _i, _p, _p, _p]),
     "fg_peer_wait_copy": (_i, [_p, _i, _i, _z, _i, _z, _z, _p, _p, _z, _p, _p]),
     "fg_peer_wait_sum": (_i, [_p, _i, _i, _z, _i, _z, _z, _p, _p, _z, _p, _p]),
+    "fg_peer_push_rows": (_i, [_p, _p, _p, _i, _i, _p, _z, _z, _z, _z, _i, _i, _p, _p, _i, _p]),
+    "fg_peer_wait_unpack": (_i, [_p, _i, _i, _z, _z, _z, _p, _p, _p, _p, _i, _i, _p, _i, _p]),
 }
 
 _lib = None
@@ -115,7 +117,7 @@ KERNELS_PER_CALL = {
     "fg_aligned_warp_bwd": 1, "fg_feats_normalize_fwd": 1, "fg_feats_normalize_bwd": 1, "fg_face_search_top1": 2, "fg_face_search_top1_tc": 6,
     "fg_face_loss_fwd": 4, "fg_face_loss_bwd": 1, "fg_face_loss_target_rows": 0,
     "fg_grad_bucket_pack": 2, "fg_grad_bucket_unpack": 1,
-    "fg_peer_epoch_advance": 1, "fg_peer_push": 1, "fg_peer_wait_copy": 1, "fg_peer_wait_sum": 1,
+    "fg_peer_epoch_advance": 1, "fg_peer_push": 1, "fg_peer_wait_copy": 1, "fg_peer_wait_sum": 1, "fg_peer_push_rows": 1, "fg_peer_wait_unpack": 1,
 }
 
 

@@ -104,6 +104,78 @@ peer_wait_sum_kernel(uint8_t* const* __restrict__ peer_base, int rank, int world
     }
 }
 
+// ---- exchange 1 without the intermediate copies: the packed row block {indicator, probs_0, probs_1, probs_2} is assembled in
+// shared memory straight from the head's outputs and stored into every peer (push_rows), and the gathered block is taken
+// apart into the tensors the assignment kernels read (wait_unpack).  Replaces torch.cat + fg_peer_push and fg_peer_wait_copy +
+// four slicing kernels.
+struct RowSrc { const void* probs[3]; int w[3]; int n_attr; };
+struct RowDst { void* probs[3]; int w[3]; int n_attr; };
+constexpr int PUSH_ROWS = 64;            // rows per CTA: 64 * row bytes is a multiple of 16 for every element size and width
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_push_rows_kernel(const uint8_t* __restrict__ ind, RowSrc src, int n, uint8_t* const* __restrict__ peer_base, size_t region_off,
+                      size_t parity_stride, size_t slot_off, size_t flags_off, int rank, int world,
+                      const unsigned* __restrict__ epoch_dev, unsigned* __restrict__ done_counter) {
+    extern __shared__ __align__(16) uint8_t rows_s[];
+    const unsigned epoch = *epoch_dev;
+    const int wtot = 1 + src.w[0] + src.w[1] + src.w[2];
+    const int r0 = blockIdx.x * PUSH_ROWS, nr = min(PUSH_ROWS, n - r0);
+    T* rs = reinterpret_cast<T*>(rows_s);
+    for (int e = threadIdx.x; e < nr * wtot; e += blockDim.x) {
+        const int r = e / wtot, c = e - r * wtot, i = r0 + r;
+        T v;
+        if (c == 0) v = from_f32<T>(ind[i] ? 1.f : 0.f);
+        else {
+            int cc = c - 1, a = 0;
+            while (a < 2 && cc >= src.w[a]) { cc -= src.w[a]; a++; }
+            v = reinterpret_cast<const T*>(src.probs[a])[(size_t)i * src.w[a] + cc];
+        }
+        rs[e] = v;
+    }
+    __syncthreads();
+    const size_t bytes = (size_t)nr * wtot * sizeof(T);             // a multiple of 16 (host check: n * row bytes % 16 == 0, PUSH_ROWS % 8 == 0)
+    const size_t n16 = bytes / 16, boff = (size_t)r0 * wtot * sizeof(T);
+    for (int p = 0; p < world; p++) {
+        uint4* dst = reinterpret_cast<uint4*>(peer_base[p] + region_off + (size_t)(epoch & 1u) * parity_stride + slot_off + boff);
+        for (size_t e = threadIdx.x; e < n16; e += blockDim.x) dst[e] = reinterpret_cast<const uint4*>(rows_s)[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(done_counter, 1u);
+        if (ticket == gridDim.x - 1u) {
+            __threadfence_system();
+            *done_counter = 0u;
+            for (int p = 0; p < world; p++)
+                st_release_sys(reinterpret_cast<unsigned*>(peer_base[p] + flags_off) + rank, epoch);      // flag_index 0 = rows
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_wait_unpack_kernel(uint8_t* const* __restrict__ peer_base, int rank, int world, size_t flags_off, size_t region_off,
+                        size_t parity_stride, const unsigned* __restrict__ epoch_dev, uint8_t* __restrict__ ind_all, RowDst dst,
+                        int n_all, int* __restrict__ status) {
+    const unsigned epoch = *epoch_dev;
+    const uint8_t* base = peer_base[rank];
+    peer_wait_flags(reinterpret_cast<const unsigned*>(base + flags_off), world, epoch, status);
+    const int wtot = 1 + dst.w[0] + dst.w[1] + dst.w[2];
+    const T* rows = reinterpret_cast<const T*>(base + region_off + (size_t)(epoch & 1u) * parity_stride);
+    const size_t total = (size_t)n_all * wtot;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = e / wtot; const int c = (int)(e - i * wtot);
+        const T v = rows[e];
+        if (c == 0) ind_all[i] = to_f32(v) != 0.f ? 1 : 0;
+        else {
+            int cc = c - 1, a = 0;
+            while (a < 2 && cc >= dst.w[a]) { cc -= dst.w[a]; a++; }
+            reinterpret_cast<T*>(dst.probs[a])[i * dst.w[a] + cc] = v;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int fg_peer_epoch_advance(uint32_t* epoch_dev, void* stream) {
@@ -157,6 +229,44 @@ extern "C" int fg_peer_wait_sum(const void* peer_base_dev, int rank, int world, 
     if (blocks > 2 * FG_NUM_SMS) blocks = 2 * FG_NUM_SMS;
     peer_wait_sum_kernel<<<blocks, 256, 0, fg_stream(stream)>>>((uint8_t* const*)peer_base_dev, rank, world, flags_off, flag_index, region_off,
                                                                parity_stride, epoch_dev, (int4*)out, n16, status);
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_peer_push_rows(const uint8_t* indicators, const void* const* probs, const int32_t* widths, int n_attr, int n,
+                                 const void* peer_base_dev, size_t region_off, size_t parity_stride, size_t slot_off, size_t flags_off,
+                                 int rank, int world, const uint32_t* epoch_dev, uint32_t* done_counter, int dtype, void* stream) {
+    if (!indicators || !probs || !widths || n_attr < 1 || n_attr > 3 || n < 1 || !peer_base_dev || !epoch_dev || !done_counter ||
+        world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world)
+        return FG_ERR_INVALID_ARG;
+    RowSrc src = {}; src.n_attr = n_attr;
+    int wtot = 1;
+    for (int a = 0; a < n_attr; a++) { if (!probs[a] || widths[a] < 1) return FG_ERR_INVALID_ARG; src.probs[a] = probs[a]; src.w[a] = widths[a]; wtot += widths[a]; }
+    const size_t esz = dtype == FG_F32 ? 4 : 2;
+    if (((size_t)n * wtot * esz) % 16 || (n % 8) || (region_off % 16) || (parity_stride % 16) || (slot_off % 16)) return FG_ERR_INVALID_ARG;
+    const size_t smem = (size_t)PUSH_ROWS * wtot * esz;
+    const unsigned grid = (unsigned)((n + PUSH_ROWS - 1) / PUSH_ROWS);
+    FG_DISPATCH_DTYPE(dtype, T,
+        peer_push_rows_kernel<T><<<grid, 256, smem, fg_stream(stream)>>>(indicators, src, n, (uint8_t* const*)peer_base_dev, region_off,
+                                                                        parity_stride, slot_off, flags_off, rank, world, epoch_dev, done_counter));
+    FG_LAUNCH_CHECK();
+    return FG_OK;
+}
+
+extern "C" int fg_peer_wait_unpack(const void* peer_base_dev, int rank, int world, size_t flags_off, size_t region_off, size_t parity_stride,
+                                   const uint32_t* epoch_dev, uint8_t* indicators_all, void* const* probs_all, const int32_t* widths,
+                                   int n_attr, int n_all, int32_t* status, int dtype, void* stream) {
+    if (!peer_base_dev || !epoch_dev || !indicators_all || !probs_all || !widths || n_attr < 1 || n_attr > 3 || n_all < 1 ||
+        world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || (region_off % 16) || (parity_stride % 16))
+        return FG_ERR_INVALID_ARG;
+    RowDst dst = {}; dst.n_attr = n_attr;
+    int wtot = 1;
+    for (int a = 0; a < n_attr; a++) { if (!probs_all[a] || widths[a] < 1) return FG_ERR_INVALID_ARG; dst.probs[a] = probs_all[a]; dst.w[a] = widths[a]; wtot += widths[a]; }
+    size_t blocks = ((size_t)n_all * wtot + 255) / 256;
+    if (blocks > 2 * FG_NUM_SMS) blocks = 2 * FG_NUM_SMS;
+    FG_DISPATCH_DTYPE(dtype, T,
+        peer_wait_unpack_kernel<T><<<(unsigned)blocks, 256, 0, fg_stream(stream)>>>((uint8_t* const*)peer_base_dev, rank, world, flags_off, region_off,
+                                                                                    parity_stride, epoch_dev, indicators_all, dst, n_all, status));
     FG_LAUNCH_CHECK();
     return FG_OK;
 }

@@ -175,6 +175,30 @@ class PeerExchange:
         self._call("fg_peer_wait_copy", self.peer_base_dev, self.rank, self.world, 0, 0, self.rows_off, self.rows_parity,
                    self._p(self.epoch), self._p(gathered), nbytes, self._p(self.status), self._st())
 
+    def push_rows_from(self, face_indicators, probs):
+        """push_rows without the packed intermediate: the {indicator, probs} row block is assembled on the device from the head's
+        outputs and stored into every peer by ONE kernel (fg_peer_push_rows)."""
+        n = face_indicators.shape[0]
+        ind = (face_indicators.view(torch.uint8) if face_indicators.dtype == torch.bool else face_indicators.to(torch.uint8)).contiguous()
+        ps = [p.detach().contiguous() for p in probs]
+        widths = (ctypes.c_int32 * len(ps))(*[p.shape[1] for p in ps])
+        ptrs = (ctypes.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
+        dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[ps[0].dtype]
+        assert n * (1 + sum(p.shape[1] for p in ps)) * ps[0].element_size() == self.slot_bytes
+        self._call("fg_peer_push_rows", self._p(ind), ptrs, widths, len(ps), n, self.peer_base_dev, self.rows_off, self.rows_parity,
+                   self.rank * self.slot_bytes, 0, self.rank, self.world, self._p(self.epoch), self._p(self.done), dt, self._st())
+
+    def wait_rows_into(self, n_all, widths, dtype, device):
+        """wait_rows + unpack_probs in one kernel (fg_peer_wait_unpack) -> (face_indicators_all bool [n_all], [probs_all ...])."""
+        ind_all = torch.empty((n_all,), dtype=torch.uint8, device=device)
+        outs = [torch.empty((n_all, w), dtype=dtype, device=device) for w in widths]
+        wa = (ctypes.c_int32 * len(outs))(*widths)
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype]
+        self._call("fg_peer_wait_unpack", self.peer_base_dev, self.rank, self.world, 0, self.rows_off, self.rows_parity, self._p(self.epoch),
+                   self._p(ind_all), ptrs, wa, len(outs), n_all, self._p(self.status), dt, self._st())
+        return ind_all.view(torch.bool), outs
+
     def sum_counts(self, counts):
         """All-reduce(SUM) of the int32 plan counts, in place: publish, wait for every rank, pull and add in rank order."""
         nbytes = counts.numel() * 4

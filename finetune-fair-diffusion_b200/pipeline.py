@@ -181,18 +181,17 @@ class GuidancePath:
         self.cfg, self.head, self.backbone, self.group = cfg, head_weights, backbone, group
         self.peer_mode, self.peer = peer_exchange, None
 
-    def _peer_for(self, packed, n_all, K):
+    def _peer_for(self, slot, n_all, K, device):
         """The PeerExchange for this batch shape: created collectively on the first multi-rank step; None = use NCCL (transport
         switched off or unavailable, rows not a multiple of 16 bytes, or a batch larger than the one it was sized for)."""
         if self.peer_mode in (False, "off") or self.peer is False:
             return None
-        slot = packed.numel() * packed.element_size()
         counts_bytes = ((n_all * K * 4 + 15) // 16) * 16
         if self.peer is None:
-            if slot % 16 or not fdist.PeerExchange.available(packed.device):
+            if slot % 16 or (n_all // fdist._world(self.group)[0]) % 8 or not fdist.PeerExchange.available(device):
                 return None
             try:
-                self.peer = fdist.PeerExchange(slot, counts_bytes, packed.device, self.group)
+                self.peer = fdist.PeerExchange(slot, counts_bytes, device, self.group)
             except Exception as e:      # no peer mapping on this machine: say so once, stay on NCCL
                 import sys
                 print(f"fairguide: PeerExchange unavailable ({type(e).__name__}: {e}); the exchanges use NCCL", file=sys.stderr)
@@ -223,19 +222,24 @@ class GuidancePath:
                   logits_attr=logits_attr)
         world, _ = fdist._world(self.group)
         if world > 1:
-            st["packed"] = fdist.pack_probs(ind, probs)
-            st["gathered"] = torch.empty((world * n, st["packed"].shape[1]), dtype=st["packed"].dtype, device=images.device)
-            st["peer"] = self._peer_for(st["packed"], world * n, K) if images.is_cuda else None
+            st["multi"] = True
+            wtot = 1 + sum(widths)
+            st["peer"] = self._peer_for(n * wtot * probs[0].element_size(), world * n, K, images.device) if images.is_cuda else None
             if st["peer"] is not None:
-                # one-shot NVLink transport: the rows leave for every peer as soon as they exist
+                # one-shot NVLink transport: the rows leave for every peer as soon as they exist, packed on the way
                 st["peer"].begin_step()
-                st["peer"].push_rows(st["packed"])
+                st["peer"].push_rows_from(ind, probs)
+            else:
+                st["packed"] = fdist.pack_probs(ind, probs)
+                st["gathered"] = torch.empty((world * n, wtot), dtype=st["packed"].dtype, device=images.device)
         return st
 
     def exchange_1(self, st):
         """Stage 5: the all-gather (no-op with one rank)."""
         if st.get("peer") is not None:
-            st["peer"].wait_rows(st["gathered"])
+            widths = KINDS[self.cfg.kind][0]
+            world, _ = fdist._world(self.group)
+            st["unpacked"] = st["peer"].wait_rows_into(world * st["ind"].shape[0], widths, st["probs"][0].dtype, st["ind"].device)
         elif "packed" in st:
             fdist.all_gather_packed(st["gathered"], st["packed"], self.group)
 
@@ -245,7 +249,9 @@ class GuidancePath:
         cfg = self.cfg
         widths, col_start, k_head, K, e1_rule = KINDS[cfg.kind]
         images = batch["images"]
-        if "gathered" in st:
+        if "unpacked" in st:
+            ind_all, probs_all = st["unpacked"]
+        elif "gathered" in st:
             ind_all, probs_all = fdist.unpack_probs(st["gathered"], widths)
         else:
             ind_all, probs_all = st["ind"], st["probs"]
@@ -318,7 +324,7 @@ class GuidancePath:
         P = probe if probe is not None else _NullProbe
         st = self.phase_a(batch, probe)
         P.begin("assign")
-        Q = P if "packed" in st else _NullProbe          # the parts of the assignment stage are of interest with several ranks only
+        Q = P if "multi" in st else _NullProbe           # the parts of the assignment stage are of interest with several ranks only
         Q.begin("exchange_rows")
         self.exchange_1(st)
         Q.end("exchange_rows")

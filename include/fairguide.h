@@ -328,6 +328,17 @@ int fg_peer_wait_copy(const void* peer_base_dev, int rank, int world, size_t fla
                       size_t parity_stride, const uint32_t* epoch_dev, void* dst, size_t bytes, int32_t* status, void* stream);
 int fg_peer_wait_sum(const void* peer_base_dev, int rank, int world, size_t flags_off, int flag_index, size_t region_off,
                      size_t parity_stride, const uint32_t* epoch_dev, int32_t* out, size_t n_elems, int32_t* status, void* stream);
+/* Exchange 1 fused with its packing / unpacking (what dist.PeerExchange uses): the row block {indicator, probs_0 .. probs_2}
+ * [n, 1 + sum(widths)] of `dtype` is assembled in shared memory from the head's outputs (indicators uint8 [n], probs[a]
+ * [n, widths[a]]; HOST arrays of device pointers / widths) and stored into slot_off of every peer's row region, flag 0 raised;
+ * fg_peer_wait_unpack waits for the `world` flags and takes the gathered [n_all, 1 + sum(widths)] block of this rank's region
+ * apart into indicators_all uint8 [n_all] and probs_all[a] [n_all, widths[a]].  n a multiple of 8. */
+int fg_peer_push_rows(const uint8_t* indicators, const void* const* probs, const int32_t* widths, int n_attr, int n,
+                      const void* peer_base_dev, size_t region_off, size_t parity_stride, size_t slot_off, size_t flags_off,
+                      int rank, int world, const uint32_t* epoch_dev, uint32_t* done_counter, int dtype, void* stream);
+int fg_peer_wait_unpack(const void* peer_base_dev, int rank, int world, size_t flags_off, size_t region_off, size_t parity_stride,
+                        const uint32_t* epoch_dev, uint8_t* indicators_all, void* const* probs_all, const int32_t* widths,
+                        int n_attr, int n_all, int32_t* status, int dtype, void* stream);
 
 #ifdef __cplusplus
 }
