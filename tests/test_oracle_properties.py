@@ -90,3 +90,83 @@ def test_hook_region_is_the_intersection_of_both_boxes_and_the_image(seed, quirk
     if right > left and top > bottom:
         want[bottom:top, left:right] = True
     assert torch.equal(g == 0.25, want)
+
+
+def test_resize_512_to_224_tap_pattern_is_static():
+    """The 512 -> 224 resize is the fixed ratio 16 : 7.  With ATen's fp32 index formula (area_pixel_compute_source_index,
+    align_corners=False) resized index o touches image indices i0(o) = floor((32 o + 9) / 14) and i0(o) + 1; inverted: image
+    index p is a tap of exactly ONE resized index, o = 7 (p >> 4) + ((7 (p & 15) + 3) >> 4), and p & 15 in {4, 11} is a tap of
+    none.  The backward kernels (fg_image_grad_quad.cuh, small_tab_512_224 in fg_image_grad_staged.cuh) build their tap tables
+    from this pattern instead of searching; the weights still come from the formula."""
+    f = np.float32
+    ss = f(512) / f(224)
+
+    def taps(o):
+        src = f(f(ss * f(f(o) + f(0.5))) - f(0.5))
+        src = max(src, f(0))
+        i0 = min(int(src), 511)
+        return i0, i0 + (1 if i0 < 511 else 0)
+
+    owner = {}
+    for o in range(224):
+        i0, i1 = taps(o)
+        assert i0 == (32 * o + 9) // 14 and i1 == i0 + 1
+        for p in (i0, i1):
+            assert p not in owner                      # no image index receives two resized indices (shrink by more than 2x)
+            owner[p] = o
+    for p in range(512):
+        q = p & 15
+        if q in (4, 11):
+            assert p not in owner
+        else:
+            assert owner[p] == 7 * (p >> 4) + ((7 * q + 3) >> 4)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 10 ** 6))
+def test_trust_region_rule_of_the_price_search(seed):
+    """The rule by which ot_solve_kernel's price search (fg_assign.cu, price_search_hybrid) stops sweeping a row: with pivot
+    prices p0 and per-class radii R, let z = cost - (p0 + R) and s = argmin z; the row is FROZEN when
+    z_s + 2 R_s < min_{l != s} z_l.  A frozen row takes class s under EVERY price vector of the box |p - p0| <= R, so counting
+    it once is exact.  (Integer keys like the kernel's, so that comparisons are exact.)"""
+    rng = np.random.default_rng(seed)
+    n, k = 400, 16
+    cost = rng.integers(0, 1 << 22, size=(n, k)).astype(np.int64) * 16 + np.arange(k)      # class index in the low bits: no ties
+    p0 = rng.integers(-(1 << 18), 1 << 18, size=k).astype(np.int64) * 16
+    R = rng.integers(1, 1 << 17, size=k).astype(np.int64) * 16
+    z = cost - (p0 + R)
+    s = z.argmin(1)
+    zs = np.sort(z, axis=1)
+    frozen = zs[:, 0] + 2 * R[s] + 16 < zs[:, 1]
+    assert frozen.any() and (~frozen).any()
+    for _ in range(20):
+        corner = rng.random() < 0.5
+        d = np.where(rng.random(k) < 0.5, -R, R) if corner else (rng.integers(-(1 << 17), 1 << 17, size=k) * 16).clip(-R, R)
+        assign = (cost - (p0 + d)).argmin(1)
+        assert (assign[frozen] == s[frozen]).all()
+
+
+@settings(max_examples=15, deadline=None)
+@given(st.integers(1, 10 ** 6), st.sampled_from([1.0, 3.0]))
+def test_tf32_candidate_rule_of_the_tensor_core_search_keeps_the_exact_argmax(seed, scale):
+    """fg_face_search_top1_tc scores every database row once with TF32 products (both operands truncated to 10 mantissa bits)
+    and re-scores exactly the rows whose approximate score is within 2 eps of the query's best, eps = 2.2e-3 |q| max|row|.
+    The exact arg-max -- and any row tied with it -- must always be among them."""
+    rng = np.random.default_rng(seed)
+    D, d, m = 3000, 256, 8
+    db = rng.standard_normal((D, d)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    db *= scale
+    db[7] = db[1500]                                            # an exact tie
+    q = rng.standard_normal((m, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[0] = db[1500] / scale                                     # the tied rows are this query's best
+    trunc = lambda x: (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    approx = trunc(q.copy()) @ trunc(db.copy()).T
+    exact = q.astype(np.float64) @ db.astype(np.float64).T
+    eps = 2.2e-3 * np.linalg.norm(q, axis=1) * np.linalg.norm(db, axis=1).max()
+    keep = approx >= approx.max(1, keepdims=True) - 2 * eps[:, None]
+    best = exact.max(1, keepdims=True)
+    assert (keep | (exact < best - 1e-12)).all()                # every exact maximiser is kept
+    assert keep[0, 7] and keep[0, 1500]
+    assert keep.sum(1).max() < 200                              # and the list stays short
