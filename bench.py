@@ -279,8 +279,10 @@ def main():
                 "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{a.workload}: {desc}", "kind": kind, "global_batch": n_workload, "images_per_step": r["images_per_step"],
                            "same_config": r["same_config"],
-                           "note": "CPU arm: the whole workload on the host cores in fp32 (the GPU arm computes C5 in bf16); requested "
-                                   f"--steps {a.steps} --warmup {a.warmup} are clamped to what the time budget holds"},
+                           "note": ("CPU arm: " + ("the whole workload" if r["same_config"] else f"{r['images_per_step']} of the workload's {n_workload} images")
+                                    + " on the host cores in fp32 (the GPU arm computes C5 in bf16); the literal per-image loops are super-linear in "
+                                    f"the batch, so requested --steps {a.steps} --warmup {a.warmup} are clamped to ONE step sized for the "
+                                    f"{a.ref_budget_s:.0f} s budget" + (": " + r["cap"] if r.get("cap") else ""))},
                 "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
