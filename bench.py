@@ -239,6 +239,28 @@ def cpu_reference_run(kind, n_workload, steps, budget_s, solver="lsa", sample=No
 
 
 # ----------------------------------------------------------------------------------------------- main
+_JSON_FD = None
+
+
+def own_stdout():
+    """Rank 0 prints ONE JSON line: everything else that writes to file descriptor 1 during the run (NCCL's version banner,
+    library chatter from C code that Python's sys.stdout redirection cannot see) is sent to stderr, and the line goes to the
+    saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,11 +307,12 @@ def main():
                                     f"{a.ref_budget_s:.0f} s budget" + (": " + r["cap"] if r.get("cap") else ""))},
                 "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
+    own_stdout()                                   # NCCL still prints its version banner to fd 1 at WARN: keep stdout for the ONE JSON line
     import torch
     import torch.distributed as dist
     import fairguide
@@ -376,8 +399,8 @@ def main():
             stage_ms["assign_parts"] = {k: probe.mean_ms(k) for k in ("exchange_rows", "plan_counts", "exchange_counts")}
         if a.profile_only:
             if rank == 0:
-                print(json.dumps({"profile_only": True, "workload": a.workload, "ms_per_step_eager": ms_eager, "stage_ms": stage_ms,
-                                  "gpu_launches_per_step": launches_per_step}))
+                emit({"profile_only": True, "workload": a.workload, "ms_per_step_eager": ms_eager, "stage_ms": stage_ms,
+                      "gpu_launches_per_step": launches_per_step})
             if world > 1:
                 dist.destroy_process_group()
             sys.exit(0)
@@ -594,7 +617,7 @@ def main():
         line["strong_scaling" if other_scaling["scaling"] == "strong" else "weak_scaling"] = other_scaling
     if with_backbone:
         line["with_backbone"] = with_backbone
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
